@@ -1,0 +1,140 @@
+"""Pin the CPU oracle (oracle/mmgl_oracle.py) against golden vectors produced by the
+REAL reference modules (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle import mmgl_oracle as O
+
+TOL = dict(rtol=1e-5, atol=2e-6)  # fp32 vs fp32, different op order only
+
+
+@pytest.mark.parametrize("name", ["xattn_layer_preln", "xattn_layer_postln"])
+def test_cross_layer_forward_backward(golden, name):
+    g = golden(name)
+    p = {k: v.clone().requires_grad_(True) for k, v in g["state"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    bank = g["bank"].clone().requires_grad_(True)
+    add = O.expand_mask(g["mask"], x.dtype, x.shape[1])
+    y = O.mpt_decoder_layer(x, p, g["cfg"]["num_heads"], cross_attention=True, bank=bank, bank_add_mask=add,
+                            do_layer_norm_before=g["cfg"]["do_layer_norm_before"])
+    torch.testing.assert_close(y, g["y"], **TOL)
+    (y * g["w"]).sum().backward()
+    torch.testing.assert_close(x.grad, g["dx"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bank.grad, g["dbank"], rtol=1e-4, atol=1e-5)
+    for k, gr in g["grads"].items():
+        torch.testing.assert_close(p[k].grad, gr, rtol=1e-4, atol=1e-5, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_xattn_core_matches_attention(golden):
+    """xattn_core (the kernel's slice) reproduces the attention inside the layer."""
+    g = golden("xattn_layer_preln")
+    p, nh = g["state"], g["cfg"]["num_heads"]
+    x = torch.nn.functional.layer_norm(g["x"], (64,), p["self_attn_layer_norm.weight"], p["self_attn_layer_norm.bias"])
+    ref = O.mpt_attention(x, g["bank"], O.expand_mask(g["mask"], x.dtype, x.shape[1]), p, nh)
+    q = torch.nn.functional.linear(x, p["self_attn.q_proj.weight"], p["self_attn.q_proj.bias"]) * (16 ** -0.5)
+    k = torch.nn.functional.linear(g["bank"], p["self_attn.k_proj.weight"], p["self_attn.k_proj.bias"])
+    v = torch.nn.functional.linear(g["bank"], p["self_attn.v_proj.weight"], p["self_attn.v_proj.bias"])
+    o, lse = O.xattn_core(q, k, v, g["mask"], nh)
+    out = torch.nn.functional.linear(o, p["self_attn.out_proj.weight"], p["self_attn.out_proj.bias"])
+    torch.testing.assert_close(out, ref, **TOL)
+    assert lse.shape == (2, nh, 24)
+
+
+def test_mpt_causal_lm(golden):
+    g = golden("mpt_lm")
+    loss, logits = O.mpt_causal_lm(g["state"], g["cfg"], g["input_ids"], g["attention_mask"], g["input_ids"],
+                                   g["bank"], g["bank_mask"])
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
+    # invariant I1: gates == 0 -> bank has no influence
+    st = {k: (torch.zeros_like(v) if "gating" in k else v) for k, v in g["state"].items()}
+    loss0, logits0 = O.mpt_causal_lm(st, g["cfg"], g["input_ids"], g["attention_mask"], g["input_ids"],
+                                     g["bank"], g["bank_mask"])
+    torch.testing.assert_close(logits0, g["logits_gates0"], rtol=1e-4, atol=1e-5)
+    _, logits_nb = O.mpt_causal_lm(st, g["cfg"], g["input_ids"], g["attention_mask"], None, None, None)
+    torch.testing.assert_close(logits_nb, logits0, rtol=0, atol=0)
+    # I3: with live gates the output differs
+    assert (logits - logits0).abs().max() > 1e-3
+
+
+def test_masked_neighbors_have_zero_influence(golden):
+    """Invariant I2: bank rows whose mask is False never change the logits."""
+    g = golden("mpt_lm")
+    bank2 = g["bank"].clone()
+    bank2[~g["bank_mask"]] = 123.0
+    _, a = O.mpt_causal_lm(g["state"], g["cfg"], g["input_ids"], g["attention_mask"], None, g["bank"], g["bank_mask"])
+    _, b = O.mpt_causal_lm(g["state"], g["cfg"], g["input_ids"], g["attention_mask"], None, bank2, g["bank_mask"])
+    assert torch.equal(a, b)
+
+
+def test_cross_wrapper(golden):
+    g = golden("wrapper_cross")
+    b = g["batch"]
+    p = g["state"]
+    n_tok = g["cfg"]["n_tokens"]
+    te = O.neighbor_projection(g["text_pooled"], p["text_embeddings.weight"], p["text_embeddings.bias"],
+                               p["text_position_embeddings.weight"], b["neighbor_pos_ids"], n_tok)
+    ve = O.neighbor_projection(g["visual_pooled"], p["visual_embeddings.weight"], p["visual_embeddings.bias"],
+                               p["visual_position_embeddings.weight"], b["neighbor_images_pos_ids"], n_tok)
+    bank, mask = O.pack_bank(te, b["neighbor_pos_ids"], b["text_locations"], ve, b["neighbor_images_pos_ids"],
+                             b["image_locations"])
+    torch.testing.assert_close(bank, g["bank"], **TOL)
+    assert torch.equal(mask, g["bank_mask"])
+    loss, logits = O.cross_attention_model_from_pooled(p, g["cfg"], b, g["text_pooled"], g["visual_pooled"])
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("lm", ["t5", "opt"])
+@pytest.mark.parametrize("pt", ["none", "laplacian", "gnn"])
+def test_self_wrapper_concat(golden, lm, pt):
+    g = golden(f"wrapper_self_{lm}_{pt}")
+    b, p, n_tok = g["batch"], g["state"], g["cfg"]["n_tokens"]
+    has_pos = pt != "none"
+    te = O.neighbor_projection(g["text_pooled"], p["text_embeddings.weight"], p["text_embeddings.bias"],
+                               p.get("text_position_embeddings.weight") if has_pos else None, b["neighbor_pos_ids"], n_tok)
+    ve = O.neighbor_projection(g["visual_pooled"], p["visual_embeddings.weight"], p["visual_embeddings.bias"],
+                               p.get("visual_position_embeddings.weight") if has_pos else None,
+                               b["neighbor_images_pos_ids"], n_tok)
+    bank, mask = O.pack_bank(te, b["neighbor_pos_ids"], b["text_locations"], ve, b["neighbor_images_pos_ids"],
+                             b["image_locations"])
+    if pt == "laplacian":
+        bank = O.lpe_add(bank, b["lpe"], p["lpe_embeddings.weight"], p["lpe_embeddings.bias"], n_tok)
+    if pt == "gnn":
+        bank = O.gnn_add(bank, b["graph"], p["gnn.w1.weight"], p["gnn.w2.weight"], n_tok)
+    emb = torch.nn.functional.embedding(b["input_ids"], p["input_embeddings.weight"])
+    embs, am, labels = O.concat_neighbors(emb, b["attention_mask"], b["labels"], bank, mask, g["cfg"]["decoder_only"])
+    torch.testing.assert_close(embs, g["inputs_embeds"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(am.float(), g["attention_mask"].float(), rtol=0, atol=0)
+    assert torch.equal(labels, g["labels"])
+
+
+def test_gcn(golden):
+    g = golden("gcn")
+    x = g["x"].clone().requires_grad_(True)
+    w1 = g["state"]["w1.weight"].clone().requires_grad_(True)
+    w2 = g["state"]["w2.weight"].clone().requires_grad_(True)
+    y = O.gcn_forward(x, g["adj"], w1, w2)
+    torch.testing.assert_close(y, g["y"], **TOL)
+    (y * g["w"]).sum().backward()
+    torch.testing.assert_close(x.grad, g["dx"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(w1.grad, g["grads"]["w1.weight"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(w2.grad, g["grads"]["w2.weight"], rtol=1e-4, atol=1e-5)
+    # invariant I6: adj == 0 -> agg == 0
+    y0 = O.gcn_forward(g["x"], torch.zeros_like(g["adj"]), g["state"]["w1.weight"], g["state"]["w2.weight"])
+    xr = torch.cat((torch.zeros(3, 1, 48), g["x"]), 1)
+    h = torch.relu(torch.nn.functional.linear(torch.cat((xr, torch.zeros_like(xr)), -1), g["state"]["w1.weight"]))
+    exp = torch.nn.functional.linear(torch.cat((h, torch.zeros_like(h)), -1), g["state"]["w2.weight"])[:, 1:]
+    torch.testing.assert_close(y0, exp, **TOL)
+
+
+def test_lora_identity_at_init():
+    """Invariant I5: LoRA with B == 0 is the base linear (parity otherwise unpinned: peft absent)."""
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 32, generator=gen)
+    w = torch.randn(16, 32, generator=gen)
+    a, b = O.lora_init(8, 32, 16, gen)
+    assert torch.equal(O.lora_linear(x, w, None, a, b, 1.0, 8), torch.nn.functional.linear(x, w))
+    b = torch.randn(16, 8, generator=gen)
+    y = O.lora_linear(x, w, None, a, b, 2.0, 8)
+    torch.testing.assert_close(y, x @ (w + (2.0 / 8) * b @ a).T, rtol=1e-5, atol=1e-5)
