@@ -1,0 +1,167 @@
+/* mmgl_b200 -- C ABI of the B200 (sm_100a) kernels behind MMGL's neighbor-fusion training step.
+ *
+ * The reference (minjiyoon/MMGL) is pure Python: it has no FFI of its own.  Each entry point below
+ * replaces a run of PyTorch/HF library calls inside the reference modules; the call sites are cited
+ * as  model/<file>:<lines>  relative to the reference root.  The Python binding that a maintainer of
+ * the reference would add is a ctypes stub; mmgl_b200/_capi.py is that stub.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (PyTorch allocations); the library never
+ *     allocates, frees or retains device memory.  Activations/weights are bf16 unless noted, row-major.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); no implicit sync.
+ *   - Return 0 on success, non-zero on error; mmgl_last_error_string() describes the last error of the
+ *     calling thread.  Nothing throws or exits.
+ *   - Entry points are re-entrant (forward thread + autograd backward thread).
+ */
+#ifndef MMGL_B200_H
+#define MMGL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMGL_ABI_VERSION 1
+
+int mmgl_version(void);
+const char* mmgl_last_error_string(void);
+/* Number of kernels this library launched since load (all threads); bench.py reports it as gpu_launches. */
+int64_t mmgl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM with fused epilogue (TMA-fed, TMEM accumulators, persistent, warp-specialised).
+ *
+ *   acc[m,n] = sum_k A0[m,k]*B0[n,k]  (+ sum_k A1[m,k]*B1[n,k] when k1 > 0)       fp32 accumulate
+ *   v = alpha * (acc + bias[n])                  bias optional (fp32)
+ *   v = max(v, 0)                                if relu
+ *   v = relu_mask[m,n] > 0 ? v : 0               if relu_mask (bf16, ld = ldmask)      (ReLU backward)
+ *   aux[m,n] = v                                 if aux (bf16, ld = ldaux)             (pre-gate value)
+ *   v = tanh(*gate) * v                          if gate (device fp32 scalar)
+ *   v += residual[m,n]                           if residual (bf16, ld = ldres)
+ *   v += D[m,n]                                  if accumulate (D read in its own dtype)
+ *   D[m,n] = v                                   bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1), ld = ldd
+ *
+ * Operand storage: a_mn_major = 0 -> A is [M rows][K cols] (K contiguous, the nn.Linear activation);
+ *                  a_mn_major = 1 -> A is [K rows][M cols] (M contiguous; transposed use, e.g. wgrad).
+ *                  b_mn_major likewise for B ([N][K] = nn.Linear weight layout when 0; [K][N] when 1).
+ * Requirements: bf16 operands, 16-byte aligned base pointers, leading dimensions multiples of 8
+ * elements, K multiple of 8.  M, N arbitrary (tails are predicated).
+ *
+ * Replaces: nn.Linear / torch.bmm call sites  model/modelling_cross_attention.py:194,198-199,273,352,355
+ * (and their autograd backward), :997,:1020 (neighbor projections), model/graph.py:24,29,
+ * peft LoRA (model/modelling_self_attention.py:80-87) via the second operand pair.
+ */
+typedef struct mmgl_gemm_args {
+  const void* a0; const void* b0; int64_t k0; int64_t lda0; int64_t ldb0;
+  const void* a1; const void* b1; int64_t k1; int64_t lda1; int64_t ldb1;
+  int32_t a_mn_major; int32_t b_mn_major;
+  int64_t m; int64_t n;
+  void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
+  float alpha; int32_t relu;
+  const float* bias;
+  const float* gate;
+  const void* residual; int64_t ldres;
+  void* aux; int64_t ldaux;
+  const void* relu_mask; int64_t ldmask;
+  int32_t force_block_n; /* 0 = heuristic; 64/128/256 to force (tests, tuning) */
+  int32_t reserved;
+} mmgl_gemm_args;
+
+int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused cross-attention core:  O = softmax(max(Q K^T + mask, FLT_MIN_FINITE)) V   per (sample, head).
+ * Q [B,S,nh*d] already scaled by d^-1/2 (done in the q_proj epilogue); K,V [B,Nk,nh*d] (may be the two
+ * halves of one fused K|V projection: pass ldk = ldv = 2*nh*d); mask [B,Nk] bytes (1 = attend).
+ * Head split/merge, mask expansion, clamp, fp32 softmax and both contractions are fused; no [B,nh,S,Nk]
+ * tensor ever reaches HBM.  lse [B,nh,S] fp32 is saved for backward.  d in {64,128}; Nk <= 256.
+ * Replaces model/modelling_cross_attention.py:176-177,206-271 and :68-79 (_expand_mask).
+ */
+int mmgl_xattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                   const uint8_t* mask, void* o, int64_t ldo, float* lse,
+                   int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
+
+/* Backward of the above: dQ [B,S,nh*d], dK/dV [B,Nk,nh*d] (lddk = lddv = 2*nh*d for a fused d(K|V)). */
+int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                   const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, const uint8_t* mask,
+                   void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                   int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (bf16 in/out, fp32 gamma/beta and statistics).
+ * Replaces nn.LayerNorm at model/modelling_cross_attention.py:320,341,350,365.
+ * y may be bf16; mean/rstd [rows] fp32 saved for backward.
+ */
+int mmgl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int64_t rows, int64_t hidden, float eps, void* stream);
+/* dx = (d_res ? d_res : 0) + LN'(dy);  dgamma/dbeta fp32 [hidden] (accumulate != 0 -> +=).
+ * dgamma/dbeta may be NULL (frozen LayerNorm: only dx).  workspace >= mmgl_layernorm_bwd_workspace_bytes. */
+size_t mmgl_layernorm_bwd_workspace_bytes(int64_t rows, int64_t hidden);
+int mmgl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* d_res, void* dx, float* dgamma, float* dbeta, int32_t accumulate,
+                       void* workspace, size_t workspace_bytes, int64_t rows, int64_t hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Reductions used by the backward pass.
+ * colsum:   out[n] (+)= scale * tanh?(gate) * sum_m x[m,n]      (bias gradients; x bf16 [M,N] ld)
+ * gate_grad: out[0] (+)= (1 - tanh(*gate)^2) * sum_{m,n} dy[m,n]*a[m,n]   (d loss / d gating scalar,
+ *           model/modelling_cross_attention.py:335,359)
+ */
+size_t mmgl_reduce_workspace_bytes(int64_t m, int64_t n);
+int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, float scale, const float* gate,
+                float* out, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64_t lda, int64_t m, int64_t n,
+                   const float* gate, float* out, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neighbor-bank packing (ragged per-sample interleave of text/image neighbor embeddings).
+ *   bank[b, loc, :] = proj[b, j, :] + pos_table[pos_id[b,j], :]  (+ lpe[b, loc+1, :] . W_lpe^T + b_lpe)
+ *   mask[b, loc*n_tok + t] = pos_id[b,j] > 0
+ * with loc = locations[b,j]; text sources j in [0,T), image sources j in [0,I).  Row width = n_tok*H.
+ * pos tables / lpe arguments may be NULL.  Slots not named by any location stay zero / masked.
+ * Replaces model/modelling_cross_attention.py:999-1004,1022-1027,1080-1104 and
+ * model/modelling_self_attention.py:284-315.
+ */
+typedef struct mmgl_bank_args {
+  const void* text_proj;  const void* text_pos_table;  const int64_t* text_pos_ids;  const int64_t* text_locations;
+  const void* image_proj; const void* image_pos_table; const int64_t* image_pos_ids; const int64_t* image_locations;
+  int64_t batch; int64_t n_text; int64_t n_image; int64_t row_width; int64_t n_tok;
+  const float* lpe; int64_t lpe_k; const void* lpe_weight; const float* lpe_bias; /* lpe [B, T+I+1, k] fp32; W bf16 [row_width, k] */
+  void* bank; uint8_t* mask;
+} mmgl_bank_args;
+int mmgl_bank_pack_fwd(const mmgl_bank_args* args, void* stream);
+
+/* Backward: d_text_proj/d_image_proj (bf16, gathered rows), d_pos tables (fp32 [rows, row_width], +=),
+ * d_lpe_weight (fp32 [row_width,k], +=), d_lpe_bias (fp32, +=).  Any output may be NULL. */
+typedef struct mmgl_bank_bwd_args {
+  const void* d_bank;
+  const int64_t* text_pos_ids;  const int64_t* text_locations;
+  const int64_t* image_pos_ids; const int64_t* image_locations;
+  int64_t batch; int64_t n_text; int64_t n_image; int64_t row_width;
+  void* d_text_proj; void* d_image_proj;
+  float* d_text_pos_table; int64_t text_pos_rows;
+  float* d_image_pos_table; int64_t image_pos_rows;
+  const float* lpe; int64_t lpe_k; float* d_lpe_weight; float* d_lpe_bias;
+} mmgl_bank_bwd_args;
+int mmgl_bank_pack_bwd(const mmgl_bank_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GCN helpers (model/graph.py:17-31).  Nodes = 1 null root + N neighbors, adj [B,N+1,N+1] fp32.
+ * concat_fwd:  out[b,i,:] = [ xr[b,i,:] , sum_j adj[b,i,j] * xr[b,j,:] ]   ([B*(N+1), 2*D] bf16)
+ *              where xr = x with a zero root row prepended when prepend_root != 0 (x is then [B,N,D]),
+ *              else xr = x ([B,N+1,D]).
+ * combine_bwd: dx[b,j,:] = dc[b,j,:D] + sum_i adj[b,i,j] * dc[b,i,D:]   then optionally * (relu_mask>0);
+ *              drop_root != 0 writes rows 1..N only (dx is [B,N,D]).
+ */
+int mmgl_gcn_concat_fwd(const void* x, const float* adj, void* out, int64_t batch, int64_t nodes, int64_t dim,
+                        int32_t prepend_root, void* stream);
+int mmgl_gcn_combine_bwd(const void* dc, const float* adj, const void* relu_mask, void* dx, int64_t batch,
+                         int64_t nodes, int64_t dim, int32_t drop_root, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMGL_B200_H */

@@ -1,0 +1,61 @@
+"""Build libmmgl_b200.so (sm_100a) in-tree with nvcc.  Usage: python -m mmgl_b200.build [--force]"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libmmgl_b200.so")
+SOURCES = ["capi.cu", "gemm_sm100.cu", "xattn.cu", "rowops.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            with open(os.path.join(root, name), "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIB_DIR, exist_ok=True)
+    stamp = os.path.join(LIB_DIR, "build.sha256")
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return LIB
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

@@ -1,0 +1,455 @@
+// tcgen05 GEMM with fused epilogue for sm_100a.
+//
+//   D = epilogue( A0 * B0^T (+ A1 * B1^T) )        bf16 x bf16 -> fp32 (TMEM) -> bf16/fp32
+//
+// Design (B200-first, not a port: the reference runs these contractions through nn.Linear/cuBLAS):
+//   * persistent CTAs (one per SM), static round-robin tile scheduler, tile = 128 x BN (BN in 64/128/256)
+//   * warp 0  : TMA producer  (cp.async.bulk.tensor, 128B swizzle, multi-stage mbarrier ring)
+//   * warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accum in TMEM)
+//   * warps 2-5: epilogue (tcgen05.ld -> registers -> fused bias/scale/ReLU/gate/residual -> global)
+//   * two accumulator stages in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+//   * both operands may be K-major or MN-major (UMMA descriptors do the transposition), so forward,
+//     dgrad and wgrad of nn.Linear run through the same kernel with no transposed copies in HBM
+//   * an optional second operand pair accumulates into the same TMEM tile (LoRA: x W^T + (x A^T) B^T;
+//     GCN: [X, adj X] W^T without materialising the concat)
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/mmgl_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmgl {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 192;      // 6 warps
+constexpr int kATileBytes = BM * BK * 2;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kBTileBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
+};
+
+struct GemmParams {
+  int64_t m, n;
+  int32_t kblocks0, kblocks1;
+  int32_t m_blocks, n_blocks;
+  void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
+  float alpha; int32_t relu;
+  const float* bias;
+  const float* gate;
+  const __nv_bfloat16* residual; int64_t ldres;
+  __nv_bfloat16* aux; int64_t ldaux;
+  const __nv_bfloat16* relu_mask; int64_t ldmask;
+  int32_t vec_ok;
+};
+
+// 8 consecutive output columns of one row: fused epilogue + store.
+__device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[8], int64_t row, int64_t col,
+                                                float gate_t) {
+  if (p.bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.relu_mask != nullptr) {
+    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + row * p.ldmask + col));
+    const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!(bf16lo(w[j]) > 0.f)) v[2 * j] = 0.f;
+      if (!(bf16hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
+    }
+  }
+  if (p.aux != nullptr) {
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p.aux + row * p.ldaux + col) = o;
+  }
+  if (p.gate != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= gate_t;
+  }
+  if (p.residual != nullptr) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldres + col));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[2 * j] += bf16lo(w[j]); v[2 * j + 1] += bf16hi(w[j]); }
+  }
+  if (p.out_fp32) {
+    float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col;
+    if (p.accumulate) {
+      const float4 a0 = *reinterpret_cast<const float4*>(dp);
+      const float4 a1 = *reinterpret_cast<const float4*>(dp + 4);
+      v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+      v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+    }
+    *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col;
+    if (p.accumulate) {
+      const uint4 a = *reinterpret_cast<const uint4*>(dp);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[2 * j] += bf16lo(w[j]); v[2 * j + 1] += bf16hi(w[j]); }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dp) = o;
+  }
+}
+
+// Scalar tail (N not a multiple of 8, or unaligned epilogue tensors).
+__device__ __forceinline__ void epilogue_store1(const GemmParams& p, float v, int64_t row, int64_t col, float gate_t) {
+  if (p.bias != nullptr) v += __ldg(p.bias + col);
+  v *= p.alpha;
+  if (p.relu) v = fmaxf(v, 0.f);
+  if (p.relu_mask != nullptr && !(__bfloat162float(p.relu_mask[row * p.ldmask + col]) > 0.f)) v = 0.f;
+  if (p.aux != nullptr) p.aux[row * p.ldaux + col] = __float2bfloat16_rn(v);
+  if (p.gate != nullptr) v *= gate_t;
+  if (p.residual != nullptr) v += __bfloat162float(p.residual[row * p.ldres + col]);
+  if (p.out_fp32) {
+    float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col;
+    if (p.accumulate) v += *dp;
+    *dp = v;
+  } else {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col;
+    if (p.accumulate) v += __bfloat162float(*dp);
+    *dp = __float2bfloat16_rn(v);
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                    const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_blocks * p.n_blocks;
+  const int kblocks = p.kblocks0 + p.kblocks1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b0);
+    if (p.kblocks1 > 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_b1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.m_blocks) * BM;
+        const int n0 = (tile / p.m_blocks) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const bool second = kb >= p.kblocks0;
+          const CUtensorMap* ma = second ? &map_a1 : &map_a0;
+          const CUtensorMap* mb = second ? &map_b1 : &map_b0;
+          const int k0 = (second ? kb - p.kblocks0 : kb) * BK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kATileBytes;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &full_bar[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sa, ma, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mb, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sb, mb, &full_bar[stage], k0, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);       // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.m_blocks) * BM;
+      const int n0 = (tile / p.m_blocks) * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int64_t row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t col0 = n0 + c * 32;
+        if (row < p.m && col0 < p.n) {
+          if (p.vec_ok && col0 + 32 <= p.n) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// --------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; uint64_t d0, d1, ld; uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.ld); mix(k.b0); mix(k.b1);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: dims (inner d0, outer d1), row pitch ld elements, box (b0 = 64 inner, b1 rows), 128B swizzle.
+// Descriptors only encode address + geometry, so caching by (ptr, geometry) is safe across reuse of the address.
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                       uint32_t b1) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, d0, d1, ld, b0, b1};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return 4; }
+  const cuuint64_t dims[2] = {d0, d1};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {b0, b1};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r, ptr,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+    return 4;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+// operand with `rows` along M or N and `k` along K
+static int operand_map(CUtensorMap* out, const void* ptr, int mn_major, int64_t rows, int64_t k, int64_t ld,
+                       int box_rows) {
+  if (mn_major) return make_tensor_map_2d(out, ptr, (uint64_t)rows, (uint64_t)k, (uint64_t)ld, 64, 64);
+  return make_tensor_map_2d(out, ptr, (uint64_t)k, (uint64_t)rows, (uint64_t)ld, 64, (uint32_t)box_rows);
+}
+
+static int pick_block_n(int64_t m, int64_t n, int sms) {
+  const int64_t mb = (m + BM - 1) / BM;
+  const int cand[3] = {256, 128, 64};
+  const double tile_cost[3] = {512.0, 290.0, 200.0};  // cycles per 64-deep k-block (MMA floor vs smem feed)
+  int best = 256; double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int64_t tiles = mb * ((n + cand[i] - 1) / cand[i]);
+    const int64_t waves = (tiles + sms - 1) / sms;
+    const double cost = waves * tile_cost[i];
+    if (cost < best_cost * 0.98) { best_cost = cost; best = cand[i]; }
+  }
+  return best;
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
+                       const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", GemmCfg<BN>::kSmemBytes, cudaGetErrorString(attr_err));
+    return 3;
+  }
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a0, b0, a1, b1, p);
+  return check_launch("mmgl_gemm_bf16");
+}
+
+template <int BN>
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
+                          const CUtensorMap& b1, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0>(a0, b0, a1, b1, p, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, 0, 1>(a0, b0, a1, b1, p, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, 1, 0>(a0, b0, a1, b1, p, s);
+  return launch_gemm<BN, 1, 1>(a0, b0, a1, b1, p, s);
+}
+
+}  // namespace mmgl
+
+using namespace mmgl;
+
+extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_REQUIRE(a != nullptr, "mmgl_gemm_bf16: null args");
+  MMGL_REQUIRE(a->m > 0 && a->n > 0 && a->k0 > 0 && a->k1 >= 0, "mmgl_gemm_bf16: bad sizes m=%lld n=%lld k0=%lld k1=%lld",
+               (long long)a->m, (long long)a->n, (long long)a->k0, (long long)a->k1);
+  MMGL_REQUIRE(a->a0 && a->b0 && a->d, "mmgl_gemm_bf16: null operand");
+  MMGL_REQUIRE(a->k0 % 8 == 0 && a->k1 % 8 == 0, "mmgl_gemm_bf16: K must be a multiple of 8 (k0=%lld k1=%lld)",
+               (long long)a->k0, (long long)a->k1);
+  MMGL_REQUIRE(a->lda0 % 8 == 0 && a->ldb0 % 8 == 0 && aligned16(a->a0) && aligned16(a->b0),
+               "mmgl_gemm_bf16: operands need 16-byte aligned base and leading dims %% 8 == 0");
+  if (a->k1 > 0)
+    MMGL_REQUIRE(a->a1 && a->b1 && a->lda1 % 8 == 0 && a->ldb1 % 8 == 0 && aligned16(a->a1) && aligned16(a->b1),
+                 "mmgl_gemm_bf16: second operand pair needs aligned pointers / leading dims");
+  MMGL_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31), "mmgl_gemm_bf16: m, n must fit in int32");
+
+  const int sms = sm_count();
+  int bn = a->force_block_n ? a->force_block_n : pick_block_n(a->m, a->n, sms);
+  MMGL_REQUIRE(bn == 64 || bn == 128 || bn == 256, "mmgl_gemm_bf16: force_block_n must be 64, 128 or 256");
+
+  GemmParams p;
+  p.m = a->m; p.n = a->n;
+  p.kblocks0 = (int32_t)((a->k0 + BK - 1) / BK);
+  p.kblocks1 = (int32_t)((a->k1 + BK - 1) / BK);
+  p.m_blocks = (int32_t)((a->m + BM - 1) / BM);
+  p.n_blocks = (int32_t)((a->n + bn - 1) / bn);
+  p.d = a->d; p.ldd = a->ldd; p.out_fp32 = a->out_fp32; p.accumulate = a->accumulate;
+  p.alpha = a->alpha; p.relu = a->relu; p.bias = a->bias; p.gate = a->gate;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ldres = a->ldres;
+  p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux); p.ldaux = a->ldaux;
+  p.relu_mask = reinterpret_cast<const __nv_bfloat16*>(a->relu_mask); p.ldmask = a->ldmask;
+  const int esz = a->out_fp32 ? 4 : 2;
+  bool vec = aligned16(a->d) && (a->ldd * esz) % 16 == 0;
+  if (a->bias) vec = vec && aligned16(a->bias);
+  if (a->residual) vec = vec && aligned16(a->residual) && a->ldres % 8 == 0;
+  if (a->aux) vec = vec && aligned16(a->aux) && a->ldaux % 8 == 0;
+  if (a->relu_mask) vec = vec && aligned16(a->relu_mask) && a->ldmask % 8 == 0;
+  p.vec_ok = vec ? 1 : 0;
+
+  CUtensorMap ma0, mb0, ma1, mb1;
+  int rc;
+  if ((rc = operand_map(&ma0, a->a0, a->a_mn_major, a->m, a->k0, a->lda0, BM))) return rc;
+  if ((rc = operand_map(&mb0, a->b0, a->b_mn_major, a->n, a->k0, a->ldb0, bn))) return rc;
+  if (a->k1 > 0) {
+    if ((rc = operand_map(&ma1, a->a1, a->a_mn_major, a->m, a->k1, a->lda1, BM))) return rc;
+    if ((rc = operand_map(&mb1, a->b1, a->b_mn_major, a->n, a->k1, a->ldb1, bn))) return rc;
+  } else {
+    ma1 = ma0; mb1 = mb0;
+  }
+  switch (bn) {
+    case 256: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
+    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
+    default:  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
+  }
+}

@@ -1,0 +1,656 @@
+"""Autograd bindings of the sm_100a kernels (libmmgl_b200.so, through the ctypes layer in _capi.py).
+
+Each ``torch.autograd.Function`` here replaces a run of PyTorch/HF library calls inside the reference modules
+(file:line citations are relative to the reference root).  Forward AND backward call the C ABI; trainable
+parameters receive ordinary ``.grad`` tensors, so ``DistributedDataParallel`` hooks fire exactly as in the
+reference's loop (language_modelling/run_generation.py:319, :485).
+
+Numerics: bf16 operands, fp32 accumulation / softmax / LayerNorm statistics.  Parameters may be stored in
+fp32 ("master" weights -- a bf16 shadow is cached per parameter version) or in bf16 (the reference's
+``model.bfloat16()`` mode, run_generation.py:306-307); gradients are returned in the parameter's dtype.
+
+There is no CPU or eager fallback: every function raises if the tensors are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+
+from . import _capi as K
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+# --------------------------------------------------------------------------------------------- helpers
+_shadow = weakref.WeakKeyDictionary()
+
+
+def w16(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """bf16 view of a weight: the tensor itself if already bf16, else a shadow cached per ``_version``."""
+    if p is None:
+        return None
+    if p.dtype == BF16 and p.is_contiguous():
+        return p.detach()
+    ent = _shadow.get(p)
+    ver = p._version
+    if ent is None or ent[0] != ver or ent[1].device != p.device:
+        ent = (ver, p.detach().to(BF16).contiguous())
+        _shadow[p] = ent
+    return ent[1]
+
+
+def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 contiguous view of a small parameter (bias, LayerNorm affine, gate)."""
+    if p is None:
+        return None
+    if p.dtype == F32 and p.is_contiguous():
+        return p.detach()
+    ent = _shadow.get(p)
+    ver = p._version
+    if ent is None or ent[0] != ver or ent[1].device != p.device:
+        ent = (ver, p.detach().to(F32).contiguous())
+        _shadow[p] = ent
+    return ent[1]
+
+
+def _gate32(g: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if g is None else f32(g).reshape(1)
+
+
+def _as2d(t: torch.Tensor) -> torch.Tensor:
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.dtype != BF16:
+        t2 = t2.to(BF16)
+    return t2 if t2.is_contiguous() else t2.contiguous()
+
+
+def _new(rows, cols, like, dtype=BF16):
+    return torch.empty((rows, cols), dtype=dtype, device=like.device)
+
+
+def _wgrad(dy2, x2, param, *, gate=None, alpha=1.0):
+    """dW[N_out, K_in] = alpha * tanh?(gate) * dy^T x, in the parameter's dtype (fp32 master or bf16)."""
+    out = torch.empty(param.shape, dtype=param.dtype if param.dtype in (BF16, F32) else F32, device=dy2.device)
+    K.gemm(dy2, x2, out, a_t=True, b_t=True, gate=gate, alpha=alpha)
+    return out
+
+
+def _bgrad(dy2, param, *, gate=None, scale=1.0):
+    out = torch.empty(param.shape, dtype=F32, device=dy2.device)
+    K.colsum(dy2, out, scale=scale, gate=gate)
+    return out if param.dtype == F32 else out.to(param.dtype)
+
+
+def _ln_fwd(x2, gamma, beta, eps):
+    y = torch.empty_like(x2)
+    mean = torch.empty(x2.shape[0], dtype=F32, device=x2.device)
+    rstd = torch.empty_like(mean)
+    K.layernorm_fwd(x2, gamma, beta, y, mean, rstd, eps)
+    return y, mean, rstd
+
+
+def _ln_bwd(dy2, x2, gamma, mean, rstd, d_res, want_affine, gamma_param, beta_param):
+    dx = torch.empty_like(x2)
+    dg = db = None
+    if want_affine:
+        dg = torch.empty(x2.shape[1], dtype=F32, device=x2.device)
+        db = torch.empty_like(dg)
+    K.layernorm_bwd(dy2, x2, gamma, mean, rstd, d_res, dx, dg, db)
+    if want_affine:
+        if gamma_param.dtype != F32:
+            dg = dg.to(gamma_param.dtype)
+        if beta_param.dtype != F32:
+            db = db.to(beta_param.dtype)
+    return dx, dg, db
+
+
+def _scalar_grad(dy2, a2, gate32, param):
+    out = torch.empty(1, dtype=F32, device=dy2.device)
+    K.gate_grad(dy2, a2, gate32, out)
+    return out.reshape(param.shape).to(param.dtype)
+
+
+def mask_u8(mask: torch.Tensor) -> torch.Tensor:
+    """[B,Nk] bool / {0,1} mask, or the reference's additive [B,1,S,Nk] mask (0 = attend), -> uint8 [B,Nk]."""
+    if mask.dim() == 4:  # additive, model/modelling_cross_attention.py:68-79
+        mask = mask[:, 0, 0, :] == 0
+    if mask.dtype != torch.uint8:
+        mask = (mask != 0).to(torch.uint8)
+    return mask.contiguous()
+
+
+# --------------------------------------------------------------------------------------------- linear
+class LinearFn(torch.autograd.Function):
+    """y = alpha * (x W^T + b) (+ residual).  nn.Linear call sites: model/modelling_cross_attention.py:194,
+    198-199, 273, 826, 997, 1020; model/modelling_self_attention.py:170, 193, 313."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, alpha):
+        x2 = _as2d(x)
+        w = w16(weight)
+        y = _new(x2.shape[0], w.shape[0], x2)
+        r2 = _as2d(residual) if residual is not None else None
+        K.gemm(x2, w, y, bias=f32(bias), alpha=alpha, residual=r2)
+        ctx.save_for_backward(x2, weight, bias)
+        ctx.alpha = alpha
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, bias = ctx.saved_tensors
+        dy2 = _as2d(dy)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = _new(x2.shape[0], x2.shape[1], x2)
+            K.gemm(dy2, w16(weight), dx, b_t=True, alpha=ctx.alpha)
+            dx = dx.reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, x2, weight, alpha=ctx.alpha)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _bgrad(dy2, bias, scale=ctx.alpha)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres, None
+
+
+def linear(x, weight, bias=None, residual=None, alpha=1.0):
+    return LinearFn.apply(x, weight, bias, residual, alpha)
+
+
+class LoRALinearFn(torch.autograd.Function):
+    """y = x W^T + b + s * (x A^T) B^T with the rank-r update accumulated into the SAME TMEM tile as the base
+    product (second operand pair of mmgl_gemm_bf16), s = lora_alpha / r folded into the stored intermediate.
+
+    LoRA as configured at model/modelling_self_attention.py:80-87 (peft; arithmetic restated, parity unpinned)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_a, lora_b, scale):
+        x2 = _as2d(x)
+        w, a, b = w16(weight), w16(lora_a), w16(lora_b)
+        r = a.shape[0]
+        t = _new(x2.shape[0], r, x2)
+        K.gemm(x2, a, t, alpha=scale)                       # t = s * x A^T            [M, r]
+        y = _new(x2.shape[0], w.shape[0], x2)
+        K.gemm(x2, w, y, a1=t, b1=b, bias=f32(bias))        # y = x W^T + t B^T + b
+        ctx.save_for_backward(x2, t, weight, bias, lora_a, lora_b)
+        ctx.scale = scale
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, t, weight, bias, lora_a, lora_b = ctx.saved_tensors
+        dy2 = _as2d(dy)
+        s = ctx.scale
+        a, b = w16(lora_a), w16(lora_b)
+        dt = _new(x2.shape[0], a.shape[0], x2)
+        K.gemm(dy2, b, dt, b_t=True, alpha=s)               # dt = s * dy B             [M, r]
+        dx = dw = dbias = da = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _new(x2.shape[0], x2.shape[1], x2)
+            K.gemm(dy2, w16(weight), dx, b_t=True, a1=dt, b1=a)   # dx = dy W + dt A
+            dx = dx.reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, x2, weight)
+        if bias is not None and ctx.needs_input_grad[2]:
+            dbias = _bgrad(dy2, bias)
+        if ctx.needs_input_grad[3]:
+            da = _wgrad(dt, x2, lora_a)                     # dA = dt^T x               [r, K]
+        if ctx.needs_input_grad[4]:
+            db = _wgrad(dy2, t, lora_b)                     # dB = dy^T (s x A^T)       [N, r]
+        return dx, dw, dbias, da, db, None
+
+
+def lora_linear(x, weight, bias, lora_a, lora_b, scale):
+    return LoRALinearFn.apply(x, weight, bias, lora_a, lora_b, scale)
+
+
+# --------------------------------------------------------------------------------------------- layernorm
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim: model/modelling_cross_attention.py:320, 341, 350, 365, 635-636."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x2 = _as2d(x)
+        g = f32(weight)
+        y, mean, rstd = _ln_fwd(x2, g, f32(bias), eps)
+        ctx.save_for_backward(x2, weight, bias, mean, rstd)
+        ctx.x_shape = x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, bias, mean, rstd = ctx.saved_tensors
+        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx, dg, db = _ln_bwd(_as2d(dy), x2, f32(weight), mean, rstd, None, want, weight, bias)
+        return dx.reshape(ctx.x_shape), dg, db, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+# --------------------------------------------------------------------------------------------- MLP
+class MLPFn(torch.autograd.Function):
+    """y = residual + fc2(relu(fc1(x))): model/modelling_cross_attention.py:352-361 (non-gated form).
+    ReLU and its backward mask live in the GEMM epilogues; no [M,F] elementwise pass touches HBM."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        x2 = _as2d(x)
+        f = _new(x2.shape[0], w1.shape[0], x2)
+        K.gemm(x2, w16(w1), f, bias=f32(b1), relu=True)
+        y = _new(x2.shape[0], w2.shape[0], x2)
+        r2 = _as2d(residual) if residual is not None else None
+        K.gemm(f, w16(w2), y, bias=f32(b2), residual=r2)
+        ctx.save_for_backward(x2, f, w1, b1, w2, b2)
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, f, w1, b1, w2, b2 = ctx.saved_tensors
+        dy2 = _as2d(dy)
+        df = torch.empty_like(f)
+        K.gemm(dy2, w16(w2), df, b_t=True, relu_mask=f)
+        dx = dw1 = db1 = dw2 = db2 = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            K.gemm(df, w16(w1), dx, b_t=True)
+            dx = dx.reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw1 = _wgrad(df, x2, w1)
+        if b1 is not None and ctx.needs_input_grad[2]:
+            db1 = _bgrad(df, b1)
+        if ctx.needs_input_grad[3]:
+            dw2 = _wgrad(dy2, f, w2)
+        if b2 is not None and ctx.needs_input_grad[4]:
+            db2 = _bgrad(dy2, b2)
+        if ctx.has_res and ctx.needs_input_grad[5]:
+            dres = dy
+        return dx, dw1, db1, dw2, db2, dres
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return MLPFn.apply(x, w1, b1, w2, b2, residual)
+
+
+# --------------------------------------------------------------------------------------------- attention core
+class XAttnCoreFn(torch.autograd.Function):
+    """O = softmax(max(Q K^T + mask, finfo.min)) V per (sample, head); Q pre-scaled.
+    model/modelling_cross_attention.py:176-177, 206-271 (+ :68-79)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, heads):
+        b, s, h = q.shape
+        nk = k.shape[1]
+        q2, k2, v2 = _as2d(q), _as2d(k), _as2d(v)
+        o = torch.empty_like(q2)
+        stats = torch.empty((b, heads, s, 2), dtype=F32, device=q.device)
+        m8 = mask_u8(mask)
+        K.xattn_fwd(q2, k2, v2, m8, o, stats, b, s, nk, heads, h // heads)
+        ctx.save_for_backward(q2, k2, v2, o, stats, m8)
+        ctx.dims = (b, s, nk, heads, h)
+        return o.reshape(b, s, h)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q2, k2, v2, o, stats, m8 = ctx.saved_tensors
+        b, s, nk, heads, h = ctx.dims
+        dq, dk, dv = torch.empty_like(q2), torch.empty_like(k2), torch.empty_like(v2)
+        K.xattn_bwd(_as2d(d_o), q2, k2, v2, o, stats, m8, dq, dk, dv, b, s, nk, heads, h // heads)
+        return dq.reshape(b, s, h), dk.reshape(b, nk, h), dv.reshape(b, nk, h), None, None
+
+
+def xattn_core(q, k, v, mask, heads):
+    return XAttnCoreFn.apply(q, k, v, mask, heads)
+
+
+# --------------------------------------------------------------------------------------------- gated cross layer
+class GatedCrossLayerFn(torch.autograd.Function):
+    """One whole gated cross-attention block, forward and backward, as a fixed schedule of fused kernels.
+
+    model/modelling_cross_attention.py:304-375 (MPTDecoderLayer, cross_attention=True) with MPTAttention :179-275:
+
+        pre-LN :  h1 = x  + tanh(g1) * Attn(LN1(x), bank);   y = h1 + tanh(g2) * fc2(relu(fc1(LN2(h1))))
+        post-LN:  h1 = LN1(x + tanh(g1) * Attn(x, bank));    y = LN2(h1 + tanh(g2) * fc2(relu(fc1(h1))))
+
+    g1 = g2 = None gives the plain residual form (peft_type != "flamingo").  Forward is 2 LayerNorms, 6 GEMMs
+    (bias, d^-1/2 scale, ReLU, tanh-gate and residual fused into their epilogues) and the attention core; the
+    pre-gate branch outputs are kept (aux epilogue output) for the scalar gate gradients.
+    """
+
+    @staticmethod
+    def forward(ctx, x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1,
+                ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln):
+        bsz, s, h = x.shape
+        nk = bank.shape[1]
+        d = h // heads
+        scaling = float(d) ** -0.5
+        x2, bank2 = _as2d(x), _as2d(bank)
+        m8 = mask_u8(mask)
+        m_rows = x2.shape[0]
+        g1f, g2f = _gate32(g1), _gate32(g2)
+        ln1g, ln2g = f32(ln1_w), f32(ln2_w)
+
+        if pre_ln:
+            a_in, mean1, rstd1 = _ln_fwd(x2, ln1g, f32(ln1_b), eps)
+        else:
+            a_in, mean1, rstd1 = x2, None, None
+        q = _new(m_rows, h, x2)
+        K.gemm(a_in, w16(wq), q, bias=f32(bq), alpha=scaling)                    # :194
+        kv = _new(bank2.shape[0], 2 * h, x2)
+        k, v = kv[:, :h], kv[:, h:]
+        K.gemm(bank2, w16(wk), k, bias=f32(bk))                                   # :198
+        K.gemm(bank2, w16(wv), v, bias=f32(bv))                                   # :199
+        o = _new(m_rows, h, x2)
+        stats = torch.empty((bsz, heads, s, 2), dtype=F32, device=x.device)
+        K.xattn_fwd(q, k, v, m8, o, stats, bsz, s, nk, heads, d)                  # :206-271
+        a_out = _new(m_rows, h, x2) if g1 is not None else None
+        u = _new(m_rows, h, x2)
+        K.gemm(o, w16(wo), u, bias=f32(bo), aux=a_out, gate=g1f, residual=x2)     # :273, :332-337
+        if pre_ln:
+            h1 = u
+            f_in, mean2, rstd2 = _ln_fwd(h1, ln2g, f32(ln2_b), eps)              # :350
+        else:
+            h1, mean1, rstd1 = _ln_fwd(u, ln1g, f32(ln1_b), eps)                 # :341
+            f_in, mean2, rstd2 = h1, None, None
+        f = _new(m_rows, w1.shape[0], x2)
+        K.gemm(f_in, w16(w1), f, bias=f32(b1), relu=True)                         # :352-353
+        c_out = _new(m_rows, h, x2) if g2 is not None else None
+        wsum = _new(m_rows, h, x2)
+        K.gemm(f, w16(w2), wsum, bias=f32(b2), aux=c_out, gate=g2f, residual=h1)  # :355-361
+        if pre_ln:
+            y = wsum
+        else:
+            y, mean2, rstd2 = _ln_fwd(wsum, ln2g, f32(ln2_b), eps)               # :365
+
+        ctx.pre_ln = pre_ln
+        ctx.dims = (bsz, s, nk, heads, h)
+        ctx.eps = eps
+        ctx.x_shape, ctx.bank_shape = x.shape, bank.shape
+        ctx.x_dtype, ctx.bank_dtype = x.dtype, bank.dtype
+        # activations: pre-LN keeps LN outputs a_in / f_in; post-LN keeps the LN inputs u / wsum
+        ctx.save_for_backward(x2, bank2, m8, a_in, mean1, rstd1, q, kv, o, stats, a_out, u, h1, f_in, mean2, rstd2,
+                              f, c_out, wsum,
+                              ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1, ln2_w, ln2_b, w1, b1, w2, b2, g2)
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, bank2, m8, a_in, mean1, rstd1, q, kv, o, stats, a_out, u, h1, f_in, mean2, rstd2, f, c_out, wsum,
+         ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1, ln2_w, ln2_b, w1, b1, w2, b2, g2) = ctx.saved_tensors
+        bsz, s, nk, heads, h = ctx.dims
+        d = h // heads
+        scaling = float(d) ** -0.5
+        pre_ln = ctx.pre_ln
+        need = ctx.needs_input_grad
+        g1f, g2f = _gate32(g1), _gate32(g2)
+        ln1g, ln2g = f32(ln1_w), f32(ln2_w)
+        dy2 = _as2d(dy)
+        k, v = kv[:, :h], kv[:, h:]
+        (i_x, i_bank, _i_mask, i_ln1w, i_ln1b, i_wq, i_bq, i_wk, i_bk, i_wv, i_bv, i_wo, i_bo, i_g1,
+         i_ln2w, i_ln2b, i_w1, i_b1, i_w2, i_b2, i_g2) = range(21)
+        grads = [None] * 24
+
+        # ---- FFN branch
+        if pre_ln:
+            dw_ = dy2                                                          # grad of wsum (= y)
+        else:
+            dw_, grads[i_ln2w], grads[i_ln2b] = _ln_bwd(dy2, wsum, ln2g, mean2, rstd2, None,
+                                                        need[i_ln2w] or need[i_ln2b], ln2_w, ln2_b)
+        if g2 is not None and need[i_g2]:
+            grads[i_g2] = _scalar_grad(dw_, c_out, g2f, g2)
+        df = torch.empty_like(f)
+        K.gemm(dw_, w16(w2), df, b_t=True, relu_mask=f, gate=g2f)             # d relu(fc1) (mask, then gate)
+        if need[i_w2]:
+            grads[i_w2] = _wgrad(dw_, f, w2, gate=g2f)
+        if b2 is not None and need[i_b2]:
+            grads[i_b2] = _bgrad(dw_, b2, gate=g2f)
+        if need[i_w1]:
+            grads[i_w1] = _wgrad(df, f_in, w1)
+        if b1 is not None and need[i_b1]:
+            grads[i_b1] = _bgrad(df, b1)
+        if pre_ln:
+            dln2 = torch.empty_like(h1)
+            K.gemm(df, w16(w1), dln2, b_t=True)
+            dh1, grads[i_ln2w], grads[i_ln2b] = _ln_bwd(dln2, h1, ln2g, mean2, rstd2, dw_,
+                                                        need[i_ln2w] or need[i_ln2b], ln2_w, ln2_b)
+            du = dh1                                                           # grad of u (= h1)
+        else:
+            dh1 = torch.empty_like(h1)
+            K.gemm(df, w16(w1), dh1, b_t=True, residual=dw_)
+            du, grads[i_ln1w], grads[i_ln1b] = _ln_bwd(dh1, u, ln1g, mean1, rstd1, None,
+                                                       need[i_ln1w] or need[i_ln1b], ln1_w, ln1_b)
+
+        # ---- attention branch
+        if g1 is not None and need[i_g1]:
+            grads[i_g1] = _scalar_grad(du, a_out, g1f, g1)
+        d_o = torch.empty_like(o)
+        K.gemm(du, w16(wo), d_o, b_t=True, gate=g1f)
+        if need[i_wo]:
+            grads[i_wo] = _wgrad(du, o, wo, gate=g1f)
+        if bo is not None and need[i_bo]:
+            grads[i_bo] = _bgrad(du, bo, gate=g1f)
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        dk, dv = dkv[:, :h], dkv[:, h:]
+        K.xattn_bwd(d_o, q, k, v, o, stats, m8, dq, dk, dv, bsz, s, nk, heads, d)
+        if need[i_wq]:
+            grads[i_wq] = _wgrad(dq, a_in, wq, alpha=scaling)
+        if bq is not None and need[i_bq]:
+            grads[i_bq] = _bgrad(dq, bq, scale=scaling)
+        if need[i_wk]:
+            grads[i_wk] = _wgrad(dk, bank2, wk)
+        if bk is not None and need[i_bk]:
+            grads[i_bk] = _bgrad(dk, bk)
+        if need[i_wv]:
+            grads[i_wv] = _wgrad(dv, bank2, wv)
+        if bv is not None and need[i_bv]:
+            grads[i_bv] = _bgrad(dv, bv)
+        if need[i_bank]:
+            dbank = torch.empty_like(bank2)
+            K.gemm(dk, w16(wk), dbank, b_t=True, a1=dv, b1=w16(wv))           # dK Wk + dV Wv in one TMEM tile
+            grads[i_bank] = dbank.reshape(ctx.bank_shape).to(ctx.bank_dtype)
+        if need[i_x]:
+            if pre_ln:
+                dln1 = torch.empty_like(x2)
+                K.gemm(dq, w16(wq), dln1, b_t=True, alpha=scaling)
+                dx, grads[i_ln1w], grads[i_ln1b] = _ln_bwd(dln1, x2, ln1g, mean1, rstd1, du,
+                                                           need[i_ln1w] or need[i_ln1b], ln1_w, ln1_b)
+            else:
+                dx = torch.empty_like(x2)
+                K.gemm(dq, w16(wq), dx, b_t=True, alpha=scaling, residual=du)
+            grads[i_x] = dx.reshape(ctx.x_shape).to(ctx.x_dtype)
+        elif pre_ln and (need[i_ln1w] or need[i_ln1b]):
+            dln1 = torch.empty_like(x2)
+            K.gemm(dq, w16(wq), dln1, b_t=True, alpha=scaling)
+            _, grads[i_ln1w], grads[i_ln1b] = _ln_bwd(dln1, x2, ln1g, mean1, rstd1, du, True, ln1_w, ln1_b)
+        return tuple(grads)
+
+
+def gated_cross_layer(x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1, ln2_w, ln2_b, w1, b1, w2, b2,
+                      g2, heads, eps=1e-5, pre_ln=True):
+    return GatedCrossLayerFn.apply(x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1,
+                                   ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln)
+
+
+# --------------------------------------------------------------------------------------------- neighbor bank
+class BankPackFn(torch.autograd.Function):
+    """Ragged interleave of projected text/image neighbor embeddings into the bank [B,(T+I)*n_tok,H] + byte mask,
+    with the position-embedding gather-add and the Laplacian-PE projection fused in.
+
+    model/modelling_cross_attention.py:999-1004, 1022-1027, 1080-1104; model/modelling_self_attention.py:284-315."""
+
+    @staticmethod
+    def forward(ctx, text_proj, text_pos_table, text_pos_ids, text_locations,
+                image_proj, image_pos_table, image_pos_ids, image_locations, lpe, lpe_weight, lpe_bias, n_tok):
+        ref = text_proj if text_proj is not None else image_proj
+        bsz = ref.shape[0]
+        n_text = text_proj.shape[1] if text_proj is not None else 0
+        n_image = image_proj.shape[1] if image_proj is not None else 0
+        row_width = ref.shape[-1]
+        n_src = n_text + n_image
+        dev = ref.device
+        a = K.BankArgs()
+        keep = []
+
+        def c16(t):
+            if t is None:
+                return None
+            t = t.to(BF16) if t.dtype != BF16 else t
+            t = t.contiguous()
+            keep.append(t)
+            return t
+
+        def ci64(t):
+            if t is None:
+                return None
+            t = t.to(torch.int64).contiguous()
+            keep.append(t)
+            return t
+
+        tp, ip = c16(text_proj), c16(image_proj)
+        tt, it = w16(text_pos_table), w16(image_pos_table)
+        tpos, tloc, ipos, iloc = ci64(text_pos_ids), ci64(text_locations), ci64(image_pos_ids), ci64(image_locations)
+        if tloc is None and n_text:  # text_only context: identity placement (modelling_cross_attention.py:1072-1078)
+            tloc = torch.arange(n_text, device=dev, dtype=torch.int64).repeat(bsz, 1).contiguous()
+        a.text_proj, a.text_pos_table, a.text_pos_ids, a.text_locations = K._p(tp), K._p(tt), K._p(tpos), K._p(tloc)
+        a.image_proj, a.image_pos_table, a.image_pos_ids, a.image_locations = K._p(ip), K._p(it), K._p(ipos), K._p(iloc)
+        a.batch, a.n_text, a.n_image, a.row_width, a.n_tok = bsz, n_text, n_image, row_width, n_tok
+        lpe32 = lw = lb = None
+        if lpe is not None:
+            lpe32 = lpe.to(F32).contiguous()
+            lw, lb = w16(lpe_weight), f32(lpe_bias)
+            a.lpe, a.lpe_k, a.lpe_weight, a.lpe_bias = K._p(lpe32), lpe32.shape[-1], K._p(lw), K._p(lb)
+        bank = torch.empty((bsz, n_src, row_width), dtype=BF16, device=dev)
+        mask = torch.empty((bsz, n_src * n_tok), dtype=torch.uint8, device=dev)
+        a.bank, a.mask = K._p(bank), K._p(mask)
+        K._req_cuda(bank, tp, ip)
+        K.bank_pack_fwd(a)
+        ctx.save_for_backward(tpos, tloc, ipos, iloc, lpe32, text_pos_table, image_pos_table, lpe_weight, lpe_bias)
+        ctx.dims = (bsz, n_text, n_image, row_width, n_tok)
+        ctx.dtypes = (text_proj.dtype if text_proj is not None else None,
+                      image_proj.dtype if image_proj is not None else None)
+        ctx.mark_non_differentiable(mask)
+        h = row_width // n_tok
+        return bank.reshape(bsz, n_src * n_tok, h), mask
+
+    @staticmethod
+    def backward(ctx, d_bank, _d_mask):
+        tpos, tloc, ipos, iloc, lpe32, t_table, i_table, lpe_w, lpe_b = ctx.saved_tensors
+        bsz, n_text, n_image, row_width, n_tok = ctx.dims
+        dev = d_bank.device
+        db = d_bank.reshape(bsz, n_text + n_image, row_width)
+        db = (db if db.dtype == BF16 else db.to(BF16)).contiguous()
+        a = K.BankBwdArgs()
+        a.d_bank = K._p(db)
+        a.text_pos_ids, a.text_locations, a.image_pos_ids, a.image_locations = K._p(tpos), K._p(tloc), K._p(ipos), K._p(iloc)
+        a.batch, a.n_text, a.n_image, a.row_width = bsz, n_text, n_image, row_width
+        need = ctx.needs_input_grad
+        d_tp = d_ip = d_tt = d_it = d_lw = d_lb = None
+        if n_text and need[0]:
+            d_tp = torch.empty((bsz, n_text, row_width), dtype=BF16, device=dev)
+            a.d_text_proj = K._p(d_tp)
+        if n_image and need[4]:
+            d_ip = torch.empty((bsz, n_image, row_width), dtype=BF16, device=dev)
+            a.d_image_proj = K._p(d_ip)
+        if t_table is not None and need[1]:
+            d_tt = torch.zeros(t_table.shape, dtype=F32, device=dev)
+            a.d_text_pos_table, a.text_pos_rows = K._p(d_tt), t_table.shape[0]
+        if i_table is not None and need[5]:
+            d_it = torch.zeros(i_table.shape, dtype=F32, device=dev)
+            a.d_image_pos_table, a.image_pos_rows = K._p(d_it), i_table.shape[0]
+        if lpe32 is not None:
+            a.lpe, a.lpe_k = K._p(lpe32), lpe32.shape[-1]
+            if need[9]:
+                d_lw = torch.zeros(lpe_w.shape, dtype=F32, device=dev)
+                a.d_lpe_weight = K._p(d_lw)
+            if lpe_b is not None and need[10]:
+                d_lb = torch.zeros(lpe_b.shape, dtype=F32, device=dev)
+                a.d_lpe_bias = K._p(d_lb)
+        K.bank_pack_bwd(a)
+        t_dt, i_dt = ctx.dtypes
+        if d_tp is not None and t_dt != BF16:
+            d_tp = d_tp.to(t_dt)
+        if d_ip is not None and i_dt != BF16:
+            d_ip = d_ip.to(i_dt)
+
+        def cast(g, p):
+            return None if g is None else (g if p.dtype == F32 else g.to(p.dtype))
+        return (d_tp, cast(d_tt, t_table) if d_tt is not None else None, None, None,
+                d_ip, cast(d_it, i_table) if d_it is not None else None, None, None,
+                None, cast(d_lw, lpe_w) if d_lw is not None else None,
+                cast(d_lb, lpe_b) if d_lb is not None else None, None)
+
+
+def bank_pack(text_proj, text_pos_table, text_pos_ids, text_locations,
+              image_proj=None, image_pos_table=None, image_pos_ids=None, image_locations=None,
+              lpe=None, lpe_weight=None, lpe_bias=None, n_tok=1):
+    """text_proj [B,T,n_tok*H], image_proj [B,I,n_tok*H] -> bank [B,(T+I)*n_tok,H] bf16, mask uint8 [B,(T+I)*n_tok]."""
+    return BankPackFn.apply(text_proj, text_pos_table, text_pos_ids, text_locations,
+                            image_proj, image_pos_table, image_pos_ids, image_locations,
+                            lpe, lpe_weight, lpe_bias, n_tok)
+
+
+# --------------------------------------------------------------------------------------------- GCN
+class GCNFn(torch.autograd.Function):
+    """2-layer mean-aggregate GCN with a null root node (model/graph.py:17-31):
+        Xr = [0; X];  H = relu([Xr, adj Xr] W1^T);  Y = ([H, adj H] W2^T)[:, 1:]
+    The concat is never materialised for the GEMM: [X, AX] W^T = X Wa^T + (AX) Wb^T runs as the two operand
+    pairs of one tcgen05 GEMM (Wa/Wb are column slices of W, addressed through the TMA descriptor)."""
+
+    @staticmethod
+    def forward(ctx, x, adj, w1, w2):
+        bsz, n, din = x.shape
+        nodes = n + 1
+        dh, dout = w1.shape[0], w2.shape[0]
+        xb = x.to(BF16).contiguous() if x.dtype != BF16 or not x.is_contiguous() else x
+        adj32 = adj.to(F32).contiguous()
+        c1 = torch.empty((bsz * nodes, 2 * din), dtype=BF16, device=x.device)
+        K.gcn_concat_fwd(xb, adj32, c1, bsz, nodes, din, True)
+        w1b, w2b = w16(w1), w16(w2)
+        hid = _new(bsz * nodes, dh, xb)
+        K.gemm(c1[:, :din], w1b[:, :din], hid, a1=c1[:, din:], b1=w1b[:, din:], relu=True)
+        c2 = torch.empty((bsz * nodes, 2 * dh), dtype=BF16, device=x.device)
+        K.gcn_concat_fwd(hid, adj32, c2, bsz, nodes, dh, False)
+        y = _new(bsz * nodes, dout, xb)
+        K.gemm(c2[:, :dh], w2b[:, :dh], y, a1=c2[:, dh:], b1=w2b[:, dh:])
+        ctx.save_for_backward(adj32, c1, hid, c2, w1, w2)
+        ctx.dims = (bsz, nodes, din, dh, dout)
+        ctx.x_dtype = x.dtype
+        return y.reshape(bsz, nodes, dout)[:, 1:, :]
+
+    @staticmethod
+    def backward(ctx, dy):
+        adj32, c1, hid, c2, w1, w2 = ctx.saved_tensors
+        bsz, nodes, din, dh, dout = ctx.dims
+        dev = dy.device
+        dyf = torch.zeros((bsz, nodes, dout), dtype=BF16, device=dev)
+        dyf[:, 1:, :] = dy
+        dy2 = dyf.reshape(bsz * nodes, dout)
+        dx = dw1 = dw2 = None
+        if ctx.needs_input_grad[3]:
+            dw2 = _wgrad(dy2, c2, w2)
+        dc2 = _new(bsz * nodes, 2 * dh, dy2)
+        K.gemm(dy2, w16(w2), dc2, b_t=True)
+        dhid = _new(bsz * nodes, dh, dy2)
+        K.gcn_combine_bwd(dc2, adj32, hid, dhid, bsz, nodes, dh, False)          # ReLU mask applied here
+        if ctx.needs_input_grad[2]:
+            dw1 = _wgrad(dhid, c1, w1)
+        if ctx.needs_input_grad[0]:
+            dc1 = _new(bsz * nodes, 2 * din, dy2)
+            K.gemm(dhid, w16(w1), dc1, b_t=True)
+            dxb = torch.empty((bsz, nodes - 1, din), dtype=BF16, device=dev)
+            K.gcn_combine_bwd(dc1, adj32, None, dxb, bsz, nodes, din, True)
+            dx = dxb.to(ctx.x_dtype)
+        return dx, None, dw1, dw2
+
+
+def gcn(x, adj, w1, w2):
+    return GCNFn.apply(x, adj, w1, w2)
