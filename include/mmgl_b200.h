@@ -37,6 +37,8 @@ int64_t mmgl_launch_count(void);
  *   v = alpha * (acc + bias[n])                  bias optional (fp32)
  *   v = max(v, 0)                                if relu
  *   v = relu_mask[m,n] > 0 ? v : 0               if relu_mask (bf16, ld = ldmask)      (ReLU backward)
+ *   v = keep(m,n) ? v / (1 - p) : 0              if dropout_p > 0 (counter-based mask from dropout_seed, see
+ *                                                mmgl_dropout_apply; p is quantised to 1/65536)
  *   aux[m,n] = v                                 if aux (bf16, ld = ldaux)             (pre-gate value)
  *   v = tanh(*gate) * v                          if gate (device fp32 scalar)
  *   v += residual[m,n]                           if residual (bf16, ld = ldres)
@@ -47,7 +49,7 @@ int64_t mmgl_launch_count(void);
  *                  a_mn_major = 1 -> A is [K rows][M cols] (M contiguous; transposed use, e.g. wgrad).
  *                  b_mn_major likewise for B ([N][K] = nn.Linear weight layout when 0; [K][N] when 1).
  * Requirements: bf16 operands, 16-byte aligned base pointers, leading dimensions multiples of 8
- * elements, K multiple of 8.  M, N arbitrary (tails are predicated).
+ * elements.  M, N, K arbitrary (TMA zero-fills operand tails, output tails are predicated).
  *
  * Replaces: nn.Linear / torch.bmm call sites  model/modelling_cross_attention.py:194,198-199,273,352,355
  * (and their autograd backward), :997,:1020 (neighbor projections), model/graph.py:24,29,
@@ -66,7 +68,8 @@ typedef struct mmgl_gemm_args {
   void* aux; int64_t ldaux;
   const void* relu_mask; int64_t ldmask;
   int32_t force_block_n; /* 0 = heuristic; 64/128/256 to force (tests, tuning) */
-  int32_t reserved;
+  float dropout_p;       /* 0 = no dropout */
+  uint64_t dropout_seed;
 } mmgl_gemm_args;
 
 int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
@@ -76,16 +79,20 @@ int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
  * Q [B,S,nh*d] already scaled by d^-1/2 (done in the q_proj epilogue); K,V [B,Nk,nh*d] (may be the two
  * halves of one fused K|V projection: pass ldk = ldv = 2*nh*d); mask [B,Nk] bytes (1 = attend).
  * Head split/merge, mask expansion, clamp, fp32 softmax and both contractions are fused; no [B,nh,S,Nk]
- * tensor ever reaches HBM.  lse [B,nh,S] fp32 is saved for backward.  d in {64,128}; Nk <= 256.
+ * tensor ever reaches HBM.  stats [B,nh,S,2] fp32 = (row max, 1 / row sum) is saved for backward
+ * (log-sum-exp = stats[0] - log(stats[1])).  d in {64,128}; Nk <= 256 forward (128 when d = 128).
  * Replaces model/modelling_cross_attention.py:176-177,206-271 and :68-79 (_expand_mask).
  */
 int mmgl_xattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                   const uint8_t* mask, void* o, int64_t ldo, float* lse,
+                   const uint8_t* mask, void* o, int64_t ldo, float* stats,
                    int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
 
-/* Backward of the above: dQ [B,S,nh*d], dK/dV [B,Nk,nh*d] (lddk = lddv = 2*nh*d for a fused d(K|V)). */
+/* Backward of the above: dQ [B,S,nh*d], dK/dV [B,Nk,nh*d] (lddk = lddv = 2*nh*d for a fused d(K|V)).  Nk <= 128.
+ * Reference artifact reproduced on purpose: the clamp torch.max(S + mask, finfo.min) (:225-228) ties on every masked
+ * entry and torch splits a tie's gradient in half, so dS of a masked entry is 0.5 * P (dP - delta).  It is only
+ * non-zero for a sample whose neighbors are ALL masked (P uniform); everywhere else P = 0 on masked entries. */
 int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
-                   const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, const uint8_t* mask,
+                   const void* v, int64_t ldv, const void* o, int64_t ldo, const float* stats, const uint8_t* mask,
                    void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                    int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
 
@@ -115,6 +122,13 @@ int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, float scale, c
 int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64_t lda, int64_t m, int64_t n,
                    const float* gate, float* out, int32_t accumulate, void* workspace, size_t workspace_bytes,
                    void* stream);
+
+/* out[m,n] = keep(m,n) ? x[m,n] / (1 - p) : 0 with the SAME counter-based mask the GEMM epilogue applies for
+ * (seed, p): keep(m,n) iff 16 bits of splitmix64(seed ^ (2g + (n%8)/4)) >= round(p*65536), g = m*ceil(N/8) + n/8,
+ * lane (n%8)%4.  Used by backward to re-apply the forward mask (nn.functional.dropout,
+ * model/modelling_cross_attention.py:332, :356).  x, out bf16 [M,N] with leading dims ldx / ldo; in-place allowed. */
+int mmgl_dropout_apply(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t m, int64_t n, float p,
+                       uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbor-bank packing (ragged per-sample interleave of text/image neighbor embeddings).

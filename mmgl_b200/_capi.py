@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("residual", c_vp), ("ldres", c_i64),
         ("aux", c_vp), ("ldaux", c_i64),
         ("relu_mask", c_vp), ("ldmask", c_i64),
-        ("force_block_n", c_i32), ("reserved", c_i32),
+        ("force_block_n", c_i32), ("dropout_p", c_f32), ("dropout_seed", C.c_uint64),
     ]
 
 
@@ -78,6 +78,7 @@ SIGNATURES = {
     "mmgl_reduce_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_colsum": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_f32, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
     "mmgl_gate_grad": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
+    "mmgl_dropout_apply": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, C.c_uint64, c_vp]),
     "mmgl_bank_pack_fwd": (c_i32, [C.POINTER(BankArgs), c_vp]),
     "mmgl_bank_pack_bwd": (c_i32, [C.POINTER(BankBwdArgs), c_vp]),
     "mmgl_gcn_concat_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp]),
@@ -145,7 +146,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
          gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None,
-         accumulate: bool = False, block_n: int = 0) -> torch.Tensor:
+         accumulate: bool = False, block_n: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T (+ A1 @ B1^T)).
 
     a:  [M,K] (a_t=False) or [K,M] (a_t=True: A is used transposed, i.e. stored M-contiguous)
@@ -181,6 +182,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.aux, g.ldaux = _p(aux), (_ld(aux) if aux is not None else 0)
     g.relu_mask, g.ldmask = _p(relu_mask), (_ld(relu_mask) if relu_mask is not None else 0)
     g.force_block_n = block_n
+    g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     _check(lib().mmgl_gemm_bf16(C.byref(g), _stream()), "mmgl_gemm_bf16")
     return out
 
@@ -247,6 +249,15 @@ def gate_grad(dy, a, gate, out, accumulate=False):
     ws = _workspace(nbytes, dy.device)
     _check(lib().mmgl_gate_grad(_p(dy), _ld(dy), _p(a), _ld(a), m, n, _p(gate), _p(out), int(accumulate), _p(ws),
                                 nbytes, _stream()), "mmgl_gate_grad")
+    return out
+
+
+def dropout_apply(x, out, p, seed):
+    """out = keep ? x / (1-p) : 0 with the GEMM epilogue's mask for (seed, p); x, out bf16 2-D views."""
+    _req_cuda(x, out)
+    m, n = x.shape
+    _check(lib().mmgl_dropout_apply(_p(x), _ld(x), _p(out), _ld(out), m, n, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                    _stream()), "mmgl_dropout_apply")
     return out
 
 

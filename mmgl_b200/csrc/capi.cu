@@ -30,6 +30,25 @@ int sm_count() {
   return cached[dev];
 }
 
+int bind_device_of(const void* device_ptr, const char* who) {
+  if (device_ptr == nullptr) { set_error("%s: null pointer", who); return 2; }
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, device_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cudaPointerGetAttributes failed: %s (no CUDA device? this library has no CPU path)", who,
+              cudaGetErrorString(e));
+    return 3;
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+    set_error("%s: expected a CUDA device pointer (this library has no CPU path)", who);
+    return 2;
+  }
+  e = cudaSetDevice(at.device);
+  if (e != cudaSuccess) { set_error("%s: cudaSetDevice(%d) failed: %s", who, at.device, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
 }  // namespace mmgl
 
 extern "C" int mmgl_version(void) { return MMGL_ABI_VERSION; }

@@ -12,6 +12,10 @@ namespace mmgl {
 void set_error(const char* fmt, ...);          // thread-local message, returned by mmgl_last_error_string()
 extern std::atomic<int64_t> g_launch_count;    // every kernel launch of this library bumps it
 int sm_count();                                // SM count of the current device (cached per device)
+// Make the device that owns `device_ptr` current for the calling thread (this library links its own CUDA runtime;
+// PyTorch's autograd threads may not have bound a context yet, and driver calls such as cuTensorMapEncodeTiled
+// need one).  Returns 0 or an error code with the message set.
+int bind_device_of(const void* device_ptr, const char* who);
 
 inline int check_launch(const char* what) {
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -40,6 +44,11 @@ inline int check_launch(const char* what) {
     }                                                                          \
   } while (0)
 
+#define MMGL_BIND(ptr, who)                                   \
+  do {                                                        \
+    if (int rc__ = ::mmgl::bind_device_of((ptr), (who))) return rc__; \
+  } while (0)
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- small device helpers -------------------------------------------------------------------
@@ -58,6 +67,29 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- counter-based dropout mask ---------------------------------------------------------------
+// 16 random bits per element from splitmix64 of (seed, row, col / 8); element (row, col) is KEPT iff its 16-bit lane
+// >= thresh, thresh = round(p * 65536).  Stateless, so backward regenerates the forward mask from the seed alone
+// (nn.functional.dropout call sites: model/modelling_cross_attention.py:332, :356).
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+struct DropBits { uint64_t lo, hi; };
+__host__ __device__ __forceinline__ DropBits dropout_bits(uint64_t seed, int64_t row, int64_t col8, int64_t groups_per_row) {
+  const uint64_t g = static_cast<uint64_t>(row * groups_per_row + col8);
+  DropBits b;
+  b.lo = splitmix64(seed ^ (2 * g));
+  b.hi = splitmix64(seed ^ (2 * g + 1));
+  return b;
+}
+__host__ __device__ __forceinline__ bool dropout_keep(const DropBits& b, int e, uint32_t thresh) {
+  const uint64_t w = (e < 4) ? b.lo : b.hi;
+  return static_cast<uint32_t>((w >> (16 * (e & 3))) & 0xFFFFu) >= thresh;
 }
 
 }  // namespace mmgl

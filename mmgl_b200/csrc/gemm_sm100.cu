@@ -50,6 +50,7 @@ struct GemmParams {
   __nv_bfloat16* aux; int64_t ldaux;
   const __nv_bfloat16* relu_mask; int64_t ldmask;
   int32_t vec_ok;
+  uint32_t drop_thresh; float drop_scale; uint64_t drop_seed; int64_t drop_groups;  // drop_thresh == 0: no dropout
 };
 
 // 8 consecutive output columns of one row: fused epilogue + store.
@@ -75,6 +76,11 @@ __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[
       if (!(bf16lo(w[j]) > 0.f)) v[2 * j] = 0.f;
       if (!(bf16hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
     }
+  }
+  if (p.drop_thresh != 0) {
+    const DropBits bits = dropout_bits(p.drop_seed, row, col >> 3, p.drop_groups);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = dropout_keep(bits, j, p.drop_thresh) ? v[j] * p.drop_scale : 0.f;
   }
   if (p.aux != nullptr) {
     uint4 o;
@@ -121,6 +127,10 @@ __device__ __forceinline__ void epilogue_store1(const GemmParams& p, float v, in
   v *= p.alpha;
   if (p.relu) v = fmaxf(v, 0.f);
   if (p.relu_mask != nullptr && !(__bfloat162float(p.relu_mask[row * p.ldmask + col]) > 0.f)) v = 0.f;
+  if (p.drop_thresh != 0) {
+    const DropBits bits = dropout_bits(p.drop_seed, row, col >> 3, p.drop_groups);
+    v = dropout_keep(bits, (int)(col & 7), p.drop_thresh) ? v * p.drop_scale : 0.f;
+  }
   if (p.aux != nullptr) p.aux[row * p.ldaux + col] = __float2bfloat16_rn(v);
   if (p.gate != nullptr) v *= gate_t;
   if (p.residual != nullptr) v += __bfloat162float(p.residual[row * p.ldres + col]);
@@ -402,11 +412,10 @@ using namespace mmgl;
 extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a != nullptr, "mmgl_gemm_bf16: null args");
+  MMGL_BIND(a->d, "mmgl_gemm_bf16");
   MMGL_REQUIRE(a->m > 0 && a->n > 0 && a->k0 > 0 && a->k1 >= 0, "mmgl_gemm_bf16: bad sizes m=%lld n=%lld k0=%lld k1=%lld",
                (long long)a->m, (long long)a->n, (long long)a->k0, (long long)a->k1);
   MMGL_REQUIRE(a->a0 && a->b0 && a->d, "mmgl_gemm_bf16: null operand");
-  MMGL_REQUIRE(a->k0 % 8 == 0 && a->k1 % 8 == 0, "mmgl_gemm_bf16: K must be a multiple of 8 (k0=%lld k1=%lld)",
-               (long long)a->k0, (long long)a->k1);
   MMGL_REQUIRE(a->lda0 % 8 == 0 && a->ldb0 % 8 == 0 && aligned16(a->a0) && aligned16(a->b0),
                "mmgl_gemm_bf16: operands need 16-byte aligned base and leading dims %% 8 == 0");
   if (a->k1 > 0)
@@ -436,6 +445,11 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   if (a->aux) vec = vec && aligned16(a->aux) && a->ldaux % 8 == 0;
   if (a->relu_mask) vec = vec && aligned16(a->relu_mask) && a->ldmask % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
+  MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "mmgl_gemm_bf16: dropout_p must be in [0,1)");
+  p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
+  p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
+  p.drop_seed = a->dropout_seed;
+  p.drop_groups = (a->n + 7) / 8;
 
   CUtensorMap ma0, mb0, ma1, mb1;
   int rc;

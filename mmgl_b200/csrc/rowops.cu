@@ -227,6 +227,31 @@ gate_final_kernel(const float* __restrict__ partial, int blocks, const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------ dropout re-application
+// out = keep ? x * scale : 0 with the GEMM epilogue's counter-based mask.  One thread per 8-column group.
+__global__ void __launch_bounds__(256)
+dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                     int64_t m, int64_t n, uint32_t thresh, float scale, uint64_t seed, int vec) {
+  const int64_t groups = (n + 7) / 8;
+  const int64_t total = m * groups;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / groups, g = i % groups, col = g * 8;
+    const DropBits bits = dropout_bits(seed, row, g, groups);
+    if (vec && col + 8 <= n) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + col)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = dropout_keep(bits, e, thresh) ? f[e] * scale : 0.f;
+      *reinterpret_cast<uint4*>(out + row * ldo + col) = pack8(f);
+    } else {
+      for (int e = 0; e < 8 && col + e < n; ++e) {
+        const float v = __bfloat162float(x[row * ldx + col + e]);
+        out[row * ldo + col + e] = __float2bfloat16_rn(dropout_keep(bits, e, thresh) ? v * scale : 0.f);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ neighbor bank
 // grid (batch*(T+I), ceil(row_width/2048)), 256 threads x 8 columns.
 __global__ void __launch_bounds__(256)
@@ -413,6 +438,7 @@ using namespace mmgl;
 extern "C" int mmgl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                   float* rstd, int64_t rows, int64_t hidden, float eps, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(x, "mmgl_layernorm_fwd");
   MMGL_REQUIRE(x && gamma && beta && y && mean && rstd, "mmgl_layernorm_fwd: null pointer");
   MMGL_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && hidden <= 8192,
                "mmgl_layernorm_fwd: hidden must be a multiple of 8 and <= 8192 (got %lld)", (long long)hidden);
@@ -439,6 +465,7 @@ extern "C" int mmgl_layernorm_bwd(const void* dy, const void* x, const float* ga
                                   int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows,
                                   int64_t hidden, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(x, "mmgl_layernorm_bwd");
   MMGL_REQUIRE(dy && x && gamma && mean && rstd && dx, "mmgl_layernorm_bwd: null pointer");
   MMGL_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && hidden <= 4096,
                "mmgl_layernorm_bwd: hidden must be a multiple of 8 and <= 4096 (got %lld)", (long long)hidden);
@@ -477,6 +504,7 @@ extern "C" int mmgl_layernorm_bwd(const void* dy, const void* x, const float* ga
 extern "C" int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, float scale, const float* gate,
                            float* out, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(x, "mmgl_colsum");
   MMGL_REQUIRE(x && out && m > 0 && n > 0, "mmgl_colsum: bad arguments");
   MMGL_REQUIRE(aligned16(x) && ldx % 8 == 0, "mmgl_colsum: x must be 16B aligned with ld %% 8 == 0");
   MMGL_REQUIRE(workspace && workspace_bytes >= mmgl_reduce_workspace_bytes(m, n), "mmgl_colsum: workspace too small");
@@ -494,6 +522,7 @@ extern "C" int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64
                               const float* gate, float* out, int32_t accumulate, void* workspace,
                               size_t workspace_bytes, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(dy, "mmgl_gate_grad");
   MMGL_REQUIRE(dy && a && gate && out && m > 0 && n > 0, "mmgl_gate_grad: bad arguments");
   MMGL_REQUIRE(n % 8 == 0 && lddy % 8 == 0 && lda % 8 == 0 && aligned16(dy) && aligned16(a),
                "mmgl_gate_grad: needs n, ld %% 8 == 0 and 16B alignment");
@@ -506,9 +535,27 @@ extern "C" int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64
   return check_launch("mmgl_gate_grad(final)");
 }
 
+extern "C" int mmgl_dropout_apply(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t m, int64_t n, float p,
+                                  uint64_t seed, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(x, "mmgl_dropout_apply");
+  MMGL_REQUIRE(x && out && m > 0 && n > 0, "mmgl_dropout_apply: bad arguments");
+  MMGL_REQUIRE(p >= 0.f && p < 1.f, "mmgl_dropout_apply: p must be in [0,1)");
+  const uint32_t thresh = (uint32_t)(p * 65536.f + 0.5f);
+  const float scale = thresh ? 65536.f / (65536.f - (float)thresh) : 1.f;
+  const int vec = aligned16(x) && aligned16(out) && ldx % 8 == 0 && ldo % 8 == 0;
+  const int64_t total = m * ((n + 7) / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, m, n,
+                                                       thresh, scale, seed, vec);
+  return check_launch("mmgl_dropout_apply");
+}
+
 extern "C" int mmgl_bank_pack_fwd(const mmgl_bank_args* a, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a && a->bank && a->mask && a->batch > 0, "mmgl_bank_pack_fwd: bad arguments");
+  MMGL_BIND(a->bank, "mmgl_bank_pack_fwd");
   MMGL_REQUIRE(a->n_text >= 0 && a->n_image >= 0 && a->n_text + a->n_image > 0, "mmgl_bank_pack_fwd: no neighbors");
   MMGL_REQUIRE(a->row_width % 8 == 0 && a->n_tok > 0 && a->n_tok <= 256 && a->row_width % a->n_tok == 0,
                "mmgl_bank_pack_fwd: row_width must be a multiple of 8 and of n_tok");
@@ -526,6 +573,7 @@ extern "C" int mmgl_bank_pack_fwd(const mmgl_bank_args* a, void* stream_) {
 extern "C" int mmgl_bank_pack_bwd(const mmgl_bank_bwd_args* a, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a && a->d_bank && a->batch > 0 && a->row_width % 8 == 0, "mmgl_bank_pack_bwd: bad arguments");
+  MMGL_BIND(a->d_bank, "mmgl_bank_pack_bwd");
   const int64_t n_src = a->n_text + a->n_image;
   const unsigned cchunks = (unsigned)((a->row_width + 2047) / 2048);
   const auto DB = (const __nv_bfloat16*)a->d_bank;
@@ -555,6 +603,7 @@ extern "C" int mmgl_bank_pack_bwd(const mmgl_bank_bwd_args* a, void* stream_) {
 extern "C" int mmgl_gcn_concat_fwd(const void* x, const float* adj, void* out, int64_t batch, int64_t nodes,
                                    int64_t dim, int32_t prepend_root, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(x, "mmgl_gcn_concat_fwd");
   MMGL_REQUIRE(x && adj && out && batch > 0 && nodes > 1 && nodes <= 96 && dim > 0, "mmgl_gcn_concat_fwd: bad arguments (nodes <= 96)");
   const size_t smem = (size_t)(nodes * nodes + nodes * 256) * sizeof(float);
   MMGL_CUDA(cudaFuncSetAttribute(gcn_concat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,6 +615,7 @@ extern "C" int mmgl_gcn_concat_fwd(const void* x, const float* adj, void* out, i
 extern "C" int mmgl_gcn_combine_bwd(const void* dc, const float* adj, const void* relu_mask, void* dx, int64_t batch,
                                     int64_t nodes, int64_t dim, int32_t drop_root, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(dc, "mmgl_gcn_combine_bwd");
   MMGL_REQUIRE(dc && adj && dx && batch > 0 && nodes > 1 && nodes <= 96 && dim > 0, "mmgl_gcn_combine_bwd: bad arguments (nodes <= 96)");
   const size_t smem = (size_t)(nodes * nodes + nodes * 256) * sizeof(float);
   MMGL_CUDA(cudaFuncSetAttribute(gcn_combine_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -278,8 +278,10 @@ xattn_bwd_kernel(const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const __nv
             p[1] = exp2f((((mk1 == 0.f) ? fmaxf(s[nt][1], -FLT_MAX) : mk1) - m_a) * kLog2e) * il_a;
             p[2] = exp2f((((mk0 == 0.f) ? fmaxf(s[nt][2], -FLT_MAX) : mk0) - m_b) * kLog2e) * il_b;
             p[3] = exp2f((((mk1 == 0.f) ? fmaxf(s[nt][3], -FLT_MAX) : mk1) - m_b) * kLog2e) * il_b;
-            const float ds0 = p[0] * (dp[half][0] - del_a), ds1 = p[1] * (dp[half][1] - del_a);
-            const float ds2 = p[2] * (dp[half][2] - del_b), ds3 = p[3] * (dp[half][3] - del_b);
+            // masked entries tie in the reference's clamp max(S + mask, finfo.min): torch halves a tie's gradient
+            const float h0 = (mk0 == 0.f) ? 1.f : 0.5f, h1 = (mk1 == 0.f) ? 1.f : 0.5f;
+            const float ds0 = h0 * p[0] * (dp[half][0] - del_a), ds1 = h1 * p[1] * (dp[half][1] - del_a);
+            const float ds2 = h0 * p[2] * (dp[half][2] - del_b), ds3 = h1 * p[3] * (dp[half][3] - del_b);
             const uint32_t pa = pack_bf16(p[0], p[1]), pb = pack_bf16(p[2], p[3]);
             const uint32_t da = pack_bf16(ds0, ds1), db = pack_bf16(ds2, ds3);
             *reinterpret_cast<uint32_t*>(sP + ra * PP + nt * 8 + 2 * t) = pa;
@@ -421,6 +423,7 @@ extern "C" int mmgl_xattn_fwd(const void* q, int64_t ldq, const void* k, int64_t
                               const uint8_t* mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq,
                               int64_t nk, int64_t heads, int64_t d, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(q, "mmgl_xattn_fwd");
   if (int rc = check_xattn_args("mmgl_xattn_fwd", batch, seq, nk, heads, d, {ldq, ldk, ldv, ldo}, {q, k, v, o}))
     return rc;
   MMGL_REQUIRE(mask != nullptr && stats != nullptr, "mmgl_xattn_fwd: null mask/stats");
@@ -444,6 +447,7 @@ extern "C" int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int6
                               int64_t lddv, int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t d,
                               void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(q, "mmgl_xattn_bwd");
   if (int rc = check_xattn_args("mmgl_xattn_bwd", batch, seq, nk, heads, d, {lddo, ldq, ldk, ldv, ldo, lddq, lddk, lddv},
                                 {d_o, q, k, v, o, dq, dk, dv}))
     return rc;
@@ -451,14 +455,13 @@ extern "C" int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int6
 #define BWD(D_, NKT_, W_)                                                                                         \
   return launch_bwd<D_, NKT_, W_>(d_o, lddo, q, ldq, k, ldk, v, ldv, o, ldo, stats, mask, dq, lddq, dk, lddk, dv, \
                                   lddv, batch, seq, nk, heads, s)
+  MMGL_REQUIRE(nk <= 128, "mmgl_xattn_bwd: Nk must be <= 128 (got %lld)", (long long)nk);
   if (d == 64) {
     if (nk <= 64) BWD(64, 4, 4);
-    if (nk <= 128) BWD(64, 8, 8);
-    BWD(64, 16, 8);
+    BWD(64, 8, 8);
   } else {
     if (nk <= 64) BWD(128, 4, 4);
-    if (nk <= 128) BWD(128, 8, 8);
-    MMGL_REQUIRE(false, "mmgl_xattn_bwd: head_dim 128 supports Nk <= 128");
+    BWD(128, 8, 8);
   }
 #undef BWD
   return 0;

@@ -24,7 +24,19 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 # --------------------------------------------------------------------------------------------- helpers
-_shadow = weakref.WeakKeyDictionary()
+_shadow = {}   # (id(param), dtype) -> (weakref(param), version, device, converted tensor)
+
+
+def _converted(p: torch.Tensor, dtype) -> torch.Tensor:
+    """`p` converted to `dtype`, cached per parameter object and `_version` (identity-keyed: tensors do not
+    hash/compare by value, and the entry dies with the parameter)."""
+    key = (id(p), dtype)
+    ent = _shadow.get(key)
+    if ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.device:
+        return ent[3]
+    conv = p.detach().to(dtype).contiguous()
+    _shadow[key] = (weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)), p._version, p.device, conv)
+    return conv
 
 
 def w16(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -33,12 +45,7 @@ def w16(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         return None
     if p.dtype == BF16 and p.is_contiguous():
         return p.detach()
-    ent = _shadow.get(p)
-    ver = p._version
-    if ent is None or ent[0] != ver or ent[1].device != p.device:
-        ent = (ver, p.detach().to(BF16).contiguous())
-        _shadow[p] = ent
-    return ent[1]
+    return _converted(p, BF16)
 
 
 def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -47,12 +54,38 @@ def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         return None
     if p.dtype == F32 and p.is_contiguous():
         return p.detach()
-    ent = _shadow.get(p)
-    ver = p._version
-    if ent is None or ent[0] != ver or ent[1].device != p.device:
-        ent = (ver, p.detach().to(F32).contiguous())
-        _shadow[p] = ent
-    return ent[1]
+    return _converted(p, F32)
+
+
+_seed_counter = [0]
+_MASK64 = (1 << 64) - 1
+
+
+def next_dropout_seed() -> int:
+    """A fresh 64-bit seed per dropout site and step, derived from torch's seed (so ``torch.manual_seed`` makes runs
+    repeatable) and a process-local call counter.  No device sync, no RNG kernel: the mask itself is counter-based."""
+    _seed_counter[0] += 1
+    z = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1B54A32D192ED03) & _MASK64
+    z ^= z >> 32
+    return (z * 0xBF58476D1CE4E5B9) & _MASK64
+
+
+def peek_dropout_seeds(n: int):
+    """The next ``n`` seeds next_dropout_seed() will hand out (tests use it to rebuild the masks)."""
+    saved = _seed_counter[0]
+    try:
+        return [next_dropout_seed() for _ in range(n)]
+    finally:
+        _seed_counter[0] = saved
+
+
+def _undrop(dy2, p, seed):
+    """gradient w.r.t. the pre-dropout value: dy * keep / (1 - p) (same counter-based mask as forward)."""
+    if p <= 0.0:
+        return dy2
+    out = torch.empty_like(dy2)
+    K.dropout_apply(dy2, out, p, seed)
+    return out
 
 
 def _gate32(g: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -123,18 +156,20 @@ def mask_u8(mask: torch.Tensor) -> torch.Tensor:
 
 # --------------------------------------------------------------------------------------------- linear
 class LinearFn(torch.autograd.Function):
-    """y = alpha * (x W^T + b) (+ residual).  nn.Linear call sites: model/modelling_cross_attention.py:194,
-    198-199, 273, 826, 997, 1020; model/modelling_self_attention.py:170, 193, 313."""
+    """y = dropout(alpha * (x W^T + b)) (+ residual).  nn.Linear call sites: model/modelling_cross_attention.py:194,
+    198-199, 273 (+ :332 dropout, :337 residual), 826, 997, 1020; model/modelling_self_attention.py:170, 193, 313."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, alpha):
+    def forward(ctx, x, weight, bias, residual, alpha, dropout_p):
         x2 = _as2d(x)
         w = w16(weight)
         y = _new(x2.shape[0], w.shape[0], x2)
         r2 = _as2d(residual) if residual is not None else None
-        K.gemm(x2, w, y, bias=f32(bias), alpha=alpha, residual=r2)
+        seed = next_dropout_seed() if dropout_p > 0.0 else 0
+        K.gemm(x2, w, y, bias=f32(bias), alpha=alpha, residual=r2, dropout_p=dropout_p, dropout_seed=seed)
         ctx.save_for_backward(x2, weight, bias)
         ctx.alpha = alpha
+        ctx.drop = (dropout_p, seed)
         ctx.has_res = residual is not None
         ctx.x_shape = x.shape
         return y.reshape(*x.shape[:-1], w.shape[0])
@@ -142,7 +177,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x2, weight, bias = ctx.saved_tensors
-        dy2 = _as2d(dy)
+        dy2 = _undrop(_as2d(dy), *ctx.drop)
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = _new(x2.shape[0], x2.shape[1], x2)
@@ -154,11 +189,11 @@ class LinearFn(torch.autograd.Function):
             db = _bgrad(dy2, bias, scale=ctx.alpha)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
-        return dx, dw, db, dres, None
+        return dx, dw, db, dres, None, None
 
 
-def linear(x, weight, bias=None, residual=None, alpha=1.0):
-    return LinearFn.apply(x, weight, bias, residual, alpha)
+def linear(x, weight, bias=None, residual=None, alpha=1.0, dropout_p=0.0):
+    return LinearFn.apply(x, weight, bias, residual, alpha, float(dropout_p))
 
 
 class LoRALinearFn(torch.autograd.Function):
@@ -236,26 +271,28 @@ def layer_norm(x, weight, bias, eps=1e-5):
 
 # --------------------------------------------------------------------------------------------- MLP
 class MLPFn(torch.autograd.Function):
-    """y = residual + fc2(relu(fc1(x))): model/modelling_cross_attention.py:352-361 (non-gated form).
-    ReLU and its backward mask live in the GEMM epilogues; no [M,F] elementwise pass touches HBM."""
+    """y = residual + dropout(fc2(relu(fc1(x)))): model/modelling_cross_attention.py:352-361 (non-gated form).
+    ReLU, its backward mask and the dropout live in the GEMM epilogues; no [M,F] elementwise pass touches HBM."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, residual):
+    def forward(ctx, x, w1, b1, w2, b2, residual, dropout_p):
         x2 = _as2d(x)
         f = _new(x2.shape[0], w1.shape[0], x2)
         K.gemm(x2, w16(w1), f, bias=f32(b1), relu=True)
         y = _new(x2.shape[0], w2.shape[0], x2)
         r2 = _as2d(residual) if residual is not None else None
-        K.gemm(f, w16(w2), y, bias=f32(b2), residual=r2)
+        seed = next_dropout_seed() if dropout_p > 0.0 else 0
+        K.gemm(f, w16(w2), y, bias=f32(b2), residual=r2, dropout_p=dropout_p, dropout_seed=seed)
         ctx.save_for_backward(x2, f, w1, b1, w2, b2)
         ctx.has_res = residual is not None
+        ctx.drop = (dropout_p, seed)
         ctx.x_shape = x.shape
         return y.reshape(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
         x2, f, w1, b1, w2, b2 = ctx.saved_tensors
-        dy2 = _as2d(dy)
+        dy2 = _undrop(_as2d(dy), *ctx.drop)
         df = torch.empty_like(f)
         K.gemm(dy2, w16(w2), df, b_t=True, relu_mask=f)
         dx = dw1 = db1 = dw2 = db2 = dres = None
@@ -273,11 +310,11 @@ class MLPFn(torch.autograd.Function):
             db2 = _bgrad(dy2, b2)
         if ctx.has_res and ctx.needs_input_grad[5]:
             dres = dy
-        return dx, dw1, db1, dw2, db2, dres
+        return dx, dw1, db1, dw2, db2, dres, None
 
 
-def mlp(x, w1, b1, w2, b2, residual=None):
-    return MLPFn.apply(x, w1, b1, w2, b2, residual)
+def mlp(x, w1, b1, w2, b2, residual=None, dropout_p=0.0):
+    return MLPFn.apply(x, w1, b1, w2, b2, residual, float(dropout_p))
 
 
 # --------------------------------------------------------------------------------------------- attention core
@@ -327,7 +364,7 @@ class GatedCrossLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1,
-                ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln):
+                ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln, dropout_p):
         bsz, s, h = x.shape
         nk = bank.shape[1]
         d = h // heads
@@ -351,9 +388,12 @@ class GatedCrossLayerFn(torch.autograd.Function):
         o = _new(m_rows, h, x2)
         stats = torch.empty((bsz, heads, s, 2), dtype=F32, device=x.device)
         K.xattn_fwd(q, k, v, m8, o, stats, bsz, s, nk, heads, d)                  # :206-271
+        seed1 = next_dropout_seed() if dropout_p > 0.0 else 0
+        seed2 = next_dropout_seed() if dropout_p > 0.0 else 0
         a_out = _new(m_rows, h, x2) if g1 is not None else None
         u = _new(m_rows, h, x2)
-        K.gemm(o, w16(wo), u, bias=f32(bo), aux=a_out, gate=g1f, residual=x2)     # :273, :332-337
+        K.gemm(o, w16(wo), u, bias=f32(bo), aux=a_out, gate=g1f, residual=x2,     # :273, :332-337
+               dropout_p=dropout_p, dropout_seed=seed1)
         if pre_ln:
             h1 = u
             f_in, mean2, rstd2 = _ln_fwd(h1, ln2g, f32(ln2_b), eps)              # :350
@@ -364,13 +404,15 @@ class GatedCrossLayerFn(torch.autograd.Function):
         K.gemm(f_in, w16(w1), f, bias=f32(b1), relu=True)                         # :352-353
         c_out = _new(m_rows, h, x2) if g2 is not None else None
         wsum = _new(m_rows, h, x2)
-        K.gemm(f, w16(w2), wsum, bias=f32(b2), aux=c_out, gate=g2f, residual=h1)  # :355-361
+        K.gemm(f, w16(w2), wsum, bias=f32(b2), aux=c_out, gate=g2f, residual=h1,  # :355-361
+               dropout_p=dropout_p, dropout_seed=seed2)
         if pre_ln:
             y = wsum
         else:
             y, mean2, rstd2 = _ln_fwd(wsum, ln2g, f32(ln2_b), eps)               # :365
 
         ctx.pre_ln = pre_ln
+        ctx.drop1, ctx.drop2 = (dropout_p, seed1), (dropout_p, seed2)
         ctx.dims = (bsz, s, nk, heads, h)
         ctx.eps = eps
         ctx.x_shape, ctx.bank_shape = x.shape, bank.shape
@@ -396,7 +438,7 @@ class GatedCrossLayerFn(torch.autograd.Function):
         k, v = kv[:, :h], kv[:, h:]
         (i_x, i_bank, _i_mask, i_ln1w, i_ln1b, i_wq, i_bq, i_wk, i_bk, i_wv, i_bv, i_wo, i_bo, i_g1,
          i_ln2w, i_ln2b, i_w1, i_b1, i_w2, i_b2, i_g2) = range(21)
-        grads = [None] * 24
+        grads = [None] * 25
 
         # ---- FFN branch
         if pre_ln:
@@ -404,8 +446,10 @@ class GatedCrossLayerFn(torch.autograd.Function):
         else:
             dw_, grads[i_ln2w], grads[i_ln2b] = _ln_bwd(dy2, wsum, ln2g, mean2, rstd2, None,
                                                         need[i_ln2w] or need[i_ln2b], ln2_w, ln2_b)
+        dres2 = dw_                                                            # residual path of the FFN branch
         if g2 is not None and need[i_g2]:
-            grads[i_g2] = _scalar_grad(dw_, c_out, g2f, g2)
+            grads[i_g2] = _scalar_grad(dw_, c_out, g2f, g2)       # c_out is the post-dropout, pre-gate branch value
+        dw_ = _undrop(dw_, *ctx.drop2)                            # from here on: gradient of the pre-dropout fc2 output
         df = torch.empty_like(f)
         K.gemm(dw_, w16(w2), df, b_t=True, relu_mask=f, gate=g2f)             # d relu(fc1) (mask, then gate)
         if need[i_w2]:
@@ -419,24 +463,25 @@ class GatedCrossLayerFn(torch.autograd.Function):
         if pre_ln:
             dln2 = torch.empty_like(h1)
             K.gemm(df, w16(w1), dln2, b_t=True)
-            dh1, grads[i_ln2w], grads[i_ln2b] = _ln_bwd(dln2, h1, ln2g, mean2, rstd2, dw_,
+            dh1, grads[i_ln2w], grads[i_ln2b] = _ln_bwd(dln2, h1, ln2g, mean2, rstd2, dres2,
                                                         need[i_ln2w] or need[i_ln2b], ln2_w, ln2_b)
             du = dh1                                                           # grad of u (= h1)
         else:
             dh1 = torch.empty_like(h1)
-            K.gemm(df, w16(w1), dh1, b_t=True, residual=dw_)
+            K.gemm(df, w16(w1), dh1, b_t=True, residual=dres2)
             du, grads[i_ln1w], grads[i_ln1b] = _ln_bwd(dh1, u, ln1g, mean1, rstd1, None,
                                                        need[i_ln1w] or need[i_ln1b], ln1_w, ln1_b)
 
         # ---- attention branch
         if g1 is not None and need[i_g1]:
             grads[i_g1] = _scalar_grad(du, a_out, g1f, g1)
+        dud = _undrop(du, *ctx.drop1)                                          # gradient of the pre-dropout out_proj output
         d_o = torch.empty_like(o)
-        K.gemm(du, w16(wo), d_o, b_t=True, gate=g1f)
+        K.gemm(dud, w16(wo), d_o, b_t=True, gate=g1f)
         if need[i_wo]:
-            grads[i_wo] = _wgrad(du, o, wo, gate=g1f)
+            grads[i_wo] = _wgrad(dud, o, wo, gate=g1f)
         if bo is not None and need[i_bo]:
-            grads[i_bo] = _bgrad(du, bo, gate=g1f)
+            grads[i_bo] = _bgrad(dud, bo, gate=g1f)
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         dk, dv = dkv[:, :h], dkv[:, h:]
@@ -475,9 +520,9 @@ class GatedCrossLayerFn(torch.autograd.Function):
 
 
 def gated_cross_layer(x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1, ln2_w, ln2_b, w1, b1, w2, b2,
-                      g2, heads, eps=1e-5, pre_ln=True):
+                      g2, heads, eps=1e-5, pre_ln=True, dropout_p=0.0):
     return GatedCrossLayerFn.apply(x, bank, mask, ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wo, bo, g1,
-                                   ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln)
+                                   ln2_w, ln2_b, w1, b1, w2, b2, g2, heads, eps, pre_ln, float(dropout_p))
 
 
 # --------------------------------------------------------------------------------------------- neighbor bank

@@ -122,6 +122,37 @@ def xattn_core(q: Tensor, k: Tensor, v: Tensor, mask: Tensor, num_heads: int) ->
 
 
 # ----------------------------------------------------------------------------
+# dropout (nn.functional.dropout, model/modelling_cross_attention.py:332, :356)
+# ----------------------------------------------------------------------------
+def dropout_multiplier(seed: int, p: float, m: int, n: int) -> Tensor:
+    """[m,n] fp32 multiplier (0 or 1/(1-p')) of the CUDA path's counter-based dropout, restated with numpy integers.
+
+    torch's Philox stream cannot be reproduced by another implementation, so parity for dropout is (i) this mask
+    restatement, bit-exact, and (ii) the reference semantics y = x * keep / (1-p) given the same keep mask.
+    Element (r, c): g = r*ceil(n/8) + c//8; word = splitmix64(seed ^ (2g + (c%8)//4)); lane = (c%8)%4;
+    keep iff ((word >> 16*lane) & 0xFFFF) >= round(p*65536); p' = round(p*65536)/65536."""
+    import numpy as np
+    thresh = int(p * 65536.0 + 0.5)
+    if thresh == 0:
+        return torch.ones(m, n)
+    groups = (n + 7) // 8
+    r = np.arange(m, dtype=np.uint64)[:, None]
+    c = np.arange(n, dtype=np.uint64)[None, :]
+    g = r * np.uint64(groups) + c // np.uint64(8)
+    z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) ^ (np.uint64(2) * g + (c % np.uint64(8)) // np.uint64(4))
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    lane = (c % np.uint64(8)) % np.uint64(4)
+    bits = (z >> (np.uint64(16) * lane)) & np.uint64(0xFFFF)
+    keep = bits >= np.uint64(thresh)
+    scale = 65536.0 / (65536.0 - thresh)
+    return torch.from_numpy(keep.astype(np.float32) * np.float32(scale))
+
+
+# ----------------------------------------------------------------------------
 # a2: MPTDecoderLayer
 # ----------------------------------------------------------------------------
 def mpt_decoder_layer(
@@ -136,8 +167,11 @@ def mpt_decoder_layer(
     do_layer_norm_before: bool = True,
     flamingo: bool = True,
     eps: float = 1e-5,
+    drop1: Optional[Tensor] = None,
+    drop2: Optional[Tensor] = None,
 ) -> Tensor:
-    """model/modelling_cross_attention.py:304-375 (dropout = 0 / eval).
+    """model/modelling_cross_attention.py:304-375.  Dropout (:332, :356) is the identity (eval) unless the
+    multipliers ``drop1``/``drop2`` ([B*S,H], 0 or 1/(1-p)) are supplied -- see dropout_multiplier.
 
     cross_attention=True, flamingo=True: tanh-gated residuals with scalars
     ``gating1``/``gating2`` (:298-302, :334-335, :358-359)."""
@@ -150,6 +184,8 @@ def mpt_decoder_layer(
         hs = mpt_attention(hs, bank, bank_add_mask, p, num_heads)                              # :323-331
     else:
         hs = mpt_attention(hs, hs, add_mask, p, num_heads)
+    if drop1 is not None:                                                                      # :332
+        hs = hs * drop1.view(hs.shape)
     if cross_attention and flamingo:                                                           # :334-337
         hs = residual + torch.tanh(p["gating1"]) * hs
     else:
@@ -163,6 +199,8 @@ def mpt_decoder_layer(
         hs = F.layer_norm(hs, (h,), p["final_layer_norm.weight"], p["final_layer_norm.bias"], eps)
     hs = F.relu(F.linear(hs, p["fc1.weight"], p.get("fc1.bias")))                              # :352-353 (OPT: relu)
     hs = F.linear(hs, p["fc2.weight"], p.get("fc2.bias"))                                      # :355
+    if drop2 is not None:                                                                      # :356
+        hs = hs * drop2.view(hs.shape)
     if cross_attention and flamingo:                                                           # :358-361
         hs = (residual + torch.tanh(p["gating2"]) * hs).view(shape)
     else:

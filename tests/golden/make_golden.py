@@ -54,9 +54,127 @@ def mpt_args(**kw):
     return types.SimpleNamespace(**base)
 
 
+def layer_case(xa, name, pre_ln, seed, B, S, NK, H, heads, ffn):
+    """one gated cross-attention layer of the REAL reference: output + all gradients"""
+    g = torch.Generator().manual_seed(seed)
+    cfg = xa.MPTConfig(mpt_args(), tiny_opt_config(pre_ln, hidden=H, heads=heads, ffn=ffn))
+    layer = xa.MPTDecoderLayer(cfg, cross_attention=True)
+    for prm in layer.parameters():
+        prm.data.normal_(0, 0.08, generator=g)
+    for n, prm in layer.named_parameters():
+        if "layer_norm.weight" in n:
+            prm.data.add_(1.0)
+    layer.gating1.data.fill_(0.7)
+    layer.gating2.data.fill_(-0.4)
+    layer.eval()
+    # bf16-representable weights and inputs: the fp32 reference then sees exactly what the bf16 kernels see
+    for prm in layer.parameters():
+        if prm.dim() == 2:
+            prm.data.copy_(prm.data.bfloat16().float())
+    r16 = lambda t: t.bfloat16().float()
+    x = r16(torch.randn(B, S, H, generator=g)).requires_grad_(True)
+    bank = r16(torch.randn(B, NK, H, generator=g)).requires_grad_(True)
+    mask = torch.rand(B, NK, generator=g) > 0.3
+    mask[0, :] = True
+    mask[1, -5:] = False
+    add = xa._expand_mask(mask, x.dtype, tgt_len=S)
+    y = layer(x, neighbor_embeds=bank, neighbor_attention_mask=add)[0]
+    w = r16(torch.randn(B, S, H, generator=g))
+    (y * w).sum().backward()
+    save(name, dict(
+        cfg=dict(num_heads=heads, do_layer_norm_before=pre_ln), state=sd(layer), x=x.detach(), bank=bank.detach(),
+        mask=mask, y=y.detach(), w=w, dx=x.grad.clone(), dbank=bank.grad.clone(),
+        grads={k: v.grad.clone() for k, v in layer.named_parameters()}))
+
+
+def wrapper_cross_d64(xa):
+    """full reference CrossAttentionModel at head_dim 64 with bf16-representable weights: loss, logits, bank and the
+    gradients of every trainable parameter (the CUDA model-level parity test compares against these)."""
+    from transformers import (CLIPVisionConfig, CLIPVisionModel, OPTForCausalLM, RobertaConfig, RobertaModel)
+    tmp = tempfile.mkdtemp(prefix="mmgl_golden_d64_")
+    d_lm, d_txt, d_vis = (os.path.join(tmp, n) for n in ("opt", "roberta", "clipv"))
+    torch.manual_seed(71)
+    lm_cfg = tiny_opt_config(True, hidden=128, layers=4, heads=2, ffn=256, vocab=512)
+    txt_cfg = RobertaConfig(vocab_size=512, hidden_size=32, num_hidden_layers=2, num_attention_heads=2,
+                            intermediate_size=64, max_position_embeddings=40, pad_token_id=1)
+    vis_cfg = CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                               image_size=32, patch_size=16)
+    OPTForCausalLM(lm_cfg).save_pretrained(d_lm)
+    RobertaModel(txt_cfg).save_pretrained(d_txt)
+    CLIPVisionModel(vis_cfg).save_pretrained(d_vis)
+    args = mpt_args(context="all", n_text_tokens=2, n_visual_tokens=2, model_name_or_path=d_lm, text_model=d_txt,
+                    visual_model=d_vis, max_output_length=16, freeze_lm=False)
+    model = xa.CrossAttentionModel(args, tokenizer=None)
+    g = torch.Generator().manual_seed(72)
+    for n, prm in model.named_parameters():
+        if "gating" in n:
+            prm.data.fill_(0.5 if "gating1" in n else -0.6)
+        elif "neighbor_layers" in n and prm.dim() == 2:
+            prm.data.normal_(0, 0.05, generator=g)     # init_std 0.02 gives a nearly dead branch at this size
+        if prm.is_floating_point() and not n.startswith(("text_model.", "visual_model.")):
+            prm.data.copy_(prm.data.bfloat16().float())
+    model.lm.lm_head.weight = model.lm.model.decoder.embed_tokens.weight   # tie (SURVEY D12)
+    model.eval()
+    B, S, T, I, L = 2, 24, 3, 2, 12
+    ids = torch.randint(4, 512, (B, S), generator=g)
+    am = torch.ones(B, S, dtype=torch.long)
+    am[0, -3:] = 0
+    ids[0, -3:] = 1
+    am[1, 10:13] = 0          # padding in the middle (input segment right-padded before the output segment)
+    ids[1, 10:13] = 1
+    nids = torch.randint(4, 512, (B, T, L), generator=g)
+    nam = torch.ones(B, T, L, dtype=torch.long)
+    nam[:, :, -4:] = 0
+    batch = dict(
+        input_ids=ids, attention_mask=am, labels=ids.clone(),
+        neighbor_input_ids=nids, neighbor_attention_mask=nam,
+        neighbor_pos_ids=torch.tensor([[1, 2, 3], [1, 2, 0]]),
+        text_locations=torch.tensor([[0, 2, 4], [0, 2, 3]]),
+        neighbor_images=torch.randn(B, I, 3, 32, 32, generator=g),
+        neighbor_images_pos_ids=torch.tensor([[1, 2], [1, 0]]),
+        image_locations=torch.tensor([[1, 3], [1, 4]]),
+    )
+    cap = {}
+
+    def pool_hook(m, i, o):
+        o2 = o.detach().bfloat16().float()           # bf16-representable pooled features, fed on to the projections
+        cap["text_pooled"] = o2
+        return o2 + (o - o.detach())                 # keep the autograd edge to the pooler
+
+    def vis_hook(m, i, o):
+        o.pooler_output = o.pooler_output.detach().bfloat16().float()
+        cap["visual_pooled"] = o.pooler_output
+        return o
+    h1 = model.text_pooler.register_forward_hook(pool_hook)
+    h2 = model.visual_model.register_forward_hook(vis_hook)
+    h3 = model.lm.register_forward_pre_hook(lambda m, a, kw: cap.__setitem__("lm_kwargs", {k: v.detach() for k, v in kw.items() if v is not None}), with_kwargs=True)
+    out = model(**batch)
+    out.loss.backward()
+    for h in (h1, h2, h3):
+        h.remove()
+    state = {k: v for k, v in sd(model).items() if not k.startswith(("text_model.", "visual_model."))}
+    grads = {n: prm.grad.clone() for n, prm in model.named_parameters()
+             if prm.grad is not None and not n.startswith("text_pooler.") and n != "lm.lm_head.weight"}
+    save("wrapper_cross_d64", dict(
+        cfg=dict(num_heads=2, num_layers=4, neighbor_layer_wise=2, do_layer_norm_before=True, n_tokens=2),
+        lm_config=lm_cfg.to_dict(), text_config=txt_cfg.to_dict(), visual_config=vis_cfg.to_dict(),
+        state=state, batch=batch, text_pooled=cap["text_pooled"].reshape(B, T, -1),
+        visual_pooled=cap["visual_pooled"].reshape(B, I, -1), bank=cap["lm_kwargs"]["neighbor_embeds"],
+        bank_mask=cap["lm_kwargs"]["neighbor_attention_mask"], loss=out.loss.detach(), logits=out.logits.detach(),
+        grads=grads))
+
+
 def main():
     torch.manual_seed(0)
     xa = load_ref("ref_xattn", f"{REF}/model/modelling_cross_attention.py")
+    wrapper_cross_d64(xa)
+
+    # ---- case 1b: the same layer at head_dim 64 (the CUDA kernels support d in {64,128}) -------
+    for pre_ln in (True, False):
+        layer_case(xa, f"xattn_layer_d64_{'pre' if pre_ln else 'post'}ln", pre_ln, 61 + int(pre_ln),
+                   B=2, S=40, NK=24, H=128, heads=2, ffn=256)
+    if "--only-d64" in sys.argv:
+        return
 
     # ---- case 1: one gated cross-attention layer (pre-LN and post-LN) -----------------------
     for pre_ln in (True, False):

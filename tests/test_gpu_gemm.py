@@ -1,0 +1,151 @@
+"""tcgen05 GEMM (mmgl_gemm_bf16) against a plain PyTorch fp32 matmul of the same bf16-rounded operands.
+
+Floating-point kernel -> torch fp32 reference (TF32 off).  Tolerances: fp32 output 2e-5 rel-L2 (accumulation
+order only); bf16 output 4e-3 rel-L2 (one bf16 rounding, 2^-9 relative, of the fp32 result).
+"""
+import pytest
+import torch
+
+from util import BF16, assert_close, randn
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 2e-5
+TOL_BF16 = 4e-3
+
+
+def _K():
+    from mmgl_b200 import _capi
+    return _capi
+
+
+def _operands(gen, m, n, k, a_t, b_t, pad=0):
+    """bf16 operands stored in the requested majorness; returns (a_store, b_store, A[M,K] fp32, B[N,K] fp32)."""
+    a = randn(gen, m, k).to(BF16)
+    b = randn(gen, n, k).to(BF16)
+    a_store = a.t().contiguous() if a_t else a
+    b_store = b.t().contiguous() if b_t else b
+    return a_store, b_store, a.float(), b.float()
+
+
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 200, 136), (1, 8, 8), (77, 520, 1000), (72, 64, 37)])
+def test_gemm_majors_and_tails(a_t, b_t, bn, m, n, k):
+    if (a_t and m % 8) or (b_t and n % 8) or (not a_t and k % 8) or (not b_t and k % 8):
+        pytest.skip("the contiguous dim of each operand must be a multiple of 8 (16-byte rows)")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(m * 7 + n * 3 + k + bn)
+    a_s, b_s, a, b = _operands(gen, m, n, k, a_t, b_t)
+    out = torch.full((m, n), float("nan"), dtype=torch.float32, device="cuda")
+    _K().gemm(a_s, b_s, out, a_t=a_t, b_t=b_t, block_n=bn)
+    assert_close("fp32 out", out, a @ b.t(), TOL_F32)
+    out16 = torch.empty((m, n), dtype=BF16, device="cuda")
+    _K().gemm(a_s, b_s, out16, a_t=a_t, b_t=b_t, block_n=bn)
+    assert_close("bf16 out", out16, a @ b.t(), TOL_BF16)
+
+
+@pytest.mark.parametrize("m,n,k", [(640, 2048, 2048), (2560, 8192, 2048), (2560, 2048, 8192), (64, 4096, 2048)])
+def test_gemm_production_shapes_heuristic_tile(m, n, k):
+    """OPT-1.3B gated cross-attention block shapes (q/out proj, fc1, fc2, K|V proj), heuristic BLOCK_N."""
+    gen = torch.Generator().manual_seed(5)
+    a_s, b_s, a, b = _operands(gen, m, n, k, False, False)
+    out = torch.empty((m, n), dtype=BF16, device="cuda")
+    _K().gemm(a_s, b_s, out)
+    assert_close("bf16 out", out, a @ b.t(), TOL_BF16)
+
+
+def test_gemm_wgrad_shape_fp32():
+    """dW[N_out,K_in] = dy^T x: both operands MN-major, long K (= tokens), fp32 master-weight output."""
+    gen = torch.Generator().manual_seed(6)
+    rows, n_out, k_in = 1280, 2048, 512
+    dy = randn(gen, rows, n_out).to(BF16)
+    x = randn(gen, rows, k_in).to(BF16)
+    out = torch.empty((n_out, k_in), dtype=torch.float32, device="cuda")
+    _K().gemm(dy, x, out, a_t=True, b_t=True)
+    assert_close("wgrad", out, dy.float().t() @ x.float(), TOL_F32)
+
+
+@pytest.mark.parametrize("n", [256, 100])  # 100: row pitch not 16-byte aligned -> scalar epilogue path
+def test_gemm_fused_epilogue(n):
+    gen = torch.Generator().manual_seed(7 + n)
+    m, k = 200, 192
+    a_s, b_s, a, b = _operands(gen, m, n, k, False, False)
+    bias = randn(gen, n)
+    gate = torch.tensor([0.7], device="cuda")
+    res = randn(gen, m, n).to(BF16)
+    mask = randn(gen, m, n).to(BF16)
+    alpha = 0.125
+    K = _K()
+
+    # bias + alpha + relu
+    out = torch.empty((m, n), dtype=BF16, device="cuda")
+    K.gemm(a_s, b_s, out, bias=bias, alpha=alpha, relu=True)
+    assert_close("bias/alpha/relu", out, torch.relu(alpha * (a @ b.t() + bias)), TOL_BF16)
+
+    # bias, aux (pre-gate), tanh gate, residual
+    aux = torch.empty((m, n), dtype=BF16, device="cuda")
+    K.gemm(a_s, b_s, out, bias=bias, aux=aux, gate=gate, residual=res)
+    pre = a @ b.t() + bias
+    assert_close("aux", aux, pre, TOL_BF16)
+    assert_close("gate+residual", out, res.float() + torch.tanh(gate) * pre, TOL_BF16)
+
+    # relu_mask then gate (ReLU backward fused into dgrad)
+    K.gemm(a_s, b_s, out, relu_mask=mask, gate=gate)
+    want = (a @ b.t()) * (mask.float() > 0).float() * torch.tanh(gate)
+    assert_close("relu_mask", out, want, TOL_BF16)
+
+    # accumulate into fp32 and bf16 outputs
+    base = randn(gen, m, n)
+    acc = base.clone()
+    K.gemm(a_s, b_s, acc, accumulate=True)
+    assert_close("accumulate fp32", acc, base + a @ b.t(), TOL_F32)
+    acc16 = base.to(BF16)
+    K.gemm(a_s, b_s, acc16, accumulate=True)
+    assert_close("accumulate bf16", acc16, base.to(BF16).float() + a @ b.t(), TOL_BF16)
+
+
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, True)])
+def test_gemm_second_operand_pair(a_t, b_t):
+    """acc = A0 B0^T + A1 B1^T in one TMEM tile (LoRA side product, GCN concat, d_bank = dK Wk + dV Wv)."""
+    gen = torch.Generator().manual_seed(9)
+    m, n, k0, k1 = 264, 328, 200, 64
+    a0_s, b0_s, a0, b0 = _operands(gen, m, n, k0, a_t, b_t)
+    a1_s, b1_s, a1, b1 = _operands(gen, m, n, k1, a_t, b_t)
+    out = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    _K().gemm(a0_s, b0_s, out, a_t=a_t, b_t=b_t, a1=a1_s, b1=b1_s)
+    assert_close("dual", out, a0 @ b0.t() + a1 @ b1.t(), TOL_F32)
+
+
+def test_gemm_column_sliced_views():
+    """Operands / outputs that are column slices of wider buffers (fused K|V buffer, W[:, :D] halves)."""
+    gen = torch.Generator().manual_seed(10)
+    m, n, k = 96, 128, 64
+    abuf = randn(gen, m, 2 * k).to(BF16)
+    wbuf = randn(gen, n, 2 * k).to(BF16)
+    obuf = torch.zeros((m, 2 * n), dtype=BF16, device="cuda")
+    _K().gemm(abuf[:, k:], wbuf[:, :k], obuf[:, n:])
+    assert_close("sliced", obuf[:, n:], abuf[:, k:].float() @ wbuf[:, :k].float().t(), TOL_BF16)
+    assert float(obuf[:, :n].abs().max()) == 0.0, "wrote outside the output slice"
+
+
+def test_gemm_rejects_bad_arguments():
+    K = _K()
+    a = torch.zeros((8, 12), dtype=BF16, device="cuda")  # row pitch 24 B: not 16-byte aligned rows
+    b = torch.zeros((8, 12), dtype=BF16, device="cuda")
+    out = torch.zeros((8, 8), dtype=BF16, device="cuda")
+    with pytest.raises(RuntimeError, match="leading dims"):
+        K.gemm(a, b, out)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        K.gemm(a.cpu(), b.cpu(), out.cpu())
+
+
+def test_launch_counter_moves():
+    K = _K()
+    n0 = K.launch_count()
+    a = torch.ones((128, 64), dtype=BF16, device="cuda")
+    out = torch.empty((128, 128), dtype=BF16, device="cuda")
+    K.gemm(a, torch.ones((128, 64), dtype=BF16, device="cuda"), out)
+    torch.cuda.synchronize()
+    assert K.launch_count() == n0 + 1
+    assert float(out.float().min()) == 64.0 and float(out.float().max()) == 64.0

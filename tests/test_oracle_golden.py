@@ -8,7 +8,8 @@ from oracle import mmgl_oracle as O
 TOL = dict(rtol=1e-5, atol=2e-6)  # fp32 vs fp32, different op order only
 
 
-@pytest.mark.parametrize("name", ["xattn_layer_preln", "xattn_layer_postln"])
+@pytest.mark.parametrize("name", ["xattn_layer_preln", "xattn_layer_postln", "xattn_layer_d64_preln",
+                                  "xattn_layer_d64_postln"])
 def test_cross_layer_forward_backward(golden, name):
     g = golden(name)
     p = {k: v.clone().requires_grad_(True) for k, v in g["state"].items()}

@@ -1,0 +1,120 @@
+"""Per-kernel timing on one B200 (CUDA events, L2 flushed between iterations).  Development tool: prints one JSON
+line per case; bench.py is the judged entry point.  Usage: python tools/microbench.py [gemm] [xattn] [rowops]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmgl_b200 import _capi as K  # noqa: E402
+
+BF16 = torch.bfloat16
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def time_it(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_gemm():
+    shapes = [  # (M, N, K, a_t, b_t, label)
+        (2560, 2048, 2048, 0, 0, "q/out proj B=4"),
+        (2560, 8192, 2048, 0, 0, "fc1 B=4"),
+        (2560, 2048, 8192, 0, 0, "fc2 B=4"),
+        (256, 2048, 2048, 0, 0, "k/v proj B=4"),
+        (2560, 2048, 8192, 0, 1, "dgrad fc1 B=4"),
+        (8192, 2048, 2560, 1, 1, "wgrad fc1 B=4"),
+        (2048, 8192, 2560, 1, 1, "wgrad fc2 B=4"),
+        (8192, 8192, 8192, 0, 0, "square 8k"),
+        (2560, 50272, 2048, 0, 0, "lm_head B=4"),
+    ]
+    for m, n, k, a_t, b_t, label in shapes:
+        a = torch.randn((k, m) if a_t else (m, k), device="cuda").to(BF16)
+        b = torch.randn((k, n) if b_t else (n, k), device="cuda").to(BF16)
+        out = torch.empty((m, n), dtype=BF16, device="cuda")
+        flops = 2.0 * m * n * k
+        res = {"kernel": "gemm", "label": label, "m": m, "n": n, "k": k, "a_t": a_t, "b_t": b_t}
+        for bn in (0, 64, 128, 256):
+            med, best = time_it(lambda: K.gemm(a, b, out, a_t=bool(a_t), b_t=bool(b_t), block_n=bn))
+            res[f"ours_bn{bn}_tflops"] = round(flops / med / 1e9, 1)
+        am = a.t() if a_t else a
+        bm = b if b_t else b.t()
+        med, best = time_it(lambda: torch.matmul(am, bm, out=out))
+        res["cublas_tflops"] = round(flops / med / 1e9, 1)
+        print(json.dumps(res), flush=True)
+
+
+def bench_xattn():
+    for b, s, nk, heads, d in [(4, 640, 64, 32, 64), (4, 640, 128, 32, 64), (8, 640, 64, 32, 64), (2, 1152, 128, 32, 128)]:
+        h = heads * d
+        q = torch.randn(b * s, h, device="cuda").to(BF16)
+        kv = torch.randn(b * nk, 2 * h, device="cuda").to(BF16)
+        mask = torch.ones(b, nk, dtype=torch.uint8, device="cuda")
+        o = torch.empty_like(q)
+        stats = torch.empty(b, heads, s, 2, dtype=torch.float32, device="cuda")
+        do = torch.randn_like(q)
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        fwd = lambda: K.xattn_fwd(q, kv[:, :h], kv[:, h:], mask, o, stats, b, s, nk, heads, d)
+        bwd = lambda: K.xattn_bwd(do, q, kv[:, :h], kv[:, h:], o, stats, mask, dq, dkv[:, :h], dkv[:, h:], b, s, nk, heads, d)
+        fm, _ = time_it(fwd)
+        bm, _ = time_it(bwd)
+        bytes_fwd = (2 * b * s * h + 2 * b * nk * h) * 2 + b * nk
+        bytes_bwd = (4 * b * s * h + 2 * b * nk * h) * 2 + (b * s * h + 2 * b * nk * h) * 2
+        print(json.dumps({"kernel": "xattn", "b": b, "s": s, "nk": nk, "heads": heads, "d": d,
+                          "fwd_us": round(fm * 1e3, 1), "fwd_GBs": round(bytes_fwd / fm / 1e6, 1),
+                          "bwd_us": round(bm * 1e3, 1), "bwd_GBs": round(bytes_bwd / bm / 1e6, 1)}), flush=True)
+
+
+def bench_rowops():
+    rows, hidden = 2560, 2048
+    x = torch.randn(rows, hidden, device="cuda").to(BF16)
+    g = torch.ones(hidden, device="cuda")
+    bta = torch.zeros(hidden, device="cuda")
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device="cuda")
+    rstd = torch.empty(rows, device="cuda")
+    med, _ = time_it(lambda: K.layernorm_fwd(x, g, bta, y, mean, rstd, 1e-5))
+    print(json.dumps({"kernel": "layernorm_fwd", "rows": rows, "hidden": hidden, "us": round(med * 1e3, 1),
+                      "GBs": round(2 * rows * hidden * 2 / med / 1e6, 1)}), flush=True)
+    dx = torch.empty_like(x)
+    dg = torch.empty(hidden, device="cuda")
+    db = torch.empty(hidden, device="cuda")
+    med, _ = time_it(lambda: K.layernorm_bwd(y, x, g, mean, rstd, x, dx, dg, db))
+    print(json.dumps({"kernel": "layernorm_bwd(+affine)", "rows": rows, "hidden": hidden, "us": round(med * 1e3, 1)}), flush=True)
+    out = torch.empty(8192, device="cuda")
+    f = torch.randn(rows, 8192, device="cuda").to(BF16)
+    med, _ = time_it(lambda: K.colsum(f, out))
+    print(json.dumps({"kernel": "colsum", "m": rows, "n": 8192, "us": round(med * 1e3, 1),
+                      "GBs": round(rows * 8192 * 2 / med / 1e6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
+    if "gemm" in which:
+        bench_gemm()
+    if "xattn" in which:
+        bench_xattn()
+    if "rowops" in which:
+        bench_rowops()
