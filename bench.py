@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- sections/sec of MMGL's neighbor-fusion training step on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--workload cfg2|cfg4|tiny]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one optimisation step of CrossAttentionModel on one synthetic WikiWeb2M-shaped micro-batch per GPU:
+frozen RoBERTa/CLIP encoders -> neighbor projections -> bank packing -> OPT-1.3B with 4 gated cross-attention
+layers -> shifted CE -> backward -> (DDP all-reduce) -> AdamW on the trainable parameters.  Dropout is ON (p=0.1,
+train mode) exactly as in the reference's loop.  Workload = BASELINE.json configs[1] (cfg2).
+
+Output: ONE JSON line (rank 0).  ``value`` = sections/s with the batch already resident in HBM; ``e2e`` = the same
+through the public nn.Module call with pinned HOST batches (H2D inside the timed region, loss read back every step);
+``roofline`` = achieved TFLOP/s of the dominant kernel (the tcgen05 GEMM) from per-launch CUDA events in an
+instrumented replica of the timed region; ``cpu_baseline`` = the oracle port of the same step on the host cores.
+
+``--impl reference`` times the reference algorithm's CPU port (oracle/cpu_step.py) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="sections per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: OPT-1.3B context=all neighbor_mode=embedding PEFT=flamingo, ViT-B/16, seq 512(+128), <=16 nbrs
+    "cfg2": dict(lm="opt-1.3b", text="roberta-base", visual="clip-vit-base-patch16", s_in=512, s_out=128, t=11, i=5,
+                 position_type="none"),
+    # configs[3]: <=32 neighbors + graph positional encodings (Laplacian)
+    "cfg4": dict(lm="opt-1.3b", text="roberta-base", visual="clip-vit-base-patch16", s_in=512, s_out=128, t=22, i=10,
+                 position_type="laplacian"),
+    # plumbing-size model for quick checks
+    "tiny": dict(lm="opt-125m", text="roberta-base", visual="clip-vit-base-patch16", s_in=128, s_out=128, t=3, i=2,
+                 position_type="none"),
+}
+
+
+def make_args(w):
+    return types.SimpleNamespace(
+        context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=4, n_visual_tokens=4,
+        model_name_or_path=w["lm"], text_model=w["text"], visual_model=w["visual"], max_output_length=w["s_out"],
+        freeze_lm=False, num_neighbor_layers=4, neighbor_layer_wise=None, lora_r=64, lora_alpha=1, lora_dropout=0.0,
+        position_type=w["position_type"], max_text_neighbors=w["t"], max_image_neighbors=w["i"], decoder_only=True)
+
+
+def spec_for(w, batch):
+    from mmgl_b200 import synth
+    return synth.BatchSpec(batch=batch, max_input_length=w["s_in"], max_output_length=w["s_out"], text_neighbors=w["t"],
+                           image_neighbors=w["i"], with_lpe=w["position_type"] == "laplacian",
+                           with_graph=w["position_type"] == "gnn")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(a, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mmgl_b200 import configs, synth
+    from oracle import cpu_step
+    args = make_args(w)
+    lm_cfg = configs.lm_config(w["lm"])
+    args.neighbor_layer_wise = lm_cfg.num_hidden_layers // args.num_neighbor_layers
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    p, cfg, tm, vm = cpu_step.build_cpu_reference(lm_cfg, configs.text_config(w["text"]), configs.visual_config(w["visual"]), args)
+    bsz = a.cpu_sample_batch
+    batches = [synth.make_batch(spec_for(w, bsz), seed=1234 + s) for s in range(2)]
+    sec, losses = cpu_step.time_steps(p, cfg, batches, tm, vm, a.steps, a.warmup, threads)
+    val = bsz / sec
+    sample = f"{bsz} section(s) per step: full fp32 train step (frozen encoders + LM fwd/bwd + AdamW), dropout off"
+    print(json.dumps({
+        "impl": "reference", "metric": "sections_per_sec", "value": val, "unit": "sections/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, w), "per_step_sections": bsz},
+        "cpu_baseline": {"value": val, "unit": "sections/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "sections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss_first_last": [losses[0], losses[-1]]}), flush=True)
+
+
+def workload_name(a, w):
+    return (f"{a.workload}: {w['lm']} context=all neighbor_mode=embedding PEFT=flamingo + {w['text']} + {w['visual']}, "
+            f"seq {w['s_in']}+{w['s_out']}, {w['t']} text + {w['i']} image neighbors x 4 tokens, "
+            f"position_type={w['position_type']}")
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a, w):
+    import torch.distributed as dist
+    from mmgl_b200 import _capi, modules, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mmgl_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.lib()  # fail loudly if the extension is missing
+
+    torch.manual_seed(1234)
+    args = make_args(w)
+    with torch.device(dev):
+        model = modules.CrossAttentionModel(args, tokenizer=None)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "gating" in n:
+                p.fill_(0.5)  # live gates: at the reference's init (0.0) the whole cross branch is multiplied by zero
+    modules.prepare_for_training(model, dev)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        find_unused_parameters=False)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+
+    spec = spec_for(w, a.batch)
+    host = [synth.make_batch(spec, seed=1234 + rank * 100 + s, pin=True) for s in range(2)]
+    resident = [synth.to_device(b, dev) for b in host]
+    h2d = synth.batch_nbytes(host[0])
+
+    def step_resident(i):
+        out = net(**resident[i % 2])
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return out.loss
+
+    def step_e2e(i):
+        batch = synth.to_device(host[i % 2], dev)       # H2D from pinned memory, inside the timed region
+        out = net(**batch)
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return float(out.loss)                          # D2H read of the step's loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, last
+
+    for i in range(max(3, a.warmup)):
+        step_resident(i)
+    if a.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(_physical_gpu_index(local))
+    if rank == 0:
+        sampler.start()
+    n0 = _capi.launch_count()
+    ms_res, loss_res = timed(step_resident, a.steps)
+    launches = _capi.launch_count() - n0
+    ms_e2e, loss_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # instrumented replica of the timed region: per-launch CUDA events on the launching stream
+    prof_steps = min(a.steps, 3)
+    _capi.profile_begin()
+    for i in range(prof_steps):
+        step_resident(i)
+    prof = _capi.profile_end()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    g = prof.get("gemm_tcgen05", {"launches": 0, "ms": 1e-9, "work": 0.0})
+    gemm_tf = g["work"] / (g["ms"] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_tcgen05_kernel (tcgen05.mma + TMA, all GEMMs of the step)", "bound": "tensor",
+                "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
+                "traffic": None, "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                "launches_per_step": g["launches"] / prof_steps, "ms_per_step": g["ms"] / prof_steps,
+                "share_of_step": g["ms"] / prof_steps / ms_res}
+    extra = {}
+    for name in ("xattn_fwd", "xattn_bwd"):
+        if name in prof:
+            x = prof[name]
+            gbs = x["work"] / (x["ms"] * 1e-3) / 1e9
+            extra[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                           "launches_per_step": x["launches"] / prof_steps, "ms_per_step": x["ms"] / prof_steps}
+    sections = a.batch * world
+    line = {
+        "metric": "sections_per_sec", "value": sections / (ms_res * 1e-3), "unit": "sections/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_res, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(a, w), "per_gpu_batch": a.batch, "global_batch": sections,
+                   "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "AdamW(fused) on fp32 master weights",
+                   "l2": "per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; two alternating batches"},
+        "e2e": {"value": sections / (ms_e2e * 1e-3), "unit": "sections/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
+        "roofline": roofline, "roofline_attention": extra, "clocks": clocks,
+        "loss": [float(loss_res), float(loss_e2e)],
+        "trainable_params": sum(p.numel() for p in params),
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, w)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, w):
+    """The oracle port of the same step on this box's host cores, on a bounded sample (rank 0, N=1 only)."""
+    from mmgl_b200 import configs, synth
+    from oracle import cpu_step
+    args = make_args(w)
+    lm_cfg = configs.lm_config(w["lm"])
+    args.neighbor_layer_wise = lm_cfg.num_hidden_layers // args.num_neighbor_layers
+    threads = os.cpu_count() or 1
+    t0 = time.time()
+    p, cfg, tm, vm = cpu_step.build_cpu_reference(lm_cfg, configs.text_config(w["text"]), configs.visual_config(w["visual"]), args)
+    bsz = a.cpu_sample_batch
+    batches = [synth.make_batch(spec_for(w, bsz), seed=99)]
+    sec, _ = cpu_step.time_steps(p, cfg, batches, tm, vm, steps=2, warmup=1, threads=threads)
+    return {"value": bsz / sec, "unit": "sections/s", "cores": threads, "kind": "port",
+            "sample": f"{bsz} section(s) per step x 2 timed steps (+1 warm-up): full fp32 train step on host cores "
+                      f"(frozen encoders + LM fwd/bwd + AdamW), dropout off; setup {time.time() - t0 - 3 * sec:.0f}s untimed",
+            "cpu_model": _cpu_model()}
+
+
+def _physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v.strip() for v in vis.split(",") if v.strip()]
+    if local < len(ids) and ids[local].isdigit():
+        return int(ids[local])
+    return local
+
+
+def _cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+if __name__ == "__main__":
+    a = parse()
+    w = WORKLOADS[a.workload]
+    if a.impl == "reference":
+        run_reference(a, w)
+    else:
+        run_ours(a, w)

@@ -115,6 +115,50 @@ def launch_count() -> int:
     return int(lib().mmgl_launch_count())
 
 
+# ------------------------------------------------------------------------------------------- per-launch timing
+# bench.py brackets every launch of the hot kernels with CUDA events on the launching (= torch current) stream to
+# report achieved FLOP/s / GB/s against the roofline.  Off by default: zero overhead on the normal path.
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {kernel: {"launches", "ms", "work"}}; work = algorithmic FLOPs (gemm) or bytes (xattn_*), see DESIGN.md."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, work, e0, e1 in rec:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+    return out
+
+
+class _Timed:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.name, self.work, self.e0, e1))
+        return False
+
+
 def _check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
@@ -183,7 +227,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.relu_mask, g.ldmask = _p(relu_mask), (_ld(relu_mask) if relu_mask is not None else 0)
     g.force_block_n = block_n
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
-    _check(lib().mmgl_gemm_bf16(C.byref(g), _stream()), "mmgl_gemm_bf16")
+    with _Timed("gemm_tcgen05", 2.0 * m * n * (k + int(g.k1))):
+        _check(lib().mmgl_gemm_bf16(C.byref(g), _stream()), "mmgl_gemm_bf16")
     return out
 
 
@@ -192,15 +237,19 @@ def xattn_fwd(q, k, v, mask, o, stats, batch, seq, nk, heads, head_dim):
     """q,o: [B*S, H] views; k,v: [B*Nk, H] views (may be halves of a fused K|V buffer); mask u8 [B,Nk]."""
     _req_cuda(q, k, v, mask, o, stats)
     assert mask.dtype == torch.uint8 and mask.is_contiguous() and stats.dtype == torch.float32
-    _check(lib().mmgl_xattn_fwd(_p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(o), _ld(o), _p(stats),
-                                batch, seq, nk, heads, head_dim, _stream()), "mmgl_xattn_fwd")
+    h = heads * head_dim
+    with _Timed("xattn_fwd", float(batch * ((2 * seq * h + 2 * nk * h) * 2 + nk))):
+        _check(lib().mmgl_xattn_fwd(_p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(mask), _p(o), _ld(o), _p(stats),
+                                    batch, seq, nk, heads, head_dim, _stream()), "mmgl_xattn_fwd")
 
 
 def xattn_bwd(d_o, q, k, v, o, stats, mask, dq, dk, dv, batch, seq, nk, heads, head_dim):
     _req_cuda(d_o, q, k, v, o, stats, mask, dq, dk, dv)
-    _check(lib().mmgl_xattn_bwd(_p(d_o), _ld(d_o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o),
-                                _p(stats), _p(mask), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
-                                batch, seq, nk, heads, head_dim, _stream()), "mmgl_xattn_bwd")
+    h = heads * head_dim
+    with _Timed("xattn_bwd", float(batch * ((4 * seq * h + 2 * nk * h) * 2 + (seq * h + 2 * nk * h) * 2 + nk))):
+        _check(lib().mmgl_xattn_bwd(_p(d_o), _ld(d_o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o),
+                                    _p(stats), _p(mask), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
+                                    batch, seq, nk, heads, head_dim, _stream()), "mmgl_xattn_bwd")
 
 
 # ------------------------------------------------------------------------------------------- layernorm
