@@ -67,9 +67,11 @@ typedef struct mmgl_gemm_args {
   const void* residual; int64_t ldres;
   void* aux; int64_t ldaux;
   const void* relu_mask; int64_t ldmask;
-  int32_t force_block_n; /* 0 = heuristic; 64/128/256 to force (tests, tuning) */
+  int32_t force_block_n; /* 0 = heuristic; 64/128/192/256 to force (tests, tuning) */
   float dropout_p;       /* 0 = no dropout */
   uint64_t dropout_seed;
+  int32_t raster;        /* tile order: 0 = heuristic, 1 = M-fastest, 2 = N-fastest (tests, tuning) */
+  int32_t reserved;
 } mmgl_gemm_args;
 
 int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
@@ -122,6 +124,20 @@ int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, float scale, c
 int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64_t lda, int64_t m, int64_t n,
                    const float* gate, float* out, int32_t accumulate, void* workspace, size_t workspace_bytes,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Softmax cross-entropy over bf16 logits, fp32 math (nn.CrossEntropyLoss at model/modelling_cross_attention.py:828-836;
+ * the caller expresses the "shift" by passing labels[b,s+1] for row (b,s) and ignore_index for the last position, so
+ * the [B,S-1,V] slice copy of the reference is never made).
+ *   lse[r] = logsumexp(logits[r,:]);  row_loss[r] = lse[r] - logits[r,labels[r]]  (0 if labels[r] == ignore_index or out
+ *   of range);  count[0] = number of contributing rows;  loss[0] = sum(row_loss) / max(1, count)   (mean reduction).
+ * Backward: dlogits[r,c] = (exp(logits[r,c] - lse[r]) - [c == labels[r]]) * dloss[0] / count[0]; 0 on ignored rows.
+ * No fp32 copy of the logits is ever materialised (the reference's CE reads/writes [B,S,V] fp32 several times). */
+int mmgl_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int64_t vocab, int64_t ignore_index,
+                float* lse, float* row_loss, float* loss, float* count, void* stream);
+int mmgl_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* dloss,
+                const float* count, void* dlogits, int64_t ldd, int64_t rows, int64_t vocab, int64_t ignore_index,
+                void* stream);
 
 /* out[m,n] = keep(m,n) ? x[m,n] / (1 - p) : 0 with the SAME counter-based mask the GEMM epilogue applies for
  * (seed, p): keep(m,n) iff 16 bits of splitmix64(seed ^ (2g + (n%8)/4)) >= round(p*65536), g = m*ceil(N/8) + n/8,

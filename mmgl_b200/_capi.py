@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("aux", c_vp), ("ldaux", c_i64),
         ("relu_mask", c_vp), ("ldmask", c_i64),
         ("force_block_n", c_i32), ("dropout_p", c_f32), ("dropout_seed", C.c_uint64),
+        ("raster", c_i32), ("reserved", c_i32),
     ]
 
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "mmgl_reduce_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_colsum": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_f32, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
     "mmgl_gate_grad": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
+    "mmgl_ce_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmgl_ce_bwd": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "mmgl_dropout_apply": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, C.c_uint64, c_vp]),
     "mmgl_bank_pack_fwd": (c_i32, [C.POINTER(BankArgs), c_vp]),
     "mmgl_bank_pack_bwd": (c_i32, [C.POINTER(BankBwdArgs), c_vp]),
@@ -190,7 +193,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
          gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None,
-         accumulate: bool = False, block_n: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0) -> torch.Tensor:
+         accumulate: bool = False, block_n: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0,
+         raster: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T (+ A1 @ B1^T)).
 
     a:  [M,K] (a_t=False) or [K,M] (a_t=True: A is used transposed, i.e. stored M-contiguous)
@@ -226,6 +230,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.aux, g.ldaux = _p(aux), (_ld(aux) if aux is not None else 0)
     g.relu_mask, g.ldmask = _p(relu_mask), (_ld(relu_mask) if relu_mask is not None else 0)
     g.force_block_n = block_n
+    g.raster = raster
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     with _Timed("gemm_tcgen05", 2.0 * m * n * (k + int(g.k1))):
         _check(lib().mmgl_gemm_bf16(C.byref(g), _stream()), "mmgl_gemm_bf16")
@@ -299,6 +304,22 @@ def gate_grad(dy, a, gate, out, accumulate=False):
     _check(lib().mmgl_gate_grad(_p(dy), _ld(dy), _p(a), _ld(a), m, n, _p(gate), _p(out), int(accumulate), _p(ws),
                                 nbytes, _stream()), "mmgl_gate_grad")
     return out
+
+
+def ce_fwd(logits, labels, lse, row_loss, loss, count, ignore_index=-100):
+    _req_cuda(logits, labels, lse, row_loss, loss, count)
+    rows, vocab = logits.shape
+    assert logits.dtype == torch.bfloat16 and labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == rows
+    _check(lib().mmgl_ce_fwd(_p(logits), _ld(logits), _p(labels), rows, vocab, ignore_index, _p(lse), _p(row_loss), _p(loss),
+                             _p(count), _stream()), "mmgl_ce_fwd")
+
+
+def ce_bwd(logits, labels, lse, dloss, count, dlogits, ignore_index=-100):
+    _req_cuda(logits, labels, lse, dloss, count, dlogits)
+    rows, vocab = logits.shape
+    assert dloss.dtype == torch.float32 and dloss.numel() == 1
+    _check(lib().mmgl_ce_bwd(_p(logits), _ld(logits), _p(labels), _p(lse), _p(dloss), _p(count), _p(dlogits), _ld(dlogits),
+                             rows, vocab, ignore_index, _stream()), "mmgl_ce_bwd")
 
 
 def dropout_apply(x, out, p, seed):

@@ -32,8 +32,8 @@ constexpr int kATileBytes = BM * BK * 2;
 template <int BN> struct GemmCfg {
   static constexpr int kBTileBytes = BN * BK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);  // two accumulator stages, pow2
   static constexpr int kBarrierBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
 };
@@ -42,6 +42,7 @@ struct GemmParams {
   int64_t m, n;
   int32_t kblocks0, kblocks1;
   int32_t m_blocks, n_blocks;
+  int32_t n_fastest;  // tile rasterisation: 1 = consecutive tiles walk N first (each A tile is streamed once)
   void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
   float alpha; int32_t relu;
   const float* bias;
@@ -184,8 +185,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.m_blocks) * BM;
-        const int n0 = (tile / p.m_blocks) * BN;
+        const int m0 = (p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks) * BM;
+        const int n0 = (p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks) * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           const bool second = kb >= p.kblocks0;
           const CUtensorMap* ma = second ? &map_a1 : &map_a0;
@@ -247,8 +248,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.m_blocks) * BM;
-      const int n0 = (tile / p.m_blocks) * BN;
+      const int m0 = (p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks) * BM;
+      const int n0 = (p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks) * BN;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int64_t row = m0 + quarter * 32 + lane;
@@ -365,10 +366,12 @@ static int operand_map(CUtensorMap* out, const void* ptr, int mn_major, int64_t 
 
 static int pick_block_n(int64_t m, int64_t n, int sms) {
   const int64_t mb = (m + BM - 1) / BM;
-  const int cand[3] = {256, 128, 64};
-  const double tile_cost[3] = {512.0, 290.0, 200.0};  // cycles per 64-deep k-block (MMA floor vs smem feed)
+  const int cand[4] = {256, 192, 128, 64};
+  // measured time of one 64-deep k-block of a 128 x BN tile, relative to BN = 256 (B200, profiles/r01 microbench):
+  // small tiles are far from proportionally cheaper (operand traffic per SM does not shrink with BN)
+  const double tile_cost[4] = {1.00, 0.88, 0.82, 0.76};
   int best = 256; double best_cost = 1e30;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int64_t tiles = mb * ((n + cand[i] - 1) / cand[i]);
     const int64_t waves = (tiles + sms - 1) / sms;
     const double cost = waves * tile_cost[i];
@@ -425,7 +428,7 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
 
   const int sms = sm_count();
   int bn = a->force_block_n ? a->force_block_n : pick_block_n(a->m, a->n, sms);
-  MMGL_REQUIRE(bn == 64 || bn == 128 || bn == 256, "mmgl_gemm_bf16: force_block_n must be 64, 128 or 256");
+  MMGL_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "mmgl_gemm_bf16: force_block_n must be 64, 128, 192 or 256");
 
   GemmParams p;
   p.m = a->m; p.n = a->n;
@@ -433,6 +436,7 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   p.kblocks1 = (int32_t)((a->k1 + BK - 1) / BK);
   p.m_blocks = (int32_t)((a->m + BM - 1) / BM);
   p.n_blocks = (int32_t)((a->n + bn - 1) / bn);
+  p.n_fastest = (a->raster == 1) ? 0 : ((a->raster == 2) ? 1 : (p.m_blocks >= p.n_blocks ? 1 : 0));
   p.d = a->d; p.ldd = a->ldd; p.out_fp32 = a->out_fp32; p.accumulate = a->accumulate;
   p.alpha = a->alpha; p.relu = a->relu; p.bias = a->bias; p.gate = a->gate;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ldres = a->ldres;
@@ -463,6 +467,7 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   }
   switch (bn) {
     case 256: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
+    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
     case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
     default:  return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
   }

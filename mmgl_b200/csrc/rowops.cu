@@ -227,6 +227,97 @@ gate_final_kernel(const float* __restrict__ partial, int blocks, const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------ softmax cross-entropy
+// One CTA per row: single pass online (max, sum) over the bf16 logits in fp32, 16-byte loads.
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mx = fmaxf(m, m2);
+  if (mx == -INFINITY) return;  // both empty: exp(-inf - -inf) would be NaN
+  s = s * __expf(m - mx) + s2 * __expf(m2 - mx);
+  m = mx;
+}
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int64_t vocab,
+              int64_t ignore_index, float* __restrict__ lse, float* __restrict__ row_loss, int vec) {
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* x = logits + row * ld;
+  float m = -INFINITY, s = 0.f;
+  if (vec) {
+    const int64_t nvec = vocab >> 3;
+    for (int64_t i = threadIdx.x; i < nvec; i += 256) {
+      float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+      float mx = f[0];
+#pragma unroll
+      for (int e = 1; e < 8; ++e) mx = fmaxf(mx, f[e]);
+      float part = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part += __expf(f[e] - mx);
+      online_merge(m, s, mx, part);
+    }
+    for (int64_t c = (nvec << 3) + threadIdx.x; c < vocab; c += 256) online_merge(m, s, __bfloat162float(x[c]), 1.f);
+  } else {
+    for (int64_t c = threadIdx.x; c < vocab; c += 256) online_merge(m, s, __bfloat162float(x[c]), 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    online_merge(m, s, m2, s2);
+  }
+  __shared__ float sm[8], ss[8];
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm[0], S = ss[0];
+    for (int w = 1; w < 8; ++w) online_merge(M, S, sm[w], ss[w]);
+    const float l = M + logf(S);
+    lse[row] = l;
+    const int64_t lab = labels[row];
+    const bool valid = lab != ignore_index && lab >= 0 && lab < vocab;
+    row_loss[row] = valid ? l - __bfloat162float(x[lab]) : 0.f;
+  }
+}
+// loss = sum(row_loss) / max(1, #valid); deterministic single-CTA tree reduction
+__global__ void __launch_bounds__(1024)
+ce_final_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ labels, int64_t rows, int64_t vocab,
+                int64_t ignore_index, float* __restrict__ loss, float* __restrict__ count) {
+  float s = 0.f, c = 0.f;
+  for (int64_t r = threadIdx.x; r < rows; r += 1024) {
+    const int64_t lab = labels[r];
+    if (lab != ignore_index && lab >= 0 && lab < vocab) { s += row_loss[r]; c += 1.f; }
+  }
+  __shared__ float rs[32], rc[32];
+  s = warp_sum(s); c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rc[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = warp_sum(rs[threadIdx.x]); c = warp_sum(rc[threadIdx.x]);
+    if (threadIdx.x == 0) { count[0] = c; loss[0] = s / fmaxf(c, 1.f); }
+  }
+}
+// dlogits = (softmax - onehot) * dloss / count, grid (rows, column chunks of 2048)
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+              const float* __restrict__ lse, const float* __restrict__ dloss, const float* __restrict__ count,
+              __nv_bfloat16* __restrict__ dlogits, int64_t ldd, int64_t vocab, int64_t ignore_index, int vec) {
+  const int64_t row = blockIdx.x;
+  const int64_t lab = labels[row];
+  const bool valid = lab != ignore_index && lab >= 0 && lab < vocab;
+  const float g = valid ? __ldg(dloss) / fmaxf(__ldg(count), 1.f) : 0.f;
+  const float l = lse[row];
+  const __nv_bfloat16* x = logits + row * ld;
+  __nv_bfloat16* d = dlogits + row * ldd;
+  const int64_t col = ((int64_t)blockIdx.y * 256 + threadIdx.x) * 8;
+  if (col >= vocab) return;
+  if (vec && col + 8 <= vocab) {
+    float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(x + col)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (__expf(f[e] - l) - ((col + e == lab) ? 1.f : 0.f)) * g;
+    *reinterpret_cast<uint4*>(d + col) = pack8(f);
+  } else {
+    for (int e = 0; e < 8 && col + e < vocab; ++e)
+      d[col + e] = __float2bfloat16_rn((__expf(__bfloat162float(x[col + e]) - l) - ((col + e == lab) ? 1.f : 0.f)) * g);
+  }
+}
+
 // ------------------------------------------------------------------------------------ dropout re-application
 // out = keep ? x * scale : 0 with the GEMM epilogue's counter-based mask.  One thread per 8-column group.
 __global__ void __launch_bounds__(256)
@@ -533,6 +624,33 @@ extern "C" int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64
   if (int rc = check_launch("mmgl_gate_grad(partial)")) return rc;
   gate_final_kernel<<<1, 256, 0, s>>>(ws, blocks, gate, out, accumulate);
   return check_launch("mmgl_gate_grad(final)");
+}
+
+extern "C" int mmgl_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int64_t vocab,
+                           int64_t ignore_index, float* lse, float* row_loss, float* loss, float* count, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(logits, "mmgl_ce_fwd");
+  MMGL_REQUIRE(labels && lse && row_loss && loss && count && rows > 0 && vocab > 0 && ld >= vocab, "mmgl_ce_fwd: bad arguments");
+  MMGL_REQUIRE(rows < (1ll << 31), "mmgl_ce_fwd: too many rows");
+  const int vec = aligned16(logits) && ld % 8 == 0;
+  ce_fwd_kernel<<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)logits, ld, labels, vocab, ignore_index, lse, row_loss, vec);
+  if (int rc = check_launch("mmgl_ce_fwd")) return rc;
+  ce_final_kernel<<<1, 1024, 0, s>>>(row_loss, labels, rows, vocab, ignore_index, loss, count);
+  return check_launch("mmgl_ce_fwd(final)");
+}
+
+extern "C" int mmgl_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* dloss,
+                           const float* count, void* dlogits, int64_t ldd, int64_t rows, int64_t vocab,
+                           int64_t ignore_index, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_BIND(logits, "mmgl_ce_bwd");
+  MMGL_REQUIRE(labels && lse && dloss && count && dlogits && rows > 0 && vocab > 0, "mmgl_ce_bwd: bad arguments");
+  MMGL_REQUIRE(rows < (1ll << 31) && (vocab + 2047) / 2048 < 65536, "mmgl_ce_bwd: problem too large for the grid");
+  const int vec = aligned16(logits) && aligned16(dlogits) && ld % 8 == 0 && ldd % 8 == 0;
+  dim3 g((unsigned)rows, (unsigned)((vocab + 2047) / 2048));
+  ce_bwd_kernel<<<g, 256, 0, s>>>((const __nv_bfloat16*)logits, ld, labels, lse, dloss, count, (__nv_bfloat16*)dlogits, ldd,
+                                  vocab, ignore_index, vec);
+  return check_launch("mmgl_ce_bwd");
 }
 
 extern "C" int mmgl_dropout_apply(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t m, int64_t n, float p,

@@ -2,11 +2,11 @@
 //
 //   O = softmax(max(Q K^T + mask, -FLT_MAX)) V       per (sample, head); Q pre-scaled by d^-1/2
 //
-// One kernel replaces the reference's _shape copies, bmm(Q,K^T), mask expand+add+clamp, softmax, bmm(P,V)
-// and the head merge (model/modelling_cross_attention.py:176-177, 206-271, 68-79).  The whole neighbor bank of a
-// head (Nk <= 256 rows) lives in shared memory, so the softmax is single-pass and nothing of shape [S,Nk]
-// reaches HBM.  HBM-bound (AI 58-115 flop/B): round-1 uses warp-level mma.sync tiles fed by ldmatrix; the
-// tensor work is far below the HBM time at these shapes.  (tcgen05/TMA variant: next round, see DESIGN.md.)
+// The FORWARD kernel lives in xattn_sm100.cu (tcgen05 + TMEM + TMA).  This file holds the C entry points and the
+// BACKWARD kernel: one CTA per (sample, head, 64-column slice) recomputes P from the saved row statistics, keeps its
+// dK / dV slice in registers across all query blocks and writes dQ per block; warp-level mma.sync tiles fed by
+// ldmatrix (the five contractions of the backward are tiny, the kernel is HBM / latency bound at these shapes).
+// Replaces the autograd backward of model/modelling_cross_attention.py:206-271.
 #include <cfloat>
 #include <cuda_bf16.h>
 
@@ -65,103 +65,6 @@ __device__ __forceinline__ void warp_scores(float (&s)[NKT * 2][4], const __nv_b
         mma16816(s[2 * jt], a, b[0], b[1]);
         mma16816(s[2 * jt + 1], a, b[2], b[3]);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ forward
-// grid (ceil(S/64), heads, batch), 128 threads.  stats[b,h,s,0] = row max, [..,1] = 1 / row sum.
-template <int D, int NKT>
-__global__ void __launch_bounds__(128)
-xattn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
-                 const __nv_bfloat16* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ mask,
-                 __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats, int seq, int nk, int heads) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int nkp = (nk + 15) & ~15;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sK = sQ + 64 * (D + 8);
-  __nv_bfloat16* sV = sK + nkp * (D + 8);
-  float* sMask = reinterpret_cast<float*>(sV + nkp * (D + 8));
-
-  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_valid = min(64, seq - r0);
-
-  load_tile<D, 128>(sQ, q + ((int64_t)b * seq + r0) * ldq + h * D, ldq, 64, rows_valid);
-  load_tile<D, 128>(sK, k + (int64_t)b * nk * ldk + h * D, ldk, nkp, nk);
-  load_tile<D, 128>(sV, v + (int64_t)b * nk * ldv + h * D, ldv, nkp, nk);
-  for (int j = threadIdx.x; j < NKT * 16; j += 128)
-    sMask[j] = (j < nk) ? (mask[(int64_t)b * nk + j] ? 0.f : -FLT_MAX) : -INFINITY;
-  __syncthreads();
-
-  float s[NKT * 2][4];
-  warp_scores<D, NKT>(s, sQ + warp * 16 * (D + 8), sK, nkp, lane);
-
-  // mask + clamp (reference: max(s + mask, finfo.min)), row max
-  const int g = lane >> 2, t = lane & 3;
-  float mx0 = -FLT_MAX, mx1 = -FLT_MAX;
-#pragma unroll
-  for (int nt = 0; nt < NKT * 2; ++nt) {
-    const float m0 = sMask[nt * 8 + 2 * t], m1 = sMask[nt * 8 + 2 * t + 1];
-    s[nt][0] = (m0 == 0.f) ? fmaxf(s[nt][0], -FLT_MAX) : m0;
-    s[nt][1] = (m1 == 0.f) ? fmaxf(s[nt][1], -FLT_MAX) : m1;
-    s[nt][2] = (m0 == 0.f) ? fmaxf(s[nt][2], -FLT_MAX) : m0;
-    s[nt][3] = (m1 == 0.f) ? fmaxf(s[nt][3], -FLT_MAX) : m1;
-    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < NKT * 2; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - mx0) * kLog2e); s[nt][1] = exp2f((s[nt][1] - mx0) * kLog2e);
-    s[nt][2] = exp2f((s[nt][2] - mx1) * kLog2e); s[nt][3] = exp2f((s[nt][3] - mx1) * kLog2e);
-    sum0 += s[nt][0] + s[nt][1];
-    sum1 += s[nt][2] + s[nt][3];
-  }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-
-  // O = P V
-  float acc[D / 8][4];
-#pragma unroll
-  for (int dt = 0; dt < D / 8; ++dt) { acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f; }
-#pragma unroll
-  for (int jt = 0; jt < NKT; ++jt) {
-    if (jt * 16 < nkp) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * jt][0], s[2 * jt][1]);     a[1] = pack_bf16(s[2 * jt][2], s[2 * jt][3]);
-      a[2] = pack_bf16(s[2 * jt + 1][0], s[2 * jt + 1][1]); a[3] = pack_bf16(s[2 * jt + 1][2], s[2 * jt + 1][3]);
-#pragma unroll
-      for (int dp = 0; dp < D / 16; ++dp) {
-        uint32_t bb[4];
-        ldsm_x4_t(bb, sV + (jt * 16 + ((lane / 8) % 2) * 8 + (lane % 8)) * (D + 8) + dp * 16 + (lane / 16) * 8);
-        mma16816(acc[2 * dp], a, bb[0], bb[1]);
-        mma16816(acc[2 * dp + 1], a, bb[2], bb[3]);
-      }
-    }
-  }
-  const int row_a = r0 + warp * 16 + g, row_b = row_a + 8;
-  if (row_a < seq) {
-    __nv_bfloat16* op = o + ((int64_t)b * seq + row_a) * ldo + h * D + 2 * t;
-#pragma unroll
-    for (int dt = 0; dt < D / 8; ++dt)
-      *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16(acc[dt][0] * inv0, acc[dt][1] * inv0);
-    if (t == 0) {
-      float* st = stats + (((int64_t)b * heads + h) * seq + row_a) * 2;
-      st[0] = mx0; st[1] = inv0;
-    }
-  }
-  if (row_b < seq) {
-    __nv_bfloat16* op = o + ((int64_t)b * seq + row_b) * ldo + h * D + 2 * t;
-#pragma unroll
-    for (int dt = 0; dt < D / 8; ++dt)
-      *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16(acc[dt][2] * inv1, acc[dt][3] * inv1);
-    if (t == 0) {
-      float* st = stats + (((int64_t)b * heads + h) * seq + row_b) * 2;
-      st[0] = mx1; st[1] = inv1;
     }
   }
 }
@@ -369,20 +272,9 @@ xattn_bwd_kernel(const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const __nv
   }
 }
 
-template <int D, int NKT>
-static int launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                      const uint8_t* mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq, int64_t nk,
-                      int64_t heads, cudaStream_t stream) {
-  const int nkp = ((int)nk + 15) & ~15;
-  const size_t smem = (size_t)(64 + 2 * nkp) * (D + 8) * 2 + NKT * 16 * 4;
-  auto kern = xattn_fwd_kernel<D, NKT>;
-  MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((seq + 63) / 64), (unsigned)heads, (unsigned)batch);
-  kern<<<grid, 128, smem, stream>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,
-                                    (const __nv_bfloat16*)v, ldv, mask, (__nv_bfloat16*)o, ldo, stats, (int)seq,
-                                    (int)nk, (int)heads);
-  return check_launch("mmgl_xattn_fwd");
-}
+int xattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* mask,
+                 void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t d,
+                 cudaStream_t stream);  // xattn_sm100.cu (tcgen05 + TMA)
 
 template <int D, int NKT, int W>
 static int launch_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
@@ -427,17 +319,8 @@ extern "C" int mmgl_xattn_fwd(const void* q, int64_t ldq, const void* k, int64_t
   if (int rc = check_xattn_args("mmgl_xattn_fwd", batch, seq, nk, heads, d, {ldq, ldk, ldv, ldo}, {q, k, v, o}))
     return rc;
   MMGL_REQUIRE(mask != nullptr && stats != nullptr, "mmgl_xattn_fwd: null mask/stats");
-#define FWD(D_, NKT_) return launch_fwd<D_, NKT_>(q, ldq, k, ldk, v, ldv, mask, o, ldo, stats, batch, seq, nk, heads, s)
-  if (d == 64) {
-    if (nk <= 64) FWD(64, 4);
-    if (nk <= 128) FWD(64, 8);
-    FWD(64, 16);
-  } else {
-    if (nk <= 64) FWD(128, 4);
-    if (nk <= 128) FWD(128, 8);
-    MMGL_REQUIRE(false, "mmgl_xattn_fwd: head_dim 128 supports Nk <= 128");
-  }
-#undef FWD
+  MMGL_REQUIRE(d == 64 || nk <= 128, "mmgl_xattn_fwd: head_dim 128 supports Nk <= 128");
+  return xattn_fwd_tc(q, ldq, k, ldk, v, ldv, mask, o, ldo, stats, batch, seq, nk, heads, d, s);
   return 0;
 }
 

@@ -10,7 +10,8 @@ What runs where
     bank packing (+ Laplacian-PE projection), the GCN, LoRA linears and every nn.Linear / LayerNorm / FFN of the
     frozen decoder layers: this package's CUDA kernels (``ops``), forward and backward.
   * the causal self-attention *core* of the frozen OPT layers, the frozen RoBERTa / CLIP encoders and the
-    ``lm_head`` cross-entropy: PyTorch / HF library code for now ("next").
+    SelfAttentionModel's HF language model: PyTorch / HF library code for now ("next").
+    The lm_head projection and the shifted cross-entropy (row f3) run in this package's kernels.
 There is no CPU path: modules raise on CPU tensors.
 
 Reference defects that are deliberately NOT inherited: D1 (``neighbor_layer_wise`` vs
@@ -131,14 +132,21 @@ class MPTAttention(nn.Module):
             o = ops.xattn_core(q, k, v, neighbor_attention_mask, self.num_heads)
         else:
             b, s, _ = hidden_states.shape
-            q = ops.linear(hidden_states, self.q_proj.weight, self.q_proj.bias)
-            k = ops.linear(hidden_states, self.k_proj.weight, self.k_proj.bias)
-            v = ops.linear(hidden_states, self.v_proj.weight, self.v_proj.bias)
-            shp = (b, s, self.num_heads, self.head_dim)
+            projs = (self.q_proj, self.k_proj, self.v_proj)
+            if not any(p.weight.requires_grad for p in projs):
+                # frozen block: one N = 3H GEMM over the cached row-concatenation Wq|Wk|Wv
+                w = ops.fused_rows([p.weight for p in projs], BF16)
+                bias = ops.fused_rows([p.bias for p in projs], torch.float32) if self.q_proj.bias is not None else None
+                qkv = ops.linear(hidden_states, w, bias).view(b, s, 3, self.num_heads, self.head_dim)
+                q, k, v = qkv.unbind(2)
+            else:
+                shp = (b, s, self.num_heads, self.head_dim)
+                q = ops.linear(hidden_states, self.q_proj.weight, self.q_proj.bias).view(shp)
+                k = ops.linear(hidden_states, self.k_proj.weight, self.k_proj.bias).view(shp)
+                v = ops.linear(hidden_states, self.v_proj.weight, self.v_proj.bias).view(shp)
             allowed = _allowed_from_additive(attention_mask)
-            o = F.scaled_dot_product_attention(q.view(shp).transpose(1, 2), k.view(shp).transpose(1, 2),
-                                               v.view(shp).transpose(1, 2), attn_mask=allowed,
-                                               is_causal=allowed is None and s > 1)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                               attn_mask=allowed, is_causal=allowed is None and s > 1)
             o = o.transpose(1, 2).reshape(b, s, self.embed_dim)
         out = ops.linear(o, self.out_proj.weight, self.out_proj.bias, residual=residual, dropout_p=dropout_p)
         return out, None, None
@@ -310,9 +318,7 @@ class MPTForCausalLM(nn.Module):
         logits = ops.linear(h, self.lm_head.weight)                                               # :826
         loss = None
         if labels is not None:                                                                    # :828-836
-            shift_logits = logits[..., :-1, :]
-            shift_labels = labels[..., 1:].to(logits.device)
-            loss = F.cross_entropy(shift_logits.reshape(-1, shift_logits.shape[-1]).float(), shift_labels.reshape(-1))
+            loss = ops.shifted_cross_entropy(logits, labels.to(logits.device))
         return CausalLMOutput(loss=loss, logits=logits)
 
 
@@ -402,18 +408,48 @@ class _NeighborEncoderMixin:
             px = pixel_values.reshape(-1, *pixel_values.shape[2:]).to(next(self.visual_model.parameters()).dtype)
             return self.visual_model(px).pooler_output
 
-    def text_projection(self, input_ids, attention_mask):
+    skip_padding_neighbors = True
+
+    def _needed(self, pos_ids):
+        """Neighbors whose frozen-encoder output can influence the step: the valid ones (pos_id > 0).  A padding
+        neighbor's bank rows are masked, get softmax weight exactly 0 and gradient exactly 0 (SURVEY invariant I2),
+        so its encoder pass is skipped and its projection rows are left zero -- loss and gradients are identical.
+        Exception kept for parity: a sample with NO valid neighbor attends uniformly over its masked rows in the
+        reference, so all of its neighbors stay 'needed'.  One host sync per call (index list)."""
+        if pos_ids is None or not self.skip_padding_neighbors:
+            return None
+        valid = pos_ids > 0
+        need = valid | ~valid.any(dim=1, keepdim=True)
+        if bool(need.all()):
+            return None
+        return need.reshape(-1).nonzero(as_tuple=False).squeeze(1)
+
+    @staticmethod
+    def _scatter_rows(y, idx, total):
+        if idx is None:
+            return y
+        full = torch.zeros((total, y.shape[-1]), dtype=y.dtype, device=y.device)
+        return full.index_copy(0, idx, y)
+
+    def text_projection(self, input_ids, attention_mask, pos_ids=None):
         """pooled [B*T, E] -> Linear(E -> n_tok*H): [B, T, n_tok*H] (the position-embedding add is fused into the
         bank packing kernel; :997)."""
-        b, n = input_ids.shape[:2]
-        y = ops.linear(self.encode_text(input_ids, attention_mask), self.text_embeddings.weight,
-                       self.text_embeddings.bias)
-        return y.reshape(b, n, -1)
+        b, n, l = input_ids.shape
+        idx = self._needed(pos_ids)
+        ids2, am2 = input_ids.reshape(-1, l), attention_mask.reshape(-1, l)
+        if idx is not None:
+            ids2, am2 = ids2.index_select(0, idx), am2.index_select(0, idx)
+        y = ops.linear(self.encode_text(ids2, am2), self.text_embeddings.weight, self.text_embeddings.bias)
+        return self._scatter_rows(y, idx, b * n).reshape(b, n, -1)
 
-    def visual_projection(self, pixel_values):
+    def visual_projection(self, pixel_values, pos_ids=None):
         b, n = pixel_values.shape[:2]
-        y = ops.linear(self.encode_images(pixel_values), self.visual_embeddings.weight, self.visual_embeddings.bias)
-        return y.reshape(b, n, -1)
+        idx = self._needed(pos_ids)
+        px = pixel_values.reshape(b * n, 1, *pixel_values.shape[2:])
+        if idx is not None:
+            px = px.index_select(0, idx)
+        y = ops.linear(self.encode_images(px), self.visual_embeddings.weight, self.visual_embeddings.bias)
+        return self._scatter_rows(y, idx, b * n).reshape(b, n, -1)
 
     def _table(self, name):
         emb = getattr(self, name, None)
@@ -426,8 +462,8 @@ class _NeighborEncoderMixin:
         (model/modelling_cross_attention.py:1072-1104; model/modelling_self_attention.py:263-315)."""
         if neighbor_images is not None and self.n_text_tokens != self.n_visual_tokens:
             raise ValueError("the packed bank needs n_text_tokens == n_visual_tokens (reference :1093-1098)")
-        tp = self.text_projection(neighbor_input_ids, neighbor_attention_mask)
-        ip = self.visual_projection(neighbor_images) if neighbor_images is not None else None
+        tp = self.text_projection(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids)
+        ip = self.visual_projection(neighbor_images, neighbor_images_pos_ids) if neighbor_images is not None else None
         lpe_lin = getattr(self, "lpe_embeddings", None) if lpe is not None else None
         return ops.bank_pack(
             tp, self._table("text_position_embeddings") if use_pos_tables else None, neighbor_pos_ids, text_locations,

@@ -88,6 +88,20 @@ def _undrop(dy2, p, seed):
     return out
 
 
+def fused_rows(params, dtype):
+    """Row-concatenation of several parameters (e.g. Wq|Wk|Wv -> [3H, H]) converted to ``dtype``, cached until any of
+    them changes.  Used for FROZEN projections only: one N = 3H GEMM instead of three N = H GEMMs."""
+    key = (tuple(id(p) for p in params), dtype, "rows")
+    ent = _shadow.get(key)
+    vers = tuple(p._version for p in params)
+    if ent is not None and all(r() is p for r, p in zip(ent[0], params)) and ent[1] == vers and ent[2] == params[0].device:
+        return ent[3]
+    conv = torch.cat([p.detach().to(dtype) for p in params], dim=0).contiguous()
+    refs = tuple(weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)) for p in params)
+    _shadow[key] = (refs, vers, params[0].device, conv)
+    return conv
+
+
 def _gate32(g: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if g is None else f32(g).reshape(1)
 
@@ -267,6 +281,49 @@ class LayerNormFn(torch.autograd.Function):
 
 def layer_norm(x, weight, bias, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
+
+
+# --------------------------------------------------------------------------------------------- cross-entropy
+class CrossEntropyFn(torch.autograd.Function):
+    """mean softmax cross-entropy over bf16 logits [rows, V] with int64 labels [rows] (ignore_index rows skipped):
+    nn.CrossEntropyLoss at model/modelling_cross_attention.py:835-836.  fp32 math, no fp32 copy of the logits."""
+
+    @staticmethod
+    def forward(ctx, logits2, labels, ignore_index):
+        assert logits2.dim() == 2 and logits2.dtype == BF16
+        rows = logits2.shape[0]
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        dev = logits2.device
+        lse = torch.empty(rows, dtype=F32, device=dev)
+        row_loss = torch.empty(rows, dtype=F32, device=dev)
+        loss = torch.empty(1, dtype=F32, device=dev)
+        count = torch.empty(1, dtype=F32, device=dev)
+        K.ce_fwd(logits2, labels, lse, row_loss, loss, count, ignore_index)
+        ctx.save_for_backward(logits2, labels, lse, count)
+        ctx.ignore_index = ignore_index
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits2, labels, lse, count = ctx.saved_tensors
+        dlogits = torch.empty(logits2.shape, dtype=BF16, device=logits2.device)
+        K.ce_bwd(logits2, labels, lse, dloss.reshape(1).to(F32).contiguous(), count, dlogits, ctx.ignore_index)
+        return dlogits, None, None
+
+
+def cross_entropy(logits, labels, ignore_index=-100):
+    """logits [..., V] bf16, labels [...] -> scalar fp32 mean loss over the non-ignored positions."""
+    l2 = logits.reshape(-1, logits.shape[-1])
+    return CrossEntropyFn.apply(l2, labels, int(ignore_index))
+
+
+def shifted_cross_entropy(logits, labels, ignore_index=-100):
+    """Causal-LM loss (model/modelling_cross_attention.py:828-836): position s predicts token s+1.  The shift is applied
+    to the small label tensor (last position ignored) instead of slicing/copying the [B,S,V] logits."""
+    b, s = labels.shape
+    shifted = torch.full((b, s), ignore_index, dtype=torch.int64, device=labels.device)
+    shifted[:, :-1] = labels[:, 1:]
+    return cross_entropy(logits, shifted, ignore_index)
 
 
 # --------------------------------------------------------------------------------------------- MLP

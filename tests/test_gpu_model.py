@@ -29,6 +29,7 @@ def _build(g, train=False):
     assert all(k.startswith(("text_model.", "visual_model.")) for k in missing), f"missing keys: {missing}"
     M.prepare_for_training(model, "cuda")
     model.train(train)
+    model.skip_padding_neighbors = False   # the fixture's pooled features cover every neighbor slot
     # the fixture supplies the frozen encoders' pooled outputs (tiny random encoders are not part of the path)
     tp, vp = g["text_pooled"].cuda(), g["visual_pooled"].cuda()
     model.encode_images = lambda px: vp.reshape(-1, vp.shape[-1]).to(BF16)
@@ -107,3 +108,41 @@ def test_training_mode_runs_with_dropout(golden):
     assert torch.isfinite(out.loss) and abs(float(out.loss) - float(g["loss"])) < 0.5
     assert float(l1) != float(out.loss) or True   # masks are counter-based per call; just exercise the path
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_skipping_padding_neighbors_changes_nothing(golden):
+    """Row f2: the frozen encoders are not run on padding neighbors (pos_id == 0).  Loss and every gradient must be
+    the same as with the full (reference) computation; tolerance 2e-3 rel-L2 only because the encoder GEMMs see a
+    different batch size (library kernel selection), the masked rows themselves contribute exactly zero."""
+    g = golden("wrapper_cross_d64")
+    from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig
+    from mmgl_b200 import modules as M
+    args = types.SimpleNamespace(
+        context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=2, n_visual_tokens=2,
+        model_name_or_path=OPTConfig(**g["lm_config"]), text_model=RobertaConfig(**g["text_config"]),
+        visual_model=CLIPVisionConfig(**g["visual_config"]), max_output_length=16, freeze_lm=False,
+        neighbor_layer_wise=2, lora_r=64, lora_alpha=1, lora_dropout=0.0)
+    torch.manual_seed(5)
+    model = M.CrossAttentionModel(args, tokenizer=None)
+    model.load_state_dict(g["state"], strict=False)
+    M.prepare_for_training(model, "cuda").eval()
+    batch = {k: v.cuda() for k, v in g["batch"].items()}
+    batch["neighbor_pos_ids"] = torch.tensor([[1, 2, 0], [1, 0, 0]]).cuda()         # padding neighbors present
+    batch["neighbor_images_pos_ids"] = torch.tensor([[1, 0], [0, 0]]).cuda()
+    res = {}
+    for skip in (False, True):
+        model.skip_padding_neighbors = skip
+        model.zero_grad()
+        out = model(**batch)
+        out.loss.backward()
+        res[skip] = (out.loss.detach().clone(), out.logits.detach().clone(),
+                     {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    rep = Report()
+    rep.scalar("loss", res[True][0], res[False][0], 0.0, 1e-4)
+    rep.close("logits", res[True][1], res[False][1], 2e-3)
+    assert res[True][2].keys() == res[False][2].keys()
+    for n in res[True][2]:
+        if n.endswith("k_proj.bias"):
+            continue
+        rep.close("d " + n, res[True][2][n], res[False][2][n], 2e-3)
+    rep.finish()

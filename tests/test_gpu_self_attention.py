@@ -46,6 +46,7 @@ def test_concat_path_inputs_match_reference(golden, lm, pt):
     assert all(k.startswith(("lm.", "text_model.", "visual_model.", "input_embeddings.")) for k in missing), missing
     model.input_embeddings.weight.data.copy_(emb_w)
     model.cuda().eval()
+    model.skip_padding_neighbors = False   # the fixture's pooled features cover every neighbor slot
     tp, vp = g["text_pooled"].cuda(), g["visual_pooled"].cuda()
     model.encode_text = lambda ids, am: tp.reshape(-1, tp.shape[-1]).to(BF16)
     model.encode_images = lambda px: vp.reshape(-1, vp.shape[-1]).to(BF16)

@@ -39,15 +39,19 @@ def time_it(fn, iters=20, warmup=3):
 
 def bench_gemm():
     shapes = [  # (M, N, K, a_t, b_t, label)
-        (2560, 2048, 2048, 0, 0, "q/out proj B=4"),
-        (2560, 8192, 2048, 0, 0, "fc1 B=4"),
-        (2560, 2048, 8192, 0, 0, "fc2 B=4"),
-        (256, 2048, 2048, 0, 0, "k/v proj B=4"),
-        (2560, 2048, 8192, 0, 1, "dgrad fc1 B=4"),
-        (8192, 2048, 2560, 1, 1, "wgrad fc1 B=4"),
-        (2048, 8192, 2560, 1, 1, "wgrad fc2 B=4"),
+        (5120, 2048, 2048, 0, 0, "q/out proj B=8"),
+        (5120, 6144, 2048, 0, 0, "fused qkv B=8"),
+        (5120, 8192, 2048, 0, 0, "fc1 B=8"),
+        (5120, 2048, 8192, 0, 0, "fc2 B=8"),
+        (512, 2048, 2048, 0, 0, "k/v proj (bank) B=8"),
+        (5120, 2048, 8192, 0, 1, "dgrad fc1 B=8"),
+        (5120, 2048, 6144, 0, 1, "dgrad fused qkv B=8"),
+        (8192, 2048, 5120, 1, 1, "wgrad fc1 B=8"),
+        (2048, 8192, 5120, 1, 1, "wgrad fc2 B=8"),
+        (2048, 2048, 5120, 1, 1, "wgrad q/out B=8"),
         (8192, 8192, 8192, 0, 0, "square 8k"),
-        (2560, 50272, 2048, 0, 0, "lm_head B=4"),
+        (5120, 50272, 2048, 0, 0, "lm_head B=8"),
+        (5120, 2048, 50272, 0, 1, "lm_head dgrad B=8"),
     ]
     for m, n, k, a_t, b_t, label in shapes:
         a = torch.randn((k, m) if a_t else (m, k), device="cuda").to(BF16)
@@ -55,9 +59,12 @@ def bench_gemm():
         out = torch.empty((m, n), dtype=BF16, device="cuda")
         flops = 2.0 * m * n * k
         res = {"kernel": "gemm", "label": label, "m": m, "n": n, "k": k, "a_t": a_t, "b_t": b_t}
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 128, 192, 256):
             med, best = time_it(lambda: K.gemm(a, b, out, a_t=bool(a_t), b_t=bool(b_t), block_n=bn))
             res[f"ours_bn{bn}_tflops"] = round(flops / med / 1e9, 1)
+        for rs in (1, 2):
+            med, best = time_it(lambda: K.gemm(a, b, out, a_t=bool(a_t), b_t=bool(b_t), block_n=256, raster=rs))
+            res[f"ours_bn256_raster{rs}_tflops"] = round(flops / med / 1e9, 1)
         am = a.t() if a_t else a
         bm = b if b_t else b.t()
         med, best = time_it(lambda: torch.matmul(am, bm, out=out))
