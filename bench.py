@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
@@ -258,6 +259,14 @@ def run_ours(a, w):
         step_resident(i)
     prof = _capi.profile_end()
 
+    if a.gemm_table and rank == 0:
+        _capi.profile_begin(detail=True)
+        step_resident(0)
+        detail = _capi.profile_end()
+        tot = sum(v["ms"] for v in detail.values())
+        for name, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
+            tf = v["work"] / (v["ms"] * 1e-3) / 1e12 if name.startswith("gemm") else 0.0
+            print(f"{v['ms']:8.3f} ms {100 * v['ms'] / tot:5.1f}%  x{v['launches']:3d}  {tf:7.1f} TF/s  {name}", file=sys.stderr)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -71,7 +71,7 @@ typedef struct mmgl_gemm_args {
   float dropout_p;       /* 0 = no dropout */
   uint64_t dropout_seed;
   int32_t raster;        /* tile order: 0 = heuristic, 1 = M-fastest, 2 = N-fastest (tests, tuning) */
-  int32_t reserved;
+  int32_t pair;          /* CTA-pair (cta_group::2, 256-row tiles) kernel: 0 = heuristic, 1 = never, 2 = always */
 } mmgl_gemm_args;
 
 int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
@@ -80,8 +80,8 @@ int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
  * Fused cross-attention core:  O = softmax(max(Q K^T + mask, FLT_MIN_FINITE)) V   per (sample, head).
  * Q [B,S,nh*d] already scaled by d^-1/2 (done in the q_proj epilogue); K,V [B,Nk,nh*d] (may be the two
  * halves of one fused K|V projection: pass ldk = ldv = 2*nh*d); mask [B,Nk] bytes (1 = attend).
- * Head split/merge, mask expansion, clamp, fp32 softmax and both contractions are fused; no [B,nh,S,Nk]
- * tensor ever reaches HBM.  stats [B,nh,S,2] fp32 = (row max, 1 / row sum) is saved for backward
+ * Head split/merge, mask expansion, clamp, fp32 softmax and both contractions (tcgen05.mma, TMEM accumulators,
+ * TMA-staged Q / K / V tiles) are fused; no [B,nh,S,Nk] tensor ever reaches HBM.  stats [B,nh,S,2] fp32 = (row max, 1 / row sum) is saved for backward
  * (log-sum-exp = stats[0] - log(stats[1])).  d in {64,128}; Nk <= 256 forward (128 when d = 128).
  * Replaces model/modelling_cross_attention.py:176-177,206-271 and :68-79 (_expand_mask).
  */
@@ -89,7 +89,8 @@ int mmgl_xattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const
                    const uint8_t* mask, void* o, int64_t ldo, float* stats,
                    int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
 
-/* Backward of the above: dQ [B,S,nh*d], dK/dV [B,Nk,nh*d] (lddk = lddv = 2*nh*d for a fused d(K|V)).  Nk <= 128.
+/* Backward of the above (five tcgen05 contractions per 128-query tile, dK / dV accumulated in TMEM across tiles):
+ * dQ [B,S,nh*d], dK/dV [B,Nk,nh*d] (lddk = lddv = 2*nh*d for a fused d(K|V)).  Nk <= 128.
  * Reference artifact reproduced on purpose: the clamp torch.max(S + mask, finfo.min) (:225-228) ties on every masked
  * entry and torch splits a tie's gradient in half, so dS of a masked entry is 0.5 * P (dP - delta).  It is only
  * non-zero for a sample whose neighbors are ALL masked (P uniform); everywhere else P = 0 on masked entries. */

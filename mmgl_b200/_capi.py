@@ -35,7 +35,7 @@ class GemmArgs(C.Structure):
         ("aux", c_vp), ("ldaux", c_i64),
         ("relu_mask", c_vp), ("ldmask", c_i64),
         ("force_block_n", c_i32), ("dropout_p", c_f32), ("dropout_seed", C.c_uint64),
-        ("raster", c_i32), ("reserved", c_i32),
+        ("raster", c_i32), ("pair", c_i32),
     ]
 
 
@@ -122,11 +122,13 @@ def launch_count() -> int:
 # bench.py brackets every launch of the hot kernels with CUDA events on the launching (= torch current) stream to
 # report achieved FLOP/s / GB/s against the roofline.  Off by default: zero overhead on the normal path.
 _prof = None
+_prof_detail = False
 
 
-def profile_begin():
-    global _prof
+def profile_begin(detail: bool = False):
+    global _prof, _prof_detail
     _prof = []
+    _prof_detail = detail
 
 
 def profile_end():
@@ -194,7 +196,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
          gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None,
          accumulate: bool = False, block_n: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0,
-         raster: int = 0) -> torch.Tensor:
+         raster: int = 0, pair: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T (+ A1 @ B1^T)).
 
     a:  [M,K] (a_t=False) or [K,M] (a_t=True: A is used transposed, i.e. stored M-contiguous)
@@ -231,8 +233,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.relu_mask, g.ldmask = _p(relu_mask), (_ld(relu_mask) if relu_mask is not None else 0)
     g.force_block_n = block_n
     g.raster = raster
+    g.pair = pair
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
-    with _Timed("gemm_tcgen05", 2.0 * m * n * (k + int(g.k1))):
+    with _Timed(f"gemm_tcgen05 m={m} n={n} k={k + int(g.k1)} at={int(a_t)} bt={int(b_t)}" if _prof_detail else "gemm_tcgen05",
+                2.0 * m * n * (k + int(g.k1))):
         _check(lib().mmgl_gemm_bf16(C.byref(g), _stream()), "mmgl_gemm_bf16")
     return out
 

@@ -28,6 +28,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 192;      // 6 warps
 constexpr int kATileBytes = BM * BK * 2;
+// per-k-block time of one wave of CTA-pair tiles relative to one wave of single-CTA 128 x 256 tiles (B200, tools/microbench.py:
+// fc1 1410 vs 1300 TFLOP/s at BN = 256; the 256 x 128 pair tile is L2-ingest bound again)
+constexpr double kPairCost256 = 0.92;
+constexpr double kPairCost128 = 1.50;
 
 template <int BN> struct GemmCfg {
   static constexpr int kBTileBytes = BN * BK * 2;
@@ -43,6 +47,7 @@ struct GemmParams {
   int32_t kblocks0, kblocks1;
   int32_t m_blocks, n_blocks;
   int32_t n_fastest;  // tile rasterisation: 1 = consecutive tiles walk N first (each A tile is streamed once)
+  int32_t m_blocks_pair;  // CTA-pair kernel: number of 256-row tiles
   void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
   float alpha; int32_t relu;
   const float* bias;
@@ -288,6 +293,168 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------ CTA-pair (cta_group::2) variant
+// Two CTAs on the two SMs of a TPC cooperate on a 256 x BN tile: each loads its own 128 rows of A and HALF of the
+// B tile, one thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives its own 128
+// accumulator rows.  Per SM and k-block the operand ingest drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what
+// bounds the single-CTA kernel (L2 -> SM bandwidth), so the pair kernel is tensor-pipe bound at BN = 256.
+template <int BN> struct PairCfg {
+  static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;   // per CTA
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+};
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                         const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                         const GemmParams p) {
+  using Cfg = PairCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BNH = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.m_blocks_pair * p.n_blocks;
+  const int kblocks = p.kblocks0 + p.kblocks1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b0);
+    if (p.kblocks1 > 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_b1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }  // 4 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+        const int mt = p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks_pair;
+        const int nt = p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks_pair;
+        const int m0 = mt * 256 + (int)rank * BM;
+        const int n0 = nt * BN + (int)rank * BNH;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const bool second = kb >= p.kblocks0;
+          const CUtensorMap* ma = second ? &map_a1 : &map_a0;
+          const CUtensorMap* mb = second ? &map_b1 : &map_b0;
+          const int k0 = (second ? kb - p.kblocks0 : kb) * BK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kATileBytes;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, ma, &full_bar[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(sa, ma, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BNH / 64; ++j) tma_load_2d_pair(sb + j * 8192, mb, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(sb, mb, &full_bar[stage], k0, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the LEADER CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);   // frees this stage in BOTH CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[as]);        // accumulator complete -> epilogue warps of BOTH CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..5) of both CTAs: own 128 accumulator rows =====================
+    const int quarter = warp & 3;
+    const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+      const int mt = p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks_pair;
+      const int nt = p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks_pair;
+      const int n0 = nt * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * 256 + rank * BM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t col0 = n0 + c * 32;
+        if (row < p.m && col0 < p.n) {
+          if (p.vec_ok && col0 + 32 <= p.n) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still signal its barriers or read its TMEM / smem
+  if (warp == 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+}
+
 // --------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -380,6 +547,33 @@ static int pick_block_n(int64_t m, int64_t n, int sms) {
   return best;
 }
 
+// CTA-pair selection: compare estimated time (waves x per-tile cost); costs relative to one k-block of a 128 x 256
+// single-CTA tile, measured on B200 (tools/microbench.py).  Returns true and sets *bn when the pair kernel wins.
+static bool pick_pair(int64_t m, int64_t n, int sms, int* bn) {
+  if (m < 256) return false;
+  const int single_cand[4] = {256, 192, 128, 64};
+  const double single_cost[4] = {1.00, 0.88, 0.82, 0.76};
+  const int64_t mb = (m + BM - 1) / BM;
+  double best_single = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int64_t tiles = mb * ((n + single_cand[i] - 1) / single_cand[i]);
+    const double c = (double)((tiles + sms - 1) / sms) * single_cost[i];
+    if (c < best_single) best_single = c;
+  }
+  const int pair_cand[2] = {256, 128};
+  const double pair_cost[2] = {kPairCost256, kPairCost128};   // one k-block of a 256 x BN pair tile
+  const int pairs = sms / 2;
+  const int64_t mb2 = (m + 255) / 256;
+  double best_pair = 1e30; int best_bn = 256;
+  for (int i = 0; i < 2; ++i) {
+    const int64_t tiles = mb2 * ((n + pair_cand[i] - 1) / pair_cand[i]);
+    const double c = (double)((tiles + pairs - 1) / pairs) * pair_cost[i];
+    if (c < best_pair) { best_pair = c; best_bn = pair_cand[i]; }
+  }
+  if (best_pair < best_single * 0.97) { *bn = best_bn; return true; }
+  return false;
+}
+
 template <int BN, int A_MN, int B_MN>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
                        const GemmParams& p, cudaStream_t stream) {
@@ -397,6 +591,48 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUten
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a0, b0, a1, b1, p);
   return check_launch("mmgl_gemm_bf16");
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
+                            const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_pair_kernel<BN, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<BN>::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(pair, smem=%d) failed: %s", PairCfg<BN>::kSmemBytes, cudaGetErrorString(attr_err));
+    return 3;
+  }
+  const int tiles = p.m_blocks_pair * p.n_blocks;
+  const int pairs = sm_count() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = PairCfg<BN>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, p);
+  if (e != cudaSuccess) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    set_error("mmgl_gemm_bf16(pair): launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return check_launch("mmgl_gemm_bf16(pair)");
+}
+
+template <int BN>
+static int dispatch_major_pair(int a_mn, int b_mn, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
+                               const CUtensorMap& b1, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm_pair<BN, 0, 0>(a0, b0, a1, b1, p, s);
+  if (!a_mn && b_mn) return launch_gemm_pair<BN, 0, 1>(a0, b0, a1, b1, p, s);
+  if (a_mn && !b_mn) return launch_gemm_pair<BN, 1, 0>(a0, b0, a1, b1, p, s);
+  return launch_gemm_pair<BN, 1, 1>(a0, b0, a1, b1, p, s);
 }
 
 template <int BN>
@@ -430,12 +666,22 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   int bn = a->force_block_n ? a->force_block_n : pick_block_n(a->m, a->n, sms);
   MMGL_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "mmgl_gemm_bf16: force_block_n must be 64, 128, 192 or 256");
 
+  // CTA-pair kernel: 256 x {128,256} tiles.  pair = 0: heuristic, 1: never, 2: always (tests, tuning)
+  bool use_pair = false;
+  if (a->pair == 2) {
+    use_pair = true;
+    if (bn != 128) bn = 256;
+  } else if (a->pair == 0 && a->force_block_n == 0) {
+    use_pair = pick_pair(a->m, a->n, sms, &bn);
+  }
+
   GemmParams p;
   p.m = a->m; p.n = a->n;
   p.kblocks0 = (int32_t)((a->k0 + BK - 1) / BK);
   p.kblocks1 = (int32_t)((a->k1 + BK - 1) / BK);
   p.m_blocks = (int32_t)((a->m + BM - 1) / BM);
   p.n_blocks = (int32_t)((a->n + bn - 1) / bn);
+  p.m_blocks_pair = (int32_t)((a->m + 255) / 256);
   p.n_fastest = (a->raster == 1) ? 0 : ((a->raster == 2) ? 1 : (p.m_blocks >= p.n_blocks ? 1 : 0));
   p.d = a->d; p.ldd = a->ldd; p.out_fp32 = a->out_fp32; p.accumulate = a->accumulate;
   p.alpha = a->alpha; p.relu = a->relu; p.bias = a->bias; p.gate = a->gate;
@@ -458,12 +704,17 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   CUtensorMap ma0, mb0, ma1, mb1;
   int rc;
   if ((rc = operand_map(&ma0, a->a0, a->a_mn_major, a->m, a->k0, a->lda0, BM))) return rc;
-  if ((rc = operand_map(&mb0, a->b0, a->b_mn_major, a->n, a->k0, a->ldb0, bn))) return rc;
+  const int b_box = use_pair ? bn / 2 : bn;
+  if ((rc = operand_map(&mb0, a->b0, a->b_mn_major, a->n, a->k0, a->ldb0, b_box))) return rc;
   if (a->k1 > 0) {
     if ((rc = operand_map(&ma1, a->a1, a->a_mn_major, a->m, a->k1, a->lda1, BM))) return rc;
-    if ((rc = operand_map(&mb1, a->b1, a->b_mn_major, a->n, a->k1, a->ldb1, bn))) return rc;
+    if ((rc = operand_map(&mb1, a->b1, a->b_mn_major, a->n, a->k1, a->ldb1, b_box))) return rc;
   } else {
     ma1 = ma0; mb1 = mb0;
+  }
+  if (use_pair) {
+    if (bn == 256) return dispatch_major_pair<256>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
+    return dispatch_major_pair<128>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);
   }
   switch (bn) {
     case 256: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma0, mb0, ma1, mb1, p, stream);

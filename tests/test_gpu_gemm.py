@@ -45,6 +45,36 @@ def test_gemm_majors_and_tails(a_t, b_t, bn, m, n, k):
     assert_close("bf16 out", out16, a @ b.t(), TOL_BF16)
 
 
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (512, 384, 320), (300, 200, 136), (1, 8, 8), (1000, 520, 1000)])
+def test_gemm_cta_pair_kernel(a_t, b_t, bn, m, n, k):
+    """tcgen05.mma.cta_group::2: two CTAs share one 256 x BN tile (forced with pair=2), all operand majors + tails."""
+    if (a_t and m % 8) or (b_t and n % 8) or (not a_t and k % 8) or (not b_t and k % 8):
+        pytest.skip("the contiguous dim of each operand must be a multiple of 8 (16-byte rows)")
+    gen = torch.Generator().manual_seed(m * 5 + n * 3 + k + bn)
+    a_s, b_s, a, b = _operands(gen, m, n, k, a_t, b_t)
+    out = torch.full((m, n), float("nan"), dtype=torch.float32, device="cuda")
+    _K().gemm(a_s, b_s, out, a_t=a_t, b_t=b_t, block_n=bn, pair=2, raster=1 + (m + bn) % 2)
+    assert_close("fp32 out", out, a @ b.t(), TOL_F32)
+
+
+def test_gemm_cta_pair_epilogue_and_second_operand():
+    gen = torch.Generator().manual_seed(77)
+    m, n, k0, k1 = 700, 512, 256, 64
+    a0_s, b0_s, a0, b0 = _operands(gen, m, n, k0, False, False)
+    a1_s, b1_s, a1, b1 = _operands(gen, m, n, k1, False, False)
+    bias = randn(gen, n)
+    gate = torch.tensor([0.3], device="cuda")
+    res = randn(gen, m, n).to(BF16)
+    out = torch.empty((m, n), dtype=BF16, device="cuda")
+    aux = torch.empty((m, n), dtype=BF16, device="cuda")
+    _K().gemm(a0_s, b0_s, out, a1=a1_s, b1=b1_s, bias=bias, aux=aux, gate=gate, residual=res, pair=2)
+    pre = a0 @ b0.t() + a1 @ b1.t() + bias
+    assert_close("aux", aux, pre, TOL_BF16)
+    assert_close("out", out, res.float() + torch.tanh(gate) * pre, TOL_BF16)
+
+
 @pytest.mark.parametrize("m,n,k", [(640, 2048, 2048), (2560, 8192, 2048), (2560, 2048, 8192), (64, 4096, 2048)])
 def test_gemm_production_shapes_heuristic_tile(m, n, k):
     """OPT-1.3B gated cross-attention block shapes (q/out proj, fc1, fc2, K|V proj), heuristic BLOCK_N."""
