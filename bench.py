@@ -297,7 +297,8 @@ def run_ours(a, w):
         "e2e": {"value": sections / (ms_e2e * 1e-3), "unit": "sections/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
-        "roofline": roofline, "roofline_attention": extra, "clocks": clocks,
+        "roofline": roofline, "roofline_attention": extra,
+        "roofline_block": block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev), "clocks": clocks,
         "loss": [float(loss_res), float(loss_e2e)],
         "trainable_params": sum(p.numel() for p in params),
     }
@@ -306,6 +307,52 @@ def run_ours(a, w):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def block_roofline(model, batch, seq, pk, dev):
+    """The fused gated cross-attention block alone ('achieved fraction of its roofline reported per size'):
+    one MPTDecoderLayer(cross_attention=True) forward and forward+backward at this workload's shapes, for Nk = 64
+    (<=16 neighbors x 4 tokens) and Nk = 128 (<=32 neighbors), timed with CUDA events, L2 flushed between iterations.
+    Algorithmic FLOPs per section: 4*S*H^2 + 4*Nk*H^2 + 4*S*Nk*H + 4*S*H*F forward; x3 for forward+backward."""
+    layer = model.lm.model.decoder.neighbor_layers[0]
+    h = layer.embed_dim
+    f = layer.fc1.out_features
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for nk in (64, 128):
+        x = torch.randn(batch, seq, h, device=dev).to(torch.bfloat16).requires_grad_(True)
+        bank = torch.randn(batch, nk, h, device=dev).to(torch.bfloat16).requires_grad_(True)
+        mask = torch.ones(batch, nk, dtype=torch.uint8, device=dev)
+        flops = batch * (4.0 * seq * h * h + 4.0 * nk * h * h + 4.0 * seq * nk * h + 4.0 * seq * h * f)
+
+        def fwd():
+            return layer(x, neighbor_embeds=bank, neighbor_attention_mask=mask)[0]
+
+        def fwd_bwd():
+            y = fwd()
+            y.backward(y.detach())
+
+        res = {}
+        for name, fn, mult in (("fwd", fwd, 1.0), ("fwd_bwd", fwd_bwd, 3.0)):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(8):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            tf = mult * flops / (ms * 1e-3) / 1e12
+            res[name] = {"ms": ms, "achieved": tf, "unit": "TFLOP/s", "peak": pk["tf_burst"], "frac": tf / pk["tf_burst"]}
+        out[f"S{seq}_Nk{nk}_B{batch}"] = res
+        for p_ in layer.parameters():
+            p_.grad = None
+    return {"bound": "tensor", "peak_source": pk["source"] + " (burst: block timed alone)", "sizes": out}
 
 
 def cpu_baseline(a, w):

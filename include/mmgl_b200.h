@@ -72,9 +72,16 @@ typedef struct mmgl_gemm_args {
   uint64_t dropout_seed;
   int32_t raster;        /* tile order: 0 = heuristic, 1 = M-fastest, 2 = N-fastest (tests, tuning) */
   int32_t pair;          /* CTA-pair (cta_group::2, 256-row tiles) kernel: 0 = heuristic, 1 = never, 2 = always */
+  /* Optional scratch for the stream-K tail of the CTA-pair kernel (the last partial wave of tiles is cut into K-slices
+   * whose fp32 partial tiles are parked here and added by the slice-0 owner).  Caller-owned, >= mmgl_gemm_workspace_bytes(),
+   * not shared between streams that run concurrently; NULL disables stream-K.  stream_k: 2 = on, otherwise off
+   * (measured on B200 in round 1: the owner's serial fix-up reads cost about what the slices save at K <= 8192, so the
+   * data-parallel schedule stays the default until the fix-up is distributed; kept and parity-tested for that work). */
+  void* workspace; int64_t workspace_bytes; int32_t stream_k; int32_t reserved;
 } mmgl_gemm_args;
 
 int mmgl_gemm_bf16(const mmgl_gemm_args* args, void* stream);
+size_t mmgl_gemm_workspace_bytes(void);   /* enough for any problem: flags + (SMs/2) fp32 256x256 partial tiles */
 
 /* ------------------------------------------------------------------------------------------------
  * Fused cross-attention core:  O = softmax(max(Q K^T + mask, FLT_MIN_FINITE)) V   per (sample, head).

@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("relu_mask", c_vp), ("ldmask", c_i64),
         ("force_block_n", c_i32), ("dropout_p", c_f32), ("dropout_seed", C.c_uint64),
         ("raster", c_i32), ("pair", c_i32),
+        ("workspace", c_vp), ("workspace_bytes", c_i64), ("stream_k", c_i32), ("reserved", c_i32),
     ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "mmgl_last_error_string": (C.c_char_p, []),
     "mmgl_launch_count": (c_i64, []),
     "mmgl_gemm_bf16": (c_i32, [C.POINTER(GemmArgs), c_vp]),
+    "mmgl_gemm_workspace_bytes": (c_sz, []),
     "mmgl_xattn_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp,
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "mmgl_xattn_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
@@ -189,6 +191,20 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+_ws_cache = {}
+
+
+def _gemm_workspace(device) -> torch.Tensor:
+    """Stream-K scratch (fp32 partial tiles + arrival counters), one buffer per (device, stream): launches on one
+    stream are ordered, so consecutive GEMMs can share it; concurrent streams get their own."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib().mmgl_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = False, b_t: bool = False,
          a1: Optional[torch.Tensor] = None, b1: Optional[torch.Tensor] = None,
@@ -196,7 +212,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
          gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None,
          accumulate: bool = False, block_n: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0,
-         raster: int = 0, pair: int = 0) -> torch.Tensor:
+         raster: int = 0, pair: int = 0, stream_k: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(A @ B^T (+ A1 @ B1^T)).
 
     a:  [M,K] (a_t=False) or [K,M] (a_t=True: A is used transposed, i.e. stored M-contiguous)
@@ -234,6 +250,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.force_block_n = block_n
     g.raster = raster
     g.pair = pair
+    ws = _gemm_workspace(out.device)
+    g.workspace, g.workspace_bytes, g.stream_k = ws.data_ptr(), ws.numel(), stream_k
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     with _Timed(f"gemm_tcgen05 m={m} n={n} k={k + int(g.k1)} at={int(a_t)} bt={int(b_t)}" if _prof_detail else "gemm_tcgen05",
                 2.0 * m * n * (k + int(g.k1))):

@@ -30,6 +30,7 @@ constexpr int kGemmThreads = 192;      // 6 warps
 constexpr int kATileBytes = BM * BK * 2;
 // per-k-block time of one wave of CTA-pair tiles relative to one wave of single-CTA 128 x 256 tiles (B200, tools/microbench.py:
 // fc1 1410 vs 1300 TFLOP/s at BN = 256; the 256 x 128 pair tile is L2-ingest bound again)
+constexpr size_t kSkFlagBytes = 1024;   // stream-K arrival counters at the head of the workspace
 constexpr double kPairCost256 = 0.92;
 constexpr double kPairCost128 = 1.50;
 
@@ -48,6 +49,11 @@ struct GemmParams {
   int32_t m_blocks, n_blocks;
   int32_t n_fastest;  // tile rasterisation: 1 = consecutive tiles walk N first (each A tile is streamed once)
   int32_t m_blocks_pair;  // CTA-pair kernel: number of 256-row tiles
+  // stream-K tail of the CTA-pair kernel: tiles [0, sk_full) run data-parallel (whole K per tile); each of the last
+  // sk_tail tiles is cut into sk_split K-slices owned by different CTA pairs; slices > 0 park their fp32 partial tile in
+  // sk_ws and bump sk_flags[tile]; slice 0 adds them in and runs the epilogue.  sk_split <= 1: plain data-parallel.
+  int32_t sk_full, sk_split, sk_tail;
+  float* sk_ws; int32_t* sk_flags;
   void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
   float alpha; int32_t relu;
   const float* bias;
@@ -299,6 +305,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
 // B tile, one thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives its own 128
 // accumulator rows.  Per SM and k-block the operand ingest drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what
 // bounds the single-CTA kernel (L2 -> SM bandwidth), so the pair kernel is tensor-pipe bound at BN = 256.
+struct PairWork { int tile, kb0, kb1, slice, tail; };
+// it-th work item of a CTA pair; false when the pair is done.  Identical in all warp roles.
+__device__ __forceinline__ bool pair_next_work(const GemmParams& p, int cluster, int num_clusters, int num_tiles, int kblocks,
+                                               int it, PairWork& w) {
+  const int tile = cluster + it * num_clusters;
+  w.kb0 = 0; w.kb1 = kblocks; w.slice = 0; w.tail = -1;
+  if (tile < p.sk_full || p.sk_split <= 1) {
+    w.tile = tile;
+    return tile < num_tiles;
+  }
+  if (tile >= p.sk_full + num_clusters || cluster >= p.sk_tail * p.sk_split) return false;   // one tail item per pair
+  w.tail = cluster / p.sk_split;
+  w.slice = cluster % p.sk_split;
+  w.tile = p.sk_full + w.tail;
+  w.kb0 = (int)(((int64_t)w.slice * kblocks) / p.sk_split);
+  w.kb1 = (int)(((int64_t)(w.slice + 1) * kblocks) / p.sk_split);
+  return true;
+}
+__device__ __forceinline__ void spin_until_at_least(const int32_t* flag, int32_t want) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile int32_t*>(flag) < want) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mmgl: stream-K fix-up wait timed out (block %d)\n", (int)blockIdx.x);
+      __trap();
+    }
+  }
+}
+
 template <int BN> struct PairCfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kATileBytes + kBHalfBytes;   // per CTA
@@ -348,12 +383,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+      PairWork w;
+      for (int it = 0; pair_next_work(p, cluster, num_clusters, num_tiles, kblocks, it, w); ++it) {
+        const int tile = w.tile;
         const int mt = p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks_pair;
         const int nt = p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks_pair;
         const int m0 = mt * 256 + (int)rank * BM;
         const int n0 = nt * BN + (int)rank * BNH;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           const bool second = kb >= p.kblocks0;
           const CUtensorMap* ma = second ? &map_a1 : &map_a0;
           const CUtensorMap* mb = second ? &map_b1 : &map_b0;
@@ -385,11 +422,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+      PairWork w;
+      for (int it = 0; pair_next_work(p, cluster, num_clusters, num_tiles, kblocks, it, w); ++it) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -398,7 +436,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit_pair(&empty_bar[stage]);   // frees this stage in BOTH CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -413,33 +451,73 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     const int quarter = warp & 3;
     const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+    PairWork w;
+    for (int it = 0; pair_next_work(p, cluster, num_clusters, num_tiles, kblocks, it, w); ++it) {
+      const int tile = w.tile;
       const int mt = p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks_pair;
       const int nt = p.n_fastest ? tile % p.n_blocks : tile / p.m_blocks_pair;
       const int n0 = nt * BN;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int64_t row = (int64_t)mt * 256 + rank * BM + quarter * 32 + lane;
+      const int row_in_tile = (int)rank * BM + quarter * 32 + lane;
+      const int64_t row = (int64_t)mt * 256 + row_in_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      const int others = (w.tail >= 0) ? p.sk_split - 1 : 0;
+      if (w.slice > 0) {
+        // ---- stream-K contributor: park the raw fp32 partial tile, then signal the owner
+        float* dst = p.sk_ws + ((size_t)(w.tail * others + (w.slice - 1)) * 256 + row_in_tile) * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int64_t col0 = n0 + c * 32;
-        if (row < p.m && col0 < p.n) {
-          if (p.vec_ok && col0 + 32 <= p.n) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
+          for (int g = 0; g < 8; ++g)
+            __stcg(reinterpret_cast<float4*>(dst + c * 32) + g,
+                   make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                               __uint_as_float(r[4 * g + 3])));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.sk_flags + w.tail, 1);
+      } else {
+        if (others > 0) {   // ---- stream-K owner: wait for the 8 epilogue warps of every contributor pair
+          if (lane == 0) spin_until_at_least(p.sk_flags + w.tail, 8 * others);
+          __syncwarp();
+          __threadfence();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          for (int j = 0; j < others; ++j) {
+            const float4* src = reinterpret_cast<const float4*>(
+                p.sk_ws + ((size_t)(w.tail * others + j) * 256 + row_in_tile) * BN + c * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+            for (int g = 0; g < 8; ++g) {
+              const float4 v = __ldcg(src + g);
+              r[4 * g] = __float_as_uint(__uint_as_float(r[4 * g]) + v.x);
+              r[4 * g + 1] = __float_as_uint(__uint_as_float(r[4 * g + 1]) + v.y);
+              r[4 * g + 2] = __float_as_uint(__uint_as_float(r[4 * g + 2]) + v.z);
+              r[4 * g + 3] = __float_as_uint(__uint_as_float(r[4 * g + 3]) + v.w);
             }
-          } else {
+          }
+          const int64_t col0 = n0 + c * 32;
+          if (row < p.m && col0 < p.n) {
+            if (p.vec_ok && col0 + 32 <= p.n) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+            }
           }
         }
       }
@@ -549,7 +627,7 @@ static int pick_block_n(int64_t m, int64_t n, int sms) {
 
 // CTA-pair selection: compare estimated time (waves x per-tile cost); costs relative to one k-block of a 128 x 256
 // single-CTA tile, measured on B200 (tools/microbench.py).  Returns true and sets *bn when the pair kernel wins.
-static bool pick_pair(int64_t m, int64_t n, int sms, int* bn) {
+static bool pick_pair(int64_t m, int64_t n, int sms, int* bn, bool stream_k) {
   if (m < 256) return false;
   const int single_cand[4] = {256, 192, 128, 64};
   const double single_cost[4] = {1.00, 0.88, 0.82, 0.76};
@@ -567,7 +645,14 @@ static bool pick_pair(int64_t m, int64_t n, int sms, int* bn) {
   double best_pair = 1e30; int best_bn = 256;
   for (int i = 0; i < 2; ++i) {
     const int64_t tiles = mb2 * ((n + pair_cand[i] - 1) / pair_cand[i]);
-    const double c = (double)((tiles + pairs - 1) / pairs) * pair_cost[i];
+    double waves = (double)((tiles + pairs - 1) / pairs);
+    if (stream_k && i == 0) {   // the tail wave is cut into K-slices: costs 1/split of a wave plus the fix-up
+      const int64_t r = tiles % pairs;
+      int64_t split = r > 0 ? pairs / r : 1;
+      if (split > 8) split = 8;
+      if (split >= 2) waves = (double)(tiles / pairs) + 1.0 / (double)split + 0.10;
+    }
+    const double c = waves * pair_cost[i];
     if (c < best_pair) { best_pair = c; best_bn = pair_cand[i]; }
   }
   if (best_pair < best_single * 0.97) { *bn = best_bn; return true; }
@@ -608,8 +693,16 @@ static int launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& b0, const 
   }
   const int tiles = p.m_blocks_pair * p.n_blocks;
   const int pairs = sm_count() / 2;
+  int clusters = tiles < pairs ? tiles : pairs;
+  if (p.sk_split > 1) {
+    clusters = p.sk_full > 0 ? pairs : p.sk_tail * p.sk_split;
+    if (cudaMemsetAsync(p.sk_flags, 0, (size_t)p.sk_tail * sizeof(int32_t), stream) != cudaSuccess) {
+      set_error("mmgl_gemm_bf16(pair): cudaMemsetAsync of the stream-K flags failed");
+      return 3;
+    }
+  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = PairCfg<BN>::kSmemBytes;
   cfg.stream = stream;
@@ -648,6 +741,10 @@ static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& a0, const CUten
 
 using namespace mmgl;
 
+extern "C" size_t mmgl_gemm_workspace_bytes(void) {
+  return kSkFlagBytes + (size_t)74 * 256 * 256 * sizeof(float);
+}
+
 extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a != nullptr, "mmgl_gemm_bf16: null args");
@@ -672,7 +769,7 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
     use_pair = true;
     if (bn != 128) bn = 256;
   } else if (a->pair == 0 && a->force_block_n == 0) {
-    use_pair = pick_pair(a->m, a->n, sms, &bn);
+    use_pair = pick_pair(a->m, a->n, sms, &bn, a->stream_k == 2 && a->workspace != nullptr);
   }
 
   GemmParams p;
@@ -682,6 +779,22 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   p.m_blocks = (int32_t)((a->m + BM - 1) / BM);
   p.n_blocks = (int32_t)((a->n + bn - 1) / bn);
   p.m_blocks_pair = (int32_t)((a->m + 255) / 256);
+  p.sk_full = 0; p.sk_split = 1; p.sk_tail = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
+  if (use_pair && a->stream_k == 2 && a->workspace != nullptr) {
+    const int pairs = sms / 2;
+    const int tiles = p.m_blocks_pair * p.n_blocks;
+    const int full = (tiles / pairs) * pairs, r = tiles - full;
+    const int kblocks = p.kblocks0 + p.kblocks1;
+    int split = (r > 0) ? pairs / r : 1;
+    if (split > kblocks) split = kblocks;
+    if (split > 8) split = 8;
+    const size_t need = kSkFlagBytes + (size_t)r * (split > 1 ? split - 1 : 0) * 256 * bn * sizeof(float);
+    if (split >= 2 && (size_t)a->workspace_bytes >= need && aligned16(a->workspace)) {
+      p.sk_full = full; p.sk_split = split; p.sk_tail = r;
+      p.sk_flags = reinterpret_cast<int32_t*>(a->workspace);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + kSkFlagBytes);
+    }
+  }
   p.n_fastest = (a->raster == 1) ? 0 : ((a->raster == 2) ? 1 : (p.m_blocks >= p.n_blocks ? 1 : 0));
   p.d = a->d; p.ldd = a->ldd; p.out_fp32 = a->out_fp32; p.accumulate = a->accumulate;
   p.alpha = a->alpha; p.relu = a->relu; p.bias = a->bias; p.gate = a->gate;

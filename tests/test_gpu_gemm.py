@@ -59,6 +59,32 @@ def test_gemm_cta_pair_kernel(a_t, b_t, bn, m, n, k):
     assert_close("fp32 out", out, a @ b.t(), TOL_F32)
 
 
+@pytest.mark.parametrize("m,n,k,a_t,b_t", [
+    (5120, 2048, 2048, False, False),   # 160 pair tiles on 74 pairs: 2 full waves + 12 tail tiles cut 6 ways
+    (512, 2048, 1024, False, False),    # 16 tiles, no full wave: every tile cut 4 ways
+    (2048, 2048, 5120, True, True),     # wgrad shape, 64 tiles cut in 1 (no split possible) .. heuristic decides
+    (1300, 1000, 520, False, True),     # ragged M / N / K tails inside split tiles
+    (256, 256, 64, False, False),       # one k-block: cannot be split
+])
+def test_gemm_stream_k_tail(m, n, k, a_t, b_t):
+    """The last partial wave of the CTA-pair kernel is cut into K-slices (fp32 partial tiles + fix-up by the owner):
+    results must match the plain data-parallel schedule to fp32 accumulation-order accuracy."""
+    gen = torch.Generator().manual_seed(m + n + k)
+    a_s, b_s, a, b = _operands(gen, m, n, k, a_t, b_t)
+    ref = a @ b.t()
+    for sk in (2, 1):
+        out = torch.full((m, n), float("nan"), dtype=torch.float32, device="cuda")
+        _K().gemm(a_s, b_s, out, a_t=a_t, b_t=b_t, block_n=256, pair=2, stream_k=sk)
+        assert_close(f"stream_k={sk}", out, ref, TOL_F32)
+    # fused epilogue on the owner slice + repeated launches (flag reset)
+    bias = randn(gen, n)
+    res = randn(gen, m, n).to(BF16)
+    out16 = torch.empty((m, n), dtype=BF16, device="cuda")
+    for _ in range(3):
+        _K().gemm(a_s, b_s, out16, a_t=a_t, b_t=b_t, block_n=256, pair=2, stream_k=2, bias=bias, residual=res, relu=True)
+    assert_close("epilogue", out16, torch.relu(ref + bias) + res.float(), TOL_BF16)
+
+
 def test_gemm_cta_pair_epilogue_and_second_operand():
     gen = torch.Generator().manual_seed(77)
     m, n, k0, k1 = 700, 512, 256, 64
