@@ -26,7 +26,7 @@ namespace mmgl {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 192;      // 6 warps
+constexpr int kGemmThreads = 320;      // 10 warps: TMA producer, MMA issuer, 8 epilogue warps
 constexpr int kATileBytes = BM * BK * 2;
 // per-k-block time of one wave of CTA-pair tiles relative to one wave of single-CTA 128 x 256 tiles (B200, tools/microbench.py:
 // fc1 1410 vs 1300 TFLOP/s at BN = 256; the 256 x 128 pair tile is L2-ingest bound again)
@@ -157,6 +157,125 @@ __device__ __forceinline__ void epilogue_store1(const GemmParams& p, float v, in
   }
 }
 
+// Epilogue of one warp: its 32 accumulator rows x the 32-column chunks [c_begin, c_end) of the tile at TMEM `taddr`.
+// For short-K tiles the epilogue, not the MMA, is the critical path, so the common case (bf16 output, 16-byte aligned
+// operands) issues the residual / ReLU-mask loads of chunk c+1 before it touches chunk c: their global latency hides
+// behind the TMEM load and the arithmetic of the current chunk.
+__device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t taddr, int64_t row, int n0, int c_begin,
+                                                int c_end, float gate_t) {
+  const bool fast = p.vec_ok && !p.out_fp32 && !p.accumulate;
+  const bool row_ok = row < p.m;
+  uint4 res_n[4], msk_n[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { res_n[g] = make_uint4(0, 0, 0, 0); msk_n[g] = make_uint4(0, 0, 0, 0); }
+  auto prefetch = [&](int c) {
+    const int64_t col0 = n0 + c * 32;
+    if (row_ok && col0 + 32 <= p.n) {
+      if (p.residual != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) res_n[g] = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldres + col0) + g);
+      }
+      if (p.relu_mask != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) msk_n[g] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + row * p.ldmask + col0) + g);
+      }
+    }
+  };
+  if (fast) prefetch(c_begin);
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    uint4 res[4], msk[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { res[g] = res_n[g]; msk[g] = msk_n[g]; }
+    if (fast && c + 1 < c_end) prefetch(c + 1);
+    tmem_ld_wait();
+    const int64_t col0 = n0 + c * 32;
+    if (!row_ok || col0 >= p.n) continue;
+    if (fast && col0 + 32 <= p.n) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + g);
+          v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+        }
+      }
+      if (p.alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.relu_mask != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t w[4] = {msk[g].x, msk[g].y, msk[g].z, msk[g].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(bf16lo(w[j]) > 0.f)) v[8 * g + 2 * j] = 0.f;
+            if (!(bf16hi(w[j]) > 0.f)) v[8 * g + 2 * j + 1] = 0.f;
+          }
+        }
+      }
+      if (p.drop_thresh != 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const DropBits bits = dropout_bits(p.drop_seed, row, (col0 >> 3) + g, p.drop_groups);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 * g + j] = dropout_keep(bits, j, p.drop_thresh) ? v[8 * g + j] * p.drop_scale : 0.f;
+        }
+      }
+      if (p.aux != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * g], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+          o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+          reinterpret_cast<uint4*>(p.aux + row * p.ldaux + col0)[g] = o;
+        }
+      }
+      if (p.gate != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= gate_t;
+      }
+      if (p.residual != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t w[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[8 * g + 2 * j] += bf16lo(w[j]); v[8 * g + 2 * j + 1] += bf16hi(w[j]); }
+        }
+      }
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * g], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+        o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+        reinterpret_cast<uint4*>(dp)[g] = o;
+      }
+    } else if (p.vec_ok && col0 + 32 <= p.n) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+        epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+    }
+  }
+}
+
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
@@ -182,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     tma_prefetch_desc(&map_b0);
     if (p.kblocks1 > 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_b1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
@@ -254,8 +373,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9): lane quarter = warp % 4, column half = (warp - 2) / 4 =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    constexpr int kChunksPerHalf = BN / 64;
     const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -265,28 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       tc_fence_after();
       const int64_t row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int64_t col0 = n0 + c * 32;
-        if (row < p.m && col0 < p.n) {
-          if (p.vec_ok && col0 + 32 <= p.n) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              epilogue_store8(p, v, row, col0 + g * 8, gate_t);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
-          }
-        }
-      }
+      epilogue_chunks(p, taddr, row, n0, half * kChunksPerHalf, (half + 1) * kChunksPerHalf, gate_t);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -370,7 +470,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     tma_prefetch_desc(&map_b0);
     if (p.kblocks1 > 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_b1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }  // 4 warps x 2 CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }  // 8 warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr);
@@ -447,8 +547,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps (2..5) of both CTAs: own 128 accumulator rows =====================
+    // ===================== epilogue warps (2..9) of both CTAs: own 128 accumulator rows, two column halves =====================
     const int quarter = warp & 3;
+    const int c_begin = ((warp - 2) >> 2) * (BN / 64), c_end = c_begin + BN / 64;
     const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
     PairWork w;
@@ -467,7 +568,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
         // ---- stream-K contributor: park the raw fp32 partial tile, then signal the owner
         float* dst = p.sk_ws + ((size_t)(w.tail * others + (w.slice - 1)) * 256 + row_in_tile) * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -480,14 +581,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(p.sk_flags + w.tail, 1);
-      } else {
-        if (others > 0) {   // ---- stream-K owner: wait for the 8 epilogue warps of every contributor pair
-          if (lane == 0) spin_until_at_least(p.sk_flags + w.tail, 8 * others);
-          __syncwarp();
-          __threadfence();
-        }
+      } else if (others > 0) {
+        // ---- stream-K owner: wait for the 16 epilogue warps of every contributor pair, add their partials
+        if (lane == 0) spin_until_at_least(p.sk_flags + w.tail, 16 * others);
+        __syncwarp();
+        __threadfence();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -520,6 +620,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
             }
           }
         }
+      } else {
+        epilogue_chunks(p, taddr, row, n0, c_begin, c_end, gate_t);
       }
       tc_fence_before();
       __syncwarp();

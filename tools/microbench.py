@@ -72,6 +72,34 @@ def bench_gemm():
         print(json.dumps(res), flush=True)
 
 
+def bench_epilogue():
+    """cost of the fused epilogue on the short-K, N = H GEMM (out_proj of every layer)"""
+    m, n, k = 5120, 2048, 2048
+    a = torch.randn(m, k, device="cuda").to(BF16)
+    b = torch.randn(n, k, device="cuda").to(BF16)
+    out = torch.empty((m, n), dtype=BF16, device="cuda")
+    aux = torch.empty((m, n), dtype=BF16, device="cuda")
+    res = torch.randn(m, n, device="cuda").to(BF16)
+    bias = torch.randn(n, device="cuda")
+    gate = torch.tensor([0.5], device="cuda")
+    flops = 2.0 * m * n * k
+    variants = {
+        "plain": {},
+        "bias": dict(bias=bias),
+        "bias+residual": dict(bias=bias, residual=res),
+        "bias+dropout": dict(bias=bias, dropout_p=0.1, dropout_seed=123),
+        "bias+dropout+residual": dict(bias=bias, residual=res, dropout_p=0.1, dropout_seed=123),
+        "bias+dropout+aux+gate+residual": dict(bias=bias, residual=res, aux=aux, gate=gate, dropout_p=0.1, dropout_seed=123),
+        "bias+relu (fc1-like)": dict(bias=bias, relu=True),
+    }
+    for name, kw in variants.items():
+        r = {"kernel": "gemm_epilogue", "variant": name}
+        for label, extra in (("auto", {}), ("single192", dict(block_n=192, pair=1)), ("pair256", dict(block_n=256, pair=2))):
+            med, _ = time_it(lambda: K.gemm(a, b, out, **kw, **extra))
+            r[label + "_tflops"] = round(flops / med / 1e9, 1)
+        print(json.dumps(r), flush=True)
+
+
 def bench_xattn():
     for b, s, nk, heads, d in [(4, 640, 64, 32, 64), (4, 640, 128, 32, 64), (8, 640, 64, 32, 64), (2, 1152, 128, 32, 128)]:
         h = heads * d
@@ -121,6 +149,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
     if "gemm" in which:
         bench_gemm()
+    if "epilogue" in which:
+        bench_epilogue()
     if "xattn" in which:
         bench_xattn()
     if "rowops" in which:
