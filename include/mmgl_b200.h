@@ -107,6 +107,25 @@ int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
                    int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Causal / key-padded self-attention of the (frozen) decoder layers -- SURVEY 8f row f1.
+ *   O = softmax(max(scale * Q K^T + causal + key padding, finfo.min)) V   per (sample, head); Q, K, V, O [B,S,nh*d] bf16
+ *   (views with leading dims: the three thirds of one fused [B*S, 3*nh*d] QKV projection work in place).
+ * key_mask [B,S] bytes (1 = real token, 0 = padding; NULL = no padding); causal != 0 masks keys > query.
+ * 128 x 128 score blocks on tcgen05 with TMEM accumulators, TMA-staged tiles, two-pass fp32 softmax; only blocks at or
+ * below the diagonal are visited when causal.  stats [B,nh,S,2] = (row max of the masked scaled scores, 1 / row sum).
+ * Backward = a dQ kernel (per query tile) + a dK/dV kernel (per key block), both recomputing P from stats.
+ * Replaces MPTAttention's self branch model/modelling_cross_attention.py:201-275 with the mask of :455-476.
+ * A query whose keys are ALL masked (never the case with the reference's right-padded batches) attends uniformly over the
+ * visited blocks rather than over all S keys. */
+int mmgl_sattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                   const uint8_t* key_mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq, int64_t heads,
+                   int64_t head_dim, float scale, int32_t causal, void* stream);
+int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                   int64_t ldv, const void* o, int64_t ldo, const float* stats, const uint8_t* key_mask, void* dq,
+                   int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch, int64_t seq, int64_t heads,
+                   int64_t head_dim, float scale, int32_t causal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 gamma/beta and statistics).
  * Replaces nn.LayerNorm at model/modelling_cross_attention.py:320,341,350,365.
  * y may be bf16; mean/rstd [rows] fp32 saved for backward.

@@ -90,8 +90,20 @@ class MPTLearnedPositionalEmbedding(nn.Embedding):
         return super().forward(positions[:, past_key_values_length:] + self.offset)
 
 
+class KeyPaddingCausalMask:
+    """Compact form of the reference's additive decoder mask (causal AND key-not-padding,
+    model/modelling_cross_attention.py:455-476): the [B,S] byte key mask; the [B,1,S,S] tensor is never built."""
+
+    def __init__(self, key_mask):
+        self.key_mask = key_mask
+
+
 def _allowed_from_additive(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """the reference's additive [B,1,S,S] float mask (0 = attend) -> boolean 'allowed' mask; bool passes through"""
+    if isinstance(mask, KeyPaddingCausalMask):
+        key_ok = mask.key_mask.to(torch.bool)
+        s = key_ok.shape[1]
+        return torch.ones(s, s, dtype=torch.bool, device=key_ok.device).tril_()[None, None] & key_ok[:, None, None, :]
     if mask is None or mask.dtype == torch.bool:
         return mask
     return mask == 0
@@ -119,6 +131,17 @@ class MPTAttention(nn.Module):
         self.cross_attention = cross_attention
         self.peft_type = config.peft_type
 
+    @staticmethod
+    def _key_mask(attention_mask, b, s):
+        """The self-attention kernel takes the mask in its compact form: a [B,S] key-padding mask + a causal flag.
+        MPTDecoder passes exactly that (``KeyPaddingCausalMask``); None means causal without padding; anything else
+        (an arbitrary 4-D mask handed in by other callers) returns False -> library fallback."""
+        if attention_mask is None:
+            return None, s > 1
+        if isinstance(attention_mask, KeyPaddingCausalMask):
+            return attention_mask.key_mask, True
+        return False, False
+
     def forward(self, hidden_states, attention_mask=None, neighbor_embeds=None, neighbor_attention_mask=None,
                 layer_head_mask=None, past_key_value=None, output_attentions=False, residual=None, dropout_p=0.0):
         """Returns (attn_output, None, None) like the reference.  ``residual``/``dropout_p`` (extensions) fuse the
@@ -137,17 +160,18 @@ class MPTAttention(nn.Module):
                 # frozen block: one N = 3H GEMM over the cached row-concatenation Wq|Wk|Wv
                 w = ops.fused_rows([p.weight for p in projs], BF16)
                 bias = ops.fused_rows([p.bias for p in projs], torch.float32) if self.q_proj.bias is not None else None
-                qkv = ops.linear(hidden_states, w, bias).view(b, s, 3, self.num_heads, self.head_dim)
-                q, k, v = qkv.unbind(2)
+                qkv = ops.linear(hidden_states, w, bias)
             else:
-                shp = (b, s, self.num_heads, self.head_dim)
-                q = ops.linear(hidden_states, self.q_proj.weight, self.q_proj.bias).view(shp)
-                k = ops.linear(hidden_states, self.k_proj.weight, self.k_proj.bias).view(shp)
-                v = ops.linear(hidden_states, self.v_proj.weight, self.v_proj.bias).view(shp)
-            allowed = _allowed_from_additive(attention_mask)
-            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-                                               attn_mask=allowed, is_causal=allowed is None and s > 1)
-            o = o.transpose(1, 2).reshape(b, s, self.embed_dim)
+                qkv = torch.cat([ops.linear(hidden_states, p.weight, p.bias) for p in projs], dim=-1)
+            key_mask, causal = self._key_mask(attention_mask, b, s)
+            if key_mask is not False and self.head_dim in (64, 128):
+                o = ops.self_attention(qkv, key_mask, self.num_heads, causal=causal, scale=self.scaling)
+            else:  # arbitrary [B,1,S,S] masks / other head dims: library fallback on the same semantics
+                q, k, v = qkv.view(b, s, 3, self.num_heads, self.head_dim).unbind(2)
+                allowed = _allowed_from_additive(attention_mask)
+                o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                   attn_mask=allowed, is_causal=allowed is None and s > 1)
+                o = o.transpose(1, 2).reshape(b, s, self.embed_dim)
         out = ops.linear(o, self.out_proj.weight, self.out_proj.bias, residual=residual, dropout_p=dropout_p)
         return out, None, None
 
@@ -254,9 +278,8 @@ class MPTDecoder(nn.Module):
         bsz, seq = inputs_embeds.shape[:2]
         if attention_mask is None:
             attention_mask = torch.ones(bsz, seq, device=inputs_embeds.device, dtype=torch.long)
-        # causal AND key-not-padding, as one boolean mask shared by all frozen layers (:542-544 builds the additive twin)
-        key_ok = attention_mask.to(torch.bool)
-        allowed = torch.ones(seq, seq, dtype=torch.bool, device=key_ok.device).tril_()[None, None] & key_ok[:, None, None, :]
+        # causal AND key-not-padding in compact form, shared by all frozen layers (:542-544 builds the additive twin)
+        allowed = KeyPaddingCausalMask((attention_mask != 0).to(torch.uint8).contiguous())
         pos = self.embed_positions(attention_mask)
         if self.project_in is not None:
             inputs_embeds = ops.linear(inputs_embeds, self.project_in.weight)

@@ -405,6 +405,44 @@ def xattn_core(q, k, v, mask, heads):
     return XAttnCoreFn.apply(q, k, v, mask, heads)
 
 
+class SelfAttnFn(torch.autograd.Function):
+    """Causal / key-padded self-attention over a fused QKV projection [B,S,3H] (thirds = Q | K | V, heads interleaved
+    in H): model/modelling_cross_attention.py:201-275 with the mask of :455-476.  Q is NOT pre-scaled: ``scale`` is
+    applied to the scores inside the kernel.  Backward writes dQ | dK | dV straight into one [B,S,3H] buffer."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_mask, heads, causal, scale):
+        b, s, h3 = qkv.shape
+        h = h3 // 3
+        qkv2 = _as2d(qkv)
+        km = None
+        if key_mask is not None:
+            km = key_mask if key_mask.dtype == torch.uint8 else (key_mask != 0).to(torch.uint8)
+            km = km.contiguous()
+        o = _new(b * s, h, qkv2)
+        stats = torch.empty((b, heads, s, 2), dtype=F32, device=qkv.device)
+        K.sattn_fwd(qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], km, o, stats, b, s, heads, h // heads, scale, causal)
+        ctx.save_for_backward(qkv2, o, stats, km)
+        ctx.cfg = (b, s, h, heads, bool(causal), float(scale))
+        return o.reshape(b, s, h)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv2, o, stats, km = ctx.saved_tensors
+        b, s, h, heads, causal, scale = ctx.cfg
+        dqkv = torch.empty_like(qkv2)
+        K.sattn_bwd(_as2d(d_o), qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], o, stats, km, dqkv[:, :h], dqkv[:, h:2 * h],
+                    dqkv[:, 2 * h:], b, s, heads, h // heads, scale, causal)
+        return dqkv.reshape(b, s, 3 * h), None, None, None, None
+
+
+def self_attention(qkv, key_mask, heads, causal=True, scale=None):
+    """qkv [B,S,3H] bf16 -> [B,S,H]; key_mask [B,S] (1 = real token) or None."""
+    if scale is None:
+        scale = (qkv.shape[-1] // 3 // heads) ** -0.5
+    return SelfAttnFn.apply(qkv, key_mask, heads, bool(causal), float(scale))
+
+
 # --------------------------------------------------------------------------------------------- gated cross layer
 class GatedCrossLayerFn(torch.autograd.Function):
     """One whole gated cross-attention block, forward and backward, as a fixed schedule of fused kernels.
