@@ -35,7 +35,7 @@ int64_t mmgl_launch_count(void);
  *
  *   acc[m,n] = sum_k A0[m,k]*B0[n,k]  (+ sum_k A1[m,k]*B1[n,k] when k1 > 0)       fp32 accumulate
  *   v = alpha * (acc + bias[n])                  bias optional (fp32)
- *   v = max(v, 0)                                if relu
+ *   v = act(v)                                   relu = 1: max(v,0); 2: GELU (erf); 3: quick-GELU v*sigmoid(1.702v)
  *   v = relu_mask[m,n] > 0 ? v : 0               if relu_mask (bf16, ld = ldmask)      (ReLU backward)
  *   v = keep(m,n) ? v / (1 - p) : 0              if dropout_p > 0 (counter-based mask from dropout_seed, see
  *                                                mmgl_dropout_apply; p is quantised to 1/65536)

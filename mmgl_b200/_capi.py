@@ -240,7 +240,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.m, g.n = m, n
     assert out.dtype in (torch.bfloat16, torch.float32)
     g.d, g.ldd, g.out_fp32, g.accumulate = _p(out), _ld(out), int(out.dtype == torch.float32), int(accumulate)
-    g.alpha, g.relu = float(alpha), int(relu)
+    g.alpha, g.relu = float(alpha), int(relu)   # relu: False/0 none, True/1 ReLU, 2 GELU(erf), 3 quick-GELU
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == n
     if gate is not None:

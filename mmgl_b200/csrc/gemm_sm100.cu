@@ -65,6 +65,13 @@ struct GemmParams {
   uint32_t drop_thresh; float drop_scale; uint64_t drop_seed; int64_t drop_groups;  // drop_thresh == 0: no dropout
 };
 
+// activation codes of mmgl_gemm_args.relu: 1 = ReLU, 2 = GELU (erf form, nn.GELU / HF "gelu"), 3 = quick-GELU (CLIP)
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  return v / (1.f + __expf(-1.702f * v));
+}
+
 // 8 consecutive output columns of one row: fused epilogue + store.
 __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[8], int64_t row, int64_t col,
                                                 float gate_t) {
@@ -78,7 +85,7 @@ __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[
   for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
   if (p.relu) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.relu);
   }
   if (p.relu_mask != nullptr) {
     const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + row * p.ldmask + col));
@@ -137,7 +144,7 @@ __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[
 __device__ __forceinline__ void epilogue_store1(const GemmParams& p, float v, int64_t row, int64_t col, float gate_t) {
   if (p.bias != nullptr) v += __ldg(p.bias + col);
   v *= p.alpha;
-  if (p.relu) v = fmaxf(v, 0.f);
+  if (p.relu) v = apply_act(v, p.relu);
   if (p.relu_mask != nullptr && !(__bfloat162float(p.relu_mask[row * p.ldmask + col]) > 0.f)) v = 0.f;
   if (p.drop_thresh != 0) {
     const DropBits bits = dropout_bits(p.drop_seed, row, col >> 3, p.drop_groups);
@@ -210,7 +217,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       }
       if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.relu);
       }
       if (p.relu_mask != nullptr) {
 #pragma unroll

@@ -145,8 +145,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     mbar_arrive_expect_tx(&bars[1], TB);
     tma_tile<D>(sK, &map_k, &bars[1], colq, rowb);
   }
-  // ---------------- pass 1: row maximum
-  float mx = -FLT_MAX;
+  // ---------------- pass 1: row maximum (raw_mx: unscaled maximum over the unmasked interior blocks)
+  float mx = -FLT_MAX, raw_mx = -FLT_MAX;
   for (int j = 0; j < nblk; ++j) {
     const int buf = j & 1;
     load_key_flags(sFlag + buf * 128, key_mask, b, seq, j * 128, tid);
@@ -161,7 +161,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));
       umma_commit(&bars[5]);
     }
-    __syncthreads();   // key flags visible
+    // key flags visible; a block needs the per-element mask path only if it holds a padding / out-of-range key, or
+    // is the diagonal block of a causal problem -- interior blocks take the 1-instruction-per-score path
+    const bool masked = __syncthreads_or(sFlag[buf * 128 + tid] != 0) || (causal && j == qt);
     mbar_wait(&bars[5], sphase & 1); sphase++;
     tc_fence_after();
 #pragma unroll 1
@@ -169,9 +171,14 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       uint32_t r[32];
       tmem_ld_32x32(lane_addr + c * 32, r);
       tmem_ld_wait();
+      if (masked) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        mx = fmaxf(mx, masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal));
+        for (int e = 0; e < 32; ++e)
+          mx = fmaxf(mx, masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, __uint_as_float(r[e]));
+      }
     }
     tc_fence_before();
     __syncthreads();   // S fully read before the next block's MMA overwrites it
@@ -185,6 +192,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     mbar_arrive_expect_tx(&bars[3 + b0], TB);
     tma_tile<D>(sV + b0 * TB, &map_v, &bars[3 + b0], colq, rowb);
   }
+  mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
+  const float c1 = scale * kL2E, mxc = mx * kL2E;
   float sum = 0.f;
   const uint32_t p_base = smem_u32(sP);
   for (int j = 0; j < nblk; ++j) {
@@ -202,7 +211,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));
       umma_commit(&bars[5]);
     }
-    __syncthreads();
+    const bool masked = __syncthreads_or(sFlag[buf * 128 + tid] != 0) || (causal && j == qt);
     mbar_wait(&bars[5], sphase & 1); sphase++;
     tc_fence_after();
 #pragma unroll 1
@@ -211,13 +220,22 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       tmem_ld_32x32(lane_addr + c * 32, r);
       tmem_ld_wait();
       uint32_t pk[16];
+      if (masked) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float x0 = masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal);
-        const float x1 = masked_score(__uint_as_float(r[e + 1]), scale, sFlag[buf * 128 + c * 32 + e + 1], j * 128 + c * 32 + e + 1, row, causal);
-        const float p0 = exp2f((x0 - mx) * kL2E), p1 = exp2f((x1 - mx) * kL2E);
-        sum += p0 + p1;
-        pk[e >> 1] = pack_bf16(p0, p1);
+        for (int e = 0; e < 32; e += 2) {
+          const float x0 = masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal);
+          const float x1 = masked_score(__uint_as_float(r[e + 1]), scale, sFlag[buf * 128 + c * 32 + e + 1], j * 128 + c * 32 + e + 1, row, causal);
+          const float p0 = exp2f((x0 - mx) * kL2E), p1 = exp2f((x1 - mx) * kL2E);
+          sum += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(r[e]), c1, -mxc)), p1 = exp2f(fmaf(__uint_as_float(r[e + 1]), c1, -mxc));
+          sum += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
       }
       const uint32_t slab = p_base + (c >> 1) * 16384;
 #pragma unroll
@@ -271,11 +289,13 @@ __device__ __forceinline__ void row_stats_delta(const float* stats, const __nv_b
   }
 }
 
-// P and dS of this thread's row for one 128-key block: reads S (col 0) and dP (col 128) from TMEM, writes bf16 tiles
-template <bool kWriteP>
+// P and dS of this thread's row for one 128-key block: reads S (col 0) and dP (col 128) from TMEM, writes bf16 tiles.
+// kMasked = false is the interior-block path (no padding key, not the causal diagonal, no ragged query tile).
+template <bool kWriteP, bool kMasked>
 __device__ __forceinline__ void softmax_grad_block(uint32_t lane_addr, const uint8_t* flags, int key0, int row, bool row_ok,
                                                    int causal, float scale, float m, float inv, float delta,
                                                    uint32_t p_base, uint32_t ds_base, int tid) {
+  const float c1 = scale * kL2E, mc = m * kL2E;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t rs[32], rp[32];
@@ -288,10 +308,15 @@ __device__ __forceinline__ void softmax_grad_block(uint32_t lane_addr, const uin
       float pv[2], dv[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const float x = masked_score(__uint_as_float(rs[e + u]), scale, flags[c * 32 + e + u], key0 + c * 32 + e + u, row, causal);
-        const float p = row_ok ? exp2f((x - m) * kL2E) * inv : 0.f;
+        float p;
+        if (kMasked) {
+          const float x = masked_score(__uint_as_float(rs[e + u]), scale, flags[c * 32 + e + u], key0 + c * 32 + e + u, row, causal);
+          p = row_ok ? exp2f((x - m) * kL2E) * inv : 0.f;
+        } else {
+          p = exp2f(fmaf(__uint_as_float(rs[e + u]), c1, -mc)) * inv;
+        }
         pv[u] = p;
-        dv[u] = row_ok ? p * (__uint_as_float(rp[e + u]) - delta) : 0.f;
+        dv[u] = p * (__uint_as_float(rp[e + u]) - delta);
       }
       pk[e >> 1] = pack_bf16(pv[0], pv[1]);
       dk[e >> 1] = pack_bf16(dv[0], dv[1]);
@@ -375,11 +400,15 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
       umma_commit(&bars[3]);
     }
-    __syncthreads();
+    const bool masked = __syncthreads_or(sFlag[(j & 1) * 128 + tid] != 0) || (causal && j == qt) || (r0 + 128 > seq);
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    softmax_grad_block<false>(lane_addr, sFlag + (j & 1) * 128, j * 128, row, row_ok, causal, scale, m, inv, delta, 0,
-                              smem_u32(sdS), tid);
+    if (masked)
+      softmax_grad_block<false, true>(lane_addr, sFlag + (j & 1) * 128, j * 128, row, row_ok, causal, scale, m, inv, delta, 0,
+                                      smem_u32(sdS), tid);
+    else
+      softmax_grad_block<false, false>(lane_addr, sFlag + (j & 1) * 128, j * 128, row, row_ok, causal, scale, m, inv, delta,
+                                       0, smem_u32(sdS), tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -447,7 +476,7 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
   load_key_flags(sFlag, key_mask, b, seq, kb * 128, tid);
   tc_fence_before();
-  __syncthreads();
+  const bool blk_flagged = __syncthreads_or(sFlag[tid] != 0);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
@@ -485,8 +514,12 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncwarp();
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    softmax_grad_block<true>(lane_addr, sFlag, kb * 128, row, row_ok, causal, scale, m, inv, delta, smem_u32(sP),
-                             smem_u32(sdS), tid);
+    if (blk_flagged || (causal && i == kb) || (i * 128 + 128 > seq))
+      softmax_grad_block<true, true>(lane_addr, sFlag, kb * 128, row, row_ok, causal, scale, m, inv, delta, smem_u32(sP),
+                                     smem_u32(sdS), tid);
+    else
+      softmax_grad_block<true, false>(lane_addr, sFlag, kb * 128, row, row_ok, causal, scale, m, inv, delta, smem_u32(sP),
+                                      smem_u32(sdS), tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

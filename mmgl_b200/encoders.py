@@ -1,0 +1,123 @@
+"""Frozen neighbor encoders on this package's kernels.
+
+The reference runs HF ``RobertaModel`` / ``CLIPVisionModel`` over every neighbor
+(model/modelling_cross_attention.py:992, :1018); they are frozen and run under ``no_grad``, so only an inference
+forward is needed.  ``roberta_cls_hidden`` / ``clip_pooler_output`` read the weights of the HF modules in place
+(same state-dict, nothing is copied or renamed) and run the same arithmetic through libmmgl_b200.so: fused QKV GEMM,
+tcgen05 self-attention (bidirectional, key-padding mask), out-projection with the residual in the epilogue, LayerNorm,
+FFN with GELU / quick-GELU in the epilogue.  Two things the library path cannot do:
+  * only the [CLS] row of the last hidden state is consumed (TextPooler takes ``hidden[:, 0]``; CLIP pools token 0),
+    so the LAST layer computes Q, the out-projection, the FFN and the LayerNorms for that single row per sequence;
+  * no [B,1,S,S] additive masks, no head-split copies.
+Parity: tests/test_gpu_encoders.py compares with the HF modules' own forward on the same weights.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi as K
+from .ops import BF16, F32, f32, fused_rows, w16
+
+
+def _gemm(x, w, bias=None, act=0, residual=None):
+    y = torch.empty((x.shape[0], w.shape[0]), dtype=BF16, device=x.device)
+    K.gemm(x, w, y, bias=bias, relu=act, residual=residual)
+    return y
+
+
+def _ln(x, ln):
+    y = torch.empty_like(x)
+    mean = torch.empty(x.shape[0], dtype=F32, device=x.device)
+    rstd = torch.empty_like(mean)
+    K.layernorm_fwd(x, f32(ln.weight), f32(ln.bias), y, mean, rstd, float(ln.eps))
+    return y
+
+
+def _attention(qkv, key_mask, b, s, heads, d, scale):
+    h = heads * d
+    o = torch.empty((b * s, h), dtype=BF16, device=qkv.device)
+    stats = torch.empty((b, heads, s, 2), dtype=F32, device=qkv.device)
+    K.sattn_fwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], key_mask, o, stats, b, s, heads, d, scale, False)
+    return o
+
+
+_ACT = {"relu": 1, "gelu": 2, "quick_gelu": 3}
+
+
+def _supported(cfg) -> bool:
+    d = cfg.hidden_size // cfg.num_attention_heads
+    return d in (64, 128) and cfg.hidden_size % 8 == 0 and cfg.hidden_act in _ACT
+
+
+@torch.no_grad()
+def roberta_cls_hidden(model, input_ids, attention_mask):
+    """``model(input_ids, attention_mask).last_hidden_state[:, 0]`` of a HF RobertaModel, [N, hidden] bf16.
+    (HF: models/roberta/modeling_roberta.py -- embeddings :70-150, layer :400-470; post-LN blocks.)"""
+    cfg = model.config
+    if not _supported(cfg):
+        return model(input_ids=input_ids, attention_mask=attention_mask).last_hidden_state[:, 0]
+    n, s = input_ids.shape
+    emb = model.embeddings
+    pad = emb.padding_idx
+    not_pad = (input_ids != pad).to(torch.int64)
+    pos = torch.cumsum(not_pad, dim=1) * not_pad + pad
+    x = emb.word_embeddings(input_ids) + emb.position_embeddings(pos) + emb.token_type_embeddings.weight[0]
+    x = _ln(x.reshape(n * s, -1).to(BF16).contiguous(), emb.LayerNorm)
+    heads, h = cfg.num_attention_heads, cfg.hidden_size
+    d = h // heads
+    km = (attention_mask != 0).to(torch.uint8).contiguous()
+    act = _ACT[cfg.hidden_act]
+    layers = model.encoder.layer
+    for li, layer in enumerate(layers):
+        a = layer.attention
+        w = fused_rows([a.self.query.weight, a.self.key.weight, a.self.value.weight], BF16)
+        bias = fused_rows([a.self.query.bias, a.self.key.bias, a.self.value.bias], F32)
+        qkv = _gemm(x, w, bias)
+        ctx = _attention(qkv, km, n, s, heads, d, d ** -0.5)
+        if li == len(layers) - 1:   # only [CLS] rows are consumed downstream
+            ctx = ctx.reshape(n, s, h)[:, 0].contiguous()
+            x = x.reshape(n, s, h)[:, 0].contiguous()
+        y = _ln(_gemm(ctx, w16(a.output.dense.weight), f32(a.output.dense.bias), residual=x), a.output.LayerNorm)
+        f = _gemm(y, w16(layer.intermediate.dense.weight), f32(layer.intermediate.dense.bias), act=act)
+        x = _ln(_gemm(f, w16(layer.output.dense.weight), f32(layer.output.dense.bias), residual=y), layer.output.LayerNorm)
+    return x
+
+
+@torch.no_grad()
+def clip_pooler_output(model, pixel_values):
+    """``model(pixel_values).pooler_output`` of a HF CLIPVisionModel, [N, hidden] bf16.
+    (HF: models/clip/modeling_clip.py -- CLIPVisionEmbeddings, pre-LN CLIPEncoderLayer, post_layernorm on token 0.)"""
+    cfg = model.config
+    vm = model.vision_model
+    p = cfg.patch_size
+    n, c, hh, ww = pixel_values.shape
+    if not _supported(cfg) or hh % p or ww % p or (c * p * p) % 8:
+        return model(pixel_values.to(next(model.parameters()).dtype)).pooler_output
+    gh, gw = hh // p, ww // p
+    s = gh * gw + 1
+    h, heads = cfg.hidden_size, cfg.num_attention_heads
+    d = h // heads
+    emb = vm.embeddings
+    # stride-p convolution == GEMM over unfolded patches ([c, kh, kw] order of the conv weight)
+    patches = pixel_values.reshape(n, c, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(n * gh * gw, c * p * p)
+    pe = _gemm(patches.to(BF16).contiguous(), w16(emb.patch_embedding.weight).reshape(h, c * p * p))
+    x = torch.empty((n, s, h), dtype=BF16, device=pe.device)
+    x[:, 0] = emb.class_embedding.to(BF16)
+    x[:, 1:] = pe.reshape(n, gh * gw, h)
+    x = x + emb.position_embedding.weight.to(BF16)[None, :s]
+    x = _ln(x.reshape(n * s, h), vm.pre_layrnorm)
+    act = _ACT[cfg.hidden_act]
+    layers = vm.encoder.layers
+    for li, layer in enumerate(layers):
+        a = layer.self_attn
+        y = _ln(x, layer.layer_norm1)
+        w = fused_rows([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], BF16)
+        bias = fused_rows([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], F32)
+        ctx = _attention(_gemm(y, w, bias), None, n, s, heads, d, d ** -0.5)
+        if li == len(layers) - 1:   # only the class token is pooled
+            ctx = ctx.reshape(n, s, h)[:, 0].contiguous()
+            x = x.reshape(n, s, h)[:, 0].contiguous()
+        x = _gemm(ctx, w16(a.out_proj.weight), f32(a.out_proj.bias), residual=x)
+        f = _gemm(_ln(x, layer.layer_norm2), w16(layer.mlp.fc1.weight), f32(layer.mlp.fc1.bias), act=act)
+        x = _gemm(f, w16(layer.mlp.fc2.weight), f32(layer.mlp.fc2.bias), residual=x)
+    return _ln(x, vm.post_layernorm)

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import configs, ops
+from . import configs, encoders, ops
 
 BF16 = torch.bfloat16
 
@@ -369,7 +369,10 @@ class TextPooler(nn.Module):
         self.activation = nn.Tanh()
 
     def forward(self, hidden_states):
-        return self.activation(ops.linear(hidden_states[:, 0], self.dense.weight, self.dense.bias))
+        return self.pool_cls(hidden_states[:, 0])
+
+    def pool_cls(self, cls_hidden):
+        return self.activation(ops.linear(cls_hidden, self.dense.weight, self.dense.bias))
 
 
 # ------------------------------------------------------------------------------------------------- loaders
@@ -419,17 +422,16 @@ class _NeighborEncoderMixin:
         """frozen text encoder (+ trainable pooler) -> pooled features [B*T, E]
         (model/modelling_cross_attention.py:988-996)."""
         l = input_ids.shape[-1]
-        with torch.no_grad():
-            out = self.text_model(input_ids=input_ids.reshape(-1, l), attention_mask=attention_mask.reshape(-1, l))
+        ids2, am2 = input_ids.reshape(-1, l), attention_mask.reshape(-1, l)
         if "clip" in str(self.args.text_model):
-            return out.pooler_output
-        return self.text_pooler(out.last_hidden_state)
+            with torch.no_grad():
+                return self.text_model(input_ids=ids2, attention_mask=am2).pooler_output
+        # frozen RoBERTa on this package's kernels; only the [CLS] row is consumed (TextPooler: hidden[:, 0])
+        return self.text_pooler.pool_cls(encoders.roberta_cls_hidden(self.text_model, ids2, am2))
 
     def encode_images(self, pixel_values):
         """frozen CLIP vision tower -> pooler_output [B*I, E] (model/modelling_cross_attention.py:1015-1019)."""
-        with torch.no_grad():
-            px = pixel_values.reshape(-1, *pixel_values.shape[2:]).to(next(self.visual_model.parameters()).dtype)
-            return self.visual_model(px).pooler_output
+        return encoders.clip_pooler_output(self.visual_model, pixel_values.reshape(-1, *pixel_values.shape[2:]))
 
     skip_padding_neighbors = True
 
