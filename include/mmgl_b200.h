@@ -125,6 +125,30 @@ int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
                    int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch, int64_t seq, int64_t heads,
                    int64_t head_dim, float scale, int32_t causal, void* stream);
 
+/* General form of the above: queries and keys of different lengths, an additive relative-position bias and dropout
+ * on the probabilities -- the attention of the HF T5 / OPT language model that the concat path runs
+ * (model/modelling_self_attention.py:332; HF models/t5/modeling_t5.py T5Attention: scores are NOT scaled by d^-1/2,
+ * position_bias[h, i, j] depends on j - i only, nn.functional.dropout on the softmax output; the decoder's
+ * cross-attention has seq_q = decoder length, seq_k = encoder length, no bias, key padding from the encoder mask).
+ *   P = softmax(max(scale * Q K^T + rel_bias[h][key - row + seq_q - 1] + causal + key padding, finfo.min))
+ *   O = (keep / (1 - dropout_p) . P) V     keep = the counter-based mask of mmgl_dropout_apply over the
+ *                                          [batch*heads*seq_q, seq_k] probability matrix, row = (b*heads + h)*seq_q + i
+ * q, o [B,seq_q,nh*d]; k, v [B,seq_k,nh*d] (views with leading dims); key_mask [B,seq_k] bytes or NULL;
+ * rel_bias fp32 [heads, seq_q + seq_k - 1] or NULL; stats [B,nh,seq_q,2].  causal needs seq_q == seq_k.
+ * seq_k <= 8192.  Backward returns dQ, dK, dV (the bias is treated as a constant: its table is frozen under LoRA). */
+typedef struct mmgl_attn_args {
+  const void* q; int64_t ldq; const void* k; int64_t ldk; const void* v; int64_t ldv;
+  const uint8_t* key_mask; const float* rel_bias;
+  void* o; int64_t ldo; float* stats;
+  int64_t batch; int64_t seq_q; int64_t seq_k; int64_t heads; int64_t head_dim;
+  float scale; int32_t causal; float dropout_p; int32_t reserved; uint64_t dropout_seed;
+} mmgl_attn_args;
+int mmgl_attn_fwd(const mmgl_attn_args* args, void* stream);
+/* o and stats in args are the forward outputs (read here) */
+int mmgl_attn_bwd(const mmgl_attn_args* args, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
+                  int64_t lddk, void* dv, int64_t lddv, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 gamma/beta and statistics).
  * Replaces nn.LayerNorm at model/modelling_cross_attention.py:320,341,350,365.

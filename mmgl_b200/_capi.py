@@ -62,6 +62,17 @@ class BankBwdArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    """mirror of mmgl_attn_args (include/mmgl_b200.h)"""
+    _fields_ = [
+        ("q", c_vp), ("ldq", c_i64), ("k", c_vp), ("ldk", c_i64), ("v", c_vp), ("ldv", c_i64),
+        ("key_mask", c_vp), ("rel_bias", c_vp),
+        ("o", c_vp), ("ldo", c_i64), ("stats", c_vp),
+        ("batch", c_i64), ("seq_q", c_i64), ("seq_k", c_i64), ("heads", c_i64), ("head_dim", c_i64),
+        ("scale", c_f32), ("causal", c_i32), ("dropout_p", c_f32), ("reserved", c_i32), ("dropout_seed", C.c_uint64),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols the header declares (checked by the CPU test-suite)
 SIGNATURES = {
     "mmgl_version": (c_i32, []),
@@ -79,6 +90,8 @@ SIGNATURES = {
     "mmgl_sattn_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
                                  c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                  c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp]),
+    "mmgl_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
+    "mmgl_attn_bwd": (c_i32, [C.POINTER(AttnArgs), c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "mmgl_layernorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
     "mmgl_layernorm_bwd_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_layernorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz,
@@ -301,6 +314,43 @@ def sattn_bwd(d_o, q, k, v, o, stats, key_mask, dq, dk, dv, batch, seq, heads, h
         _check(lib().mmgl_sattn_bwd(_p(d_o), _ld(d_o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(stats),
                                     _p(key_mask), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv), batch, seq, heads,
                                     head_dim, float(scale), int(causal), _stream()), "mmgl_sattn_bwd")
+
+
+def _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
+               dropout_seed):
+    a = AttnArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v)
+    a.key_mask, a.rel_bias = _p(key_mask), _p(rel_bias)
+    a.o, a.ldo, a.stats = _p(o), _ld(o), _p(stats)
+    a.batch, a.seq_q, a.seq_k, a.heads, a.head_dim = batch, seq_q, seq_k, heads, head_dim
+    a.scale, a.causal, a.dropout_p, a.dropout_seed = float(scale), int(causal), float(dropout_p), int(dropout_seed)
+    return a
+
+
+def attn_fwd(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal,
+             dropout_p=0.0, dropout_seed=0):
+    """q, o: [B*seq_q, H] views; k, v: [B*seq_k, H] views; key_mask u8 [B,seq_k] or None; rel_bias fp32
+    [heads, seq_q+seq_k-1] or None (bias of (row, key) = rel_bias[h][key - row + seq_q - 1])."""
+    _req_cuda(q, k, v, key_mask, rel_bias, o, stats)
+    assert rel_bias is None or (rel_bias.dtype == torch.float32 and rel_bias.is_contiguous()
+                                and tuple(rel_bias.shape) == (heads, seq_q + seq_k - 1))
+    assert key_mask is None or (key_mask.dtype == torch.uint8 and key_mask.is_contiguous())
+    h = heads * head_dim
+    a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
+                   dropout_seed)
+    with _Timed("sattn_fwd", float(batch * (seq_q + seq_k) * h * 2 * 2)):
+        _check(lib().mmgl_attn_fwd(C.byref(a), _stream()), "mmgl_attn_fwd")
+
+
+def attn_bwd(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv, batch, seq_q, seq_k, heads, head_dim, scale, causal,
+             dropout_p=0.0, dropout_seed=0):
+    _req_cuda(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv)
+    h = heads * head_dim
+    a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
+                   dropout_seed)
+    with _Timed("sattn_bwd", float(batch * (seq_q + seq_k) * h * 2 * 4)):
+        _check(lib().mmgl_attn_bwd(C.byref(a), _p(d_o), _ld(d_o), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
+                                   _stream()), "mmgl_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------- layernorm

@@ -68,7 +68,20 @@ struct GemmParams {
 // activation codes of mmgl_gemm_args.relu: 1 = ReLU, 2 = GELU (erf form, nn.GELU / HF "gelu"), 3 = quick-GELU (CLIP)
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == 2) {
+    // 0.5 v (1 + erf(v / sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding
+    // of the output): one rcp + one ex2 and no branches, ~3x fewer issue slots than erff() in a short-K epilogue.
+    // q = 1 - erf(z), z = |v| / sqrt2, is formed directly so the negative side does not cancel.
+    const float z = fabsf(v) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float q = poly * t * exp2f(-1.4426950408889634f * z * z);
+    const float hv = 0.5f * v;
+    return v >= 0.f ? fmaf(-hv, q, v) : hv * q;
+  }
   return v / (1.f + __expf(-1.702f * v));
 }
 

@@ -1,18 +1,26 @@
-// Causal / key-padded self-attention of the frozen decoder layers, tcgen05 + TMEM + TMA.
+// Self-attention of the decoder / encoder layers (SURVEY 8f row f1 and the concat path, row a7), tcgen05 + TMEM + TMA.
 //
-//   O = softmax(max(scale * Q K^T + causal + key-padding, finfo.min)) V      per (sample, head)
+//   O = dropout(softmax(max(scale * Q K^T + rel_bias + causal + key-padding, finfo.min))) V      per (sample, head)
 //
-// Reference: MPTAttention self branch, model/modelling_cross_attention.py:201-275 with the additive mask built at
-// :455-476 (causal AND key-not-padding).  Sequences here are short (S <= ~1200), so the kernels use 128 x 128 score blocks
-// and a TWO-PASS softmax instead of online rescaling: pass 1 recomputes nothing but the row maximum (S = Q K_j^T per key
-// block), pass 2 recomputes S, exponentiates against the final maximum and accumulates O += P_j V_j in TMEM.  One extra
-// QK^T per block buys the absence of any accumulator correction; the tensor pipe is far from the limit at these sizes.
+// References: MPTAttention self branch, model/modelling_cross_attention.py:201-275 with the additive mask built at
+// :455-476 (causal AND key-not-padding); the HF T5 / OPT attention that model/modelling_self_attention.py:332 runs
+// (T5: no 1/sqrt(d) scaling, additive relative-position bias, dropout on the probabilities; queries and keys of
+// different lengths in the decoder's cross-attention).  Sequences here are short (S <= ~1200), so the kernels use
+// 128 x 128 score blocks and a TWO-PASS softmax instead of online rescaling: pass 1 computes only the row maximum
+// (S = Q K_j^T per key block), pass 2 recomputes S, exponentiates against the final maximum and accumulates
+// O += P_j V_j in TMEM.  One extra QK^T per block buys the absence of any accumulator correction.
 //
-//   forward : CTA = (128-query tile, head, sample); K/V blocks double-buffered by TMA; only blocks j <= i when causal
+//   forward : CTA = TWO 128-query tiles of one (head, sample) in ping-pong: 8 softmax warps (4 per tile, one thread per
+//             score row = one TMEM lane, so the softmax needs no shuffles), one MMA-issuing warp and one TMA warp.  The
+//             K / V blocks stream once through a 3-stage ring for both tiles; while one tile's warps exponentiate, the
+//             tensor core runs the other tile's P V and next Q K^T.  Only blocks at or below the diagonal are visited
+//             when causal (tiles are paired heavy-with-next-heavy, heavy pairs first).
 //   backward: dQ kernel   CTA = (query tile i): loops key blocks j, dQ_i += dS_ij K_j            (accumulates in TMEM)
 //             dK/dV kernel CTA = (key block j): loops query tiles i, dV_j += P_ij^T dO_i, dK_j += dS_ij^T Q_i (TMEM)
 //             both recompute S and dP = dO V^T from Q, K, V, dO and the saved row statistics (m, 1/l).
-// Each of the 128 threads owns one score row = one TMEM lane, so the softmax needs no shuffles.
+// Masks are bit masks: one 32-bit word per 32 keys (attend = exists AND not padding), built once per CTA; the causal
+// limit of the diagonal block is a per-thread shift.  Interior blocks (all 128 keys attended, not diagonal, no bias)
+// take a 3-instruction-per-score path.
 #include <cfloat>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,25 +37,44 @@ namespace {
 
 constexpr float kL2E = 1.4426950408889634f;
 
+struct AttnParams {
+  const uint8_t* key_mask;   // [B, seq_k] or null
+  const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
+  int seq_q, seq_k, heads, causal;
+  float scale;
+  uint32_t drop_thresh;      // 0: no dropout; else round(p * 65536)
+  float drop_scale;          // 1 / (1 - p)
+  uint64_t drop_seed;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t swz(uint32_t slab_base, int row, int chunk) {
   return slab_base + row * 128 + (((chunk ^ (row & 7)) & 7) << 4);
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// masked score of (query row, key col): scale * s where attended, -FLT_MAX where masked (the reference's finfo.min after
-// the clamp), -inf for keys beyond the sequence (they do not exist in the reference)
-__device__ __forceinline__ float masked_score(float s, float scale, uint8_t key_flag, int key, int row, int causal) {
-  if (key_flag != 0) return key_flag == 1 ? -FLT_MAX : -INFINITY;
-  if (causal && key > row) return -FLT_MAX;
-  return fmaxf(s * scale, -FLT_MAX);
+// the low n bits set (n may be <= 0 or >= 32)
+__device__ __forceinline__ uint32_t low_bits(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
+
+// attend bits of the whole key range of sample b: word w covers keys [32w, 32w + 32); bit = key exists and is not padding.
+// All threads of the CTA must call (full warps).
+__device__ __forceinline__ void build_key_bits(uint32_t* kbits, const uint8_t* key_mask, int b, int seq_k, int nwords) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int w = warp; w < nwords; w += nwarps) {
+    const int key = w * 32 + lane;
+    const bool a = key < seq_k && (key_mask == nullptr || key_mask[(int64_t)b * seq_k + key] != 0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) kbits[w] = bits;
+  }
 }
-// key flags of one 128-key block into smem: 0 = attend, 1 = padding key (masked), 2 = beyond the sequence
-__device__ __forceinline__ void load_key_flags(uint8_t* dst, const uint8_t* key_mask, int b, int seq, int k0, int tid) {
-  const int key = k0 + tid;
-  uint8_t f = 2;
-  if (key < seq) f = (key_mask == nullptr || key_mask[(int64_t)b * seq + key]) ? 0 : 1;
-  dst[tid] = f;
+__device__ __forceinline__ bool block_all_attended(const uint32_t* kbits, int j) {
+  const uint4 w = *reinterpret_cast<const uint4*>(kbits + 4 * j);
+  return (w.x & w.y & w.z & w.w) == 0xffffffffu;
 }
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
 #pragma unroll
@@ -59,6 +86,17 @@ __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_
     v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * mul, __uint_as_float(r[8 * g + 7]) * mul);
     *reinterpret_cast<uint4*>(dst + 8 * g) = v;
   }
+}
+// keep bits (bit e = element e kept) of 32 consecutive keys starting at key0 (multiple of 32) of dropout row `drow`
+__device__ __forceinline__ uint32_t keep_word(const AttnParams& p, int64_t drow, int key0, int64_t groups_per_row) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const DropBits bits = dropout_bits(p.drop_seed, drow, (key0 >> 3) + g, groups_per_row);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w |= dropout_keep(bits, e, p.drop_thresh) ? (1u << (8 * g + e)) : 0u;
+  }
+  return w;
 }
 
 // issue S[128 x 128] = A[128 x D] * B[128 x D]^T (both K-major tiles of DS 64-wide slabs) into TMEM column `col`
@@ -101,185 +139,289 @@ __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, u
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// barrier indices of the forward kernel
+template <int NS> struct FwdBars {
+  static constexpr int qfull = 0;            // [2]  Q tile t landed
+  static constexpr int kfull = 2;            // [NS] K stage landed
+  static constexpr int kfree = 2 + NS;       // [NS] every MMA reading the K stage has completed
+  static constexpr int vfull = 2 + 2 * NS;   // [NS]
+  static constexpr int vfree = 2 + 3 * NS;   // [NS]
+  static constexpr int sfull = 2 + 4 * NS;   // [2]  S_t = Q_t K_j^T complete in TMEM
+  static constexpr int sfree = 4 + 4 * NS;   // [2]  pass 1: tile t's 128 threads have read S_t
+  static constexpr int pfull = 6 + 4 * NS;   // [2]  pass 2: tile t's P block is in shared memory (128 arrivals)
+  static constexpr int pfree = 8 + 4 * NS;   // [2]  P_t V_j complete: P buffer reusable, O_t updated
+  static constexpr int count = 10 + 4 * NS;
+};
+
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(320, 1)
 sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                 const __grid_constant__ CUtensorMap map_v, const uint8_t* __restrict__ key_mask,
-                 __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats, int seq, int heads, float scale,
-                 int causal, uint32_t tmem_cols) {
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p,
+                 __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats) {
   constexpr int TB = (D / 64) * 16384;   // bytes of one [128][D] tile
+  constexpr int NS = (D == 64) ? 3 : 1;  // K / V ring stages
+  using B = FwdBars<NS>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TB;          // 2 buffers
-  uint8_t* sV = sK + 2 * TB;      // 2 buffers
-  uint8_t* sP = sV + 2 * TB;      // [128][128] bf16 = 2 slabs
-  uint8_t* sFlag = sP + 32768;   // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sFlag + 256);   // q, k0, k1, v0, v1, s, o
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  uint8_t* sQ = smem;                    // 2 tiles
+  uint8_t* sK = sQ + 2 * TB;             // NS stages
+  uint8_t* sV = sK + NS * TB;            // NS stages
+  uint8_t* sP = sV + NS * TB;            // 2 x [128][128] bf16 (2 slabs each)
+  const int nbk = (p.seq_k + 127) / 128;
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(sP + 2 * 32768);   // 4 * nbk words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk + ((4 * nbk) & 1));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + B::count);
 
-  const int ntiles = (seq + 127) / 128;
-  const int qt = ntiles - 1 - (int)blockIdx.x;   // heavy (late) query tiles first
+  const int ntq = (p.seq_q + 127) / 128;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
-  const int r0 = qt * 128, row = r0 + tid;
-  const int nblk = causal ? qt + 1 : ntiles;
-  const int colq = h * D, rowb = b * seq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile 0 of the pair is the later (heavier when causal) query tile; tile 1 the one before it (absent if < 0)
+  const int qt0 = ntq - 1 - 2 * (int)blockIdx.x;
+  const int qts[2] = {qt0, qt0 - 1};
+  const int nblk[2] = {p.causal ? qt0 + 1 : nbk, qt0 - 1 < 0 ? 0 : (p.causal ? qt0 : nbk)};
+  const int nbmax = nblk[0];
+  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < B::count; ++i) {
+      const bool wide = (i >= B::sfree && i < B::sfree + 2) || (i >= B::pfull && i < B::pfull + 2);
+      mbar_init(&bars[i], wide ? 128 : 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
+  if (warp == 8) tmem_alloc<512>(tmem_ptr);
+  build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t cO = 128;
-  uint32_t kuse[2] = {0, 0}, vuse[2] = {0, 0}, sphase = 0, ophase = 0;   // thread 0 / all threads phase counters
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], TB);
-    tma_tile<D>(sQ, &map_q, &bars[0], colq, rowb + r0);
-    mbar_arrive_expect_tx(&bars[1], TB);
-    tma_tile<D>(sK, &map_k, &bars[1], colq, rowb);
-  }
-  // ---------------- pass 1: row maximum (raw_mx: unscaled maximum over the unmasked interior blocks)
-  float mx = -FLT_MAX, raw_mx = -FLT_MAX;
-  for (int j = 0; j < nblk; ++j) {
-    const int buf = j & 1;
-    load_key_flags(sFlag + buf * 128, key_mask, b, seq, j * 128, tid);
-    if (tid == 0) {
-      if (j + 1 < nblk) {
-        mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], TB);
-        tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowb + (j + 1) * 128);
-      }
-      if (j == 0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1 + buf], kuse[buf] & 1); kuse[buf]++;
-      tc_fence_after();
-      mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));
-      umma_commit(&bars[5]);
-    }
-    // key flags visible; a block needs the per-element mask path only if it holds a padding / out-of-range key, or
-    // is the diagonal block of a causal problem -- interior blocks take the 1-instruction-per-score path
-    const bool masked = __syncthreads_or(sFlag[buf * 128 + tid] != 0) || (causal && j == qt);
-    mbar_wait(&bars[5], sphase & 1); sphase++;
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_ld_wait();
-      if (masked) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          mx = fmaxf(mx, masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, __uint_as_float(r[e]));
-      }
-    }
-    tc_fence_before();
-    __syncthreads();   // S fully read before the next block's MMA overwrites it
-    tc_fence_after();
-  }
-  // ---------------- pass 2: P = exp(x - max), O += P V
-  if (tid == 0) {
-    const int b0 = 0;
-    mbar_arrive_expect_tx(&bars[1 + b0], TB);
-    tma_tile<D>(sK + b0 * TB, &map_k, &bars[1 + b0], colq, rowb);
-    mbar_arrive_expect_tx(&bars[3 + b0], TB);
-    tma_tile<D>(sV + b0 * TB, &map_v, &bars[3 + b0], colq, rowb);
-  }
-  mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
-  const float c1 = scale * kL2E, mxc = mx * kL2E;
-  float sum = 0.f;
-  const uint32_t p_base = smem_u32(sP);
-  for (int j = 0; j < nblk; ++j) {
-    const int buf = j & 1;
-    load_key_flags(sFlag + buf * 128, key_mask, b, seq, j * 128, tid);
-    if (tid == 0) {
-      if (j + 1 < nblk) {
-        mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], TB);
-        tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowb + (j + 1) * 128);
-        mbar_arrive_expect_tx(&bars[3 + (buf ^ 1)], TB);
-        tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[3 + (buf ^ 1)], colq, rowb + (j + 1) * 128);
-      }
-      mbar_wait(&bars[1 + buf], kuse[buf] & 1); kuse[buf]++;
-      tc_fence_after();
-      mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));
-      umma_commit(&bars[5]);
-    }
-    const bool masked = __syncthreads_or(sFlag[buf * 128 + tid] != 0) || (causal && j == qt);
-    mbar_wait(&bars[5], sphase & 1); sphase++;
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-      if (masked) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float x0 = masked_score(__uint_as_float(r[e]), scale, sFlag[buf * 128 + c * 32 + e], j * 128 + c * 32 + e, row, causal);
-          const float x1 = masked_score(__uint_as_float(r[e + 1]), scale, sFlag[buf * 128 + c * 32 + e + 1], j * 128 + c * 32 + e + 1, row, causal);
-          const float p0 = exp2f((x0 - mx) * kL2E), p1 = exp2f((x1 - mx) * kL2E);
-          sum += p0 + p1;
-          pk[e >> 1] = pack_bf16(p0, p1);
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t)
+        if (nblk[t] > 0) {
+          mbar_arrive_expect_tx(&bars[B::qfull + t], TB);
+          tma_tile<D>(sQ + t * TB, &map_q, &bars[B::qfull + t], colq, rowq + qts[t] * 128);
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(r[e]), c1, -mxc)), p1 = exp2f(fmaf(__uint_as_float(r[e + 1]), c1, -mxc));
-          sum += p0 + p1;
-          pk[e >> 1] = pack_bf16(p0, p1);
+      for (int n = 0; n < 2 * nbmax; ++n) {           // K block stream: pass 1 then pass 2
+        const int j = n < nbmax ? n : n - nbmax, s = n % NS;
+        if (n >= NS) mbar_wait(&bars[B::kfree + s], ((n / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[B::kfull + s], TB);
+        tma_tile<D>(sK + s * TB, &map_k, &bars[B::kfull + s], colq, rowk + j * 128);
+        if (n >= nbmax) {                               // pass 2: V block j rides along
+          const int sv = j % NS;
+          if (j >= NS) mbar_wait(&bars[B::vfree + sv], ((j / NS) - 1) & 1);
+          mbar_arrive_expect_tx(&bars[B::vfull + sv], TB);
+          tma_tile<D>(sV + sv * TB, &map_v, &bars[B::vfull + sv], colq, rowk + j * 128);
         }
       }
-      const uint32_t slab = p_base + (c >> 1) * 16384;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) sts128(swz(slab, tid, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&bars[3 + buf], vuse[buf] & 1); vuse[buf]++;
-      tc_fence_after();
-      mma_pv<D>(tmem_base + cO, p_base, smem_u32(sV + buf * TB), j != 0);
-      umma_commit(&bars[6]);
     }
     __syncwarp();
-    mbar_wait(&bars[6], ophase & 1); ophase++;   // P tile, V buffer and the S columns are free again
-    tc_fence_after();
-  }
-  const float inv = 1.f / sum;
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t q_addr[2] = {smem_u32(sQ), smem_u32(sQ + TB)};
+      const uint32_t p_addr[2] = {smem_u32(sP), smem_u32(sP + 32768)};
+      const uint32_t cS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t cO[2] = {tmem_base + 256, tmem_base + 256 + D};
+      for (int t = 0; t < 2; ++t)
+        if (nblk[t] > 0) mbar_wait(&bars[B::qfull + t], 0);
+      // pass 1: S_t(j) for the row maxima
+      for (int j = 0; j < nbmax; ++j) {
+        const int s = j % NS;
+        mbar_wait(&bars[B::kfull + s], (j / NS) & 1);
+        for (int t = 0; t < 2; ++t)
+          if (j < nblk[t]) {
+            if (j > 0) mbar_wait(&bars[B::sfree + t], (j - 1) & 1);
+            tc_fence_after();
+            mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
+            umma_commit(&bars[B::sfull + t]);
+          }
+        umma_commit(&bars[B::kfree + s]);
+      }
+      // pass 2 prologue: S_t(0)
+      {
+        const int n = nbmax, s = n % NS;
+        mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
+        for (int t = 0; t < 2; ++t)
+          if (nblk[t] > 0) {
+            mbar_wait(&bars[B::sfree + t], (nblk[t] - 1) & 1);
+            tc_fence_after();
+            mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
+            umma_commit(&bars[B::sfull + t]);
+          }
+        umma_commit(&bars[B::kfree + s]);
+      }
+      // pass 2: per tile, O_t += P_t(j) V_j followed at once by S_t(j + 1), so tile t's warps wait for two MMAs only
+      for (int j = 0; j < nbmax; ++j) {
+        const int sv = j % NS;
+        for (int t = 0; t < 2; ++t)
+          if (j < nblk[t]) {
+            const bool last_user = (t == 1) || (j >= nblk[1]);   // last tile that reads K / V block j (and j + 1)
+            mbar_wait(&bars[B::pfull + t], j & 1);
+            mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
+            tc_fence_after();
+            mma_pv<D>(cO[t], p_addr[t], smem_u32(sV + sv * TB), j != 0);
+            umma_commit(&bars[B::pfree + t]);
+            if (last_user) umma_commit(&bars[B::vfree + sv]);
+            if (j + 1 < nblk[t]) {
+              const int n = nbmax + j + 1, s = n % NS;
+              mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
+              tc_fence_after();
+              mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
+              umma_commit(&bars[B::sfull + t]);
+              if ((t == 1) || (j + 1 >= nblk[1])) umma_commit(&bars[B::kfree + s]);
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax warps: tile t = warp / 4
+    const int t = warp >> 2;
+    const int nb = nblk[t];
+    if (nb > 0) {
+      const int qt = qts[t];
+      const int tid = threadIdx.x & 127;
+      const int row = qt * 128 + tid;
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      const uint32_t cS = lane_addr + t * 128, cO = lane_addr + 256 + t * D;
+      const float scale = p.scale;
+      const bool has_bias = p.rel_bias != nullptr;
+      // bias of (row, key) = bias_row[key]  (bias_row points at the entry of key 0; negative offsets are valid memory)
+      const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+      uint32_t sphase = 0;
+      // ---------------- pass 1: row maximum
+      float mx = -FLT_MAX;     // natural units (bias / masked paths)
+      float raw_mx = -FLT_MAX; // unscaled (interior path)
+      for (int j = 0; j < nb; ++j) {
+        const bool diag = p.causal && j == qt;
+        const bool plain = !has_bias && !diag && block_all_attended(kbits, j);
+        mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
+        tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld_32x32(cS, r[0]);
 #pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + cO + c * 32, r);
-    tmem_ld_wait();
-    if (row < seq) store_row_bf16(o + ((int64_t)rowb + row) * ldo + colq + c * 32, r, inv);
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(cS + (c + 1) * 32, r[(c + 1) & 1]);
+          const uint32_t(&rc)[32] = r[c & 1];
+          if (plain) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) raw_mx = fmaxf(raw_mx, fmaxf(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1])));
+          } else {
+            uint32_t m = kbits[4 * j + c];
+            if (diag) m &= low_bits(tid - c * 32 + 1);
+            const int key0 = j * 128 + c * 32;
+            if (has_bias) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float x = fmaf(__uint_as_float(rc[e]), scale, __ldg(bias_row + min(key0 + e, p.seq_k - 1)));
+                mx = fmaxf(mx, (m >> e) & 1u ? x : -FLT_MAX);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, (m >> e) & 1u ? __uint_as_float(rc[e]) : -FLT_MAX);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[B::sfree + t]);
+      }
+      if (raw_mx > -FLT_MAX) mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
+      // A row with no attended key at all (mx == -FLT_MAX): the reference's clamp makes every existing key's score
+      // finfo.min, i.e. uniform attention -> p = 1 on the existing keys of the visited blocks.
+      const bool none = !(mx > -FLT_MAX);
+      const float c1 = none ? 0.f : scale * kL2E, mxc = none ? 0.f : mx * kL2E, bsc = none ? 0.f : kL2E;
+      // ---------------- pass 2: P = exp(x - max), O += P V
+      float sum = 0.f;
+      const uint32_t p_base = smem_u32(sP + t * 32768);
+      const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
+      const int64_t dgroups = (p.seq_k + 7) >> 3;
+      for (int j = 0; j < nb; ++j) {
+        const bool diag = p.causal && j == qt;
+        const bool plain = !has_bias && !diag && block_all_attended(kbits, j);
+        mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
+        tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld_32x32(cS, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(cS + (c + 1) * 32, r[(c + 1) & 1]);
+          uint32_t(&rc)[32] = r[c & 1];
+          const int key0 = j * 128 + c * 32;
+          if (plain) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
+              sum += pe;
+              rc[e] = __float_as_uint(pe);
+            }
+          } else {
+            uint32_t m = kbits[4 * j + c];
+            if (diag) m &= low_bits(tid - c * 32 + 1);
+            if (none) m = low_bits(p.seq_k - key0);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float off = -mxc;
+              if (has_bias) off = fmaf(__ldg(bias_row + min(key0 + e, p.seq_k - 1)), bsc, -mxc);
+              float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, off));
+              pe = (m >> e) & 1u ? pe : 0.f;
+              sum += pe;
+              rc[e] = __float_as_uint(pe);
+            }
+          }
+          if (p.drop_thresh != 0) {
+            const uint32_t keep = keep_word(p, drow, key0, dgroups);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
+          }
+          if (c == 0 && j > 0) mbar_wait(&bars[B::pfree + t], (j - 1) & 1);   // P_t(j-1) V done: buffer reusable
+          const uint32_t slab = p_base + (c >> 1) * 16384;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            sts128(swz(slab, tid, (c & 1) * 4 + g),
+                   pack_bf16(__uint_as_float(rc[8 * g]), __uint_as_float(rc[8 * g + 1])),
+                   pack_bf16(__uint_as_float(rc[8 * g + 2]), __uint_as_float(rc[8 * g + 3])),
+                   pack_bf16(__uint_as_float(rc[8 * g + 4]), __uint_as_float(rc[8 * g + 5])),
+                   pack_bf16(__uint_as_float(rc[8 * g + 6]), __uint_as_float(rc[8 * g + 7])));
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars[B::pfull + t]);
+      }
+      mbar_wait(&bars[B::pfree + t], (nb - 1) & 1);   // all of O_t accumulated
+      tc_fence_after();
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(cO + c * 32, r);
+        tmem_ld_wait();
+        if (row < p.seq_q) store_row_bf16(o + ((int64_t)rowq + row) * ldo + colq + c * 32, r, inv);
+      }
+      if (row < p.seq_q)
+        *reinterpret_cast<float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2) = make_float2(mx, inv);
+    }
   }
-  if (row < seq) *reinterpret_cast<float2*>(stats + (((int64_t)b * heads + h) * seq + row) * 2) = make_float2(mx, inv);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, tmem_cols);
+  if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
 // per-row backward inputs of this thread: (max, 1/sum) and delta = rowsum(dO * O)
 template <int D>
 __device__ __forceinline__ void row_stats_delta(const float* stats, const __nv_bfloat16* o, int64_t ldo,
-                                                const __nv_bfloat16* d_o, int64_t lddo, int b, int h, int heads, int seq,
+                                                const __nv_bfloat16* d_o, int64_t lddo, int b, int h, int heads, int seq_q,
                                                 int row, float& m, float& inv, float& delta) {
   m = 0.f; inv = 0.f; delta = 0.f;
-  if (row >= seq) return;
-  const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * seq + row) * 2);
+  if (row >= seq_q) return;
+  const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * seq_q + row) * 2);
   m = st.x; inv = st.y;
-  const uint4* po = reinterpret_cast<const uint4*>(o + ((int64_t)b * seq + row) * ldo + h * D);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + ((int64_t)b * seq + row) * lddo + h * D);
+  const uint4* po = reinterpret_cast<const uint4*>(o + ((int64_t)b * seq_q + row) * ldo + h * D);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + ((int64_t)b * seq_q + row) * lddo + h * D);
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) {
     const uint4 vo = __ldg(po + i), vd = __ldg(pd + i);
@@ -290,33 +432,42 @@ __device__ __forceinline__ void row_stats_delta(const float* stats, const __nv_b
 }
 
 // P and dS of this thread's row for one 128-key block: reads S (col 0) and dP (col 128) from TMEM, writes bf16 tiles.
-// kMasked = false is the interior-block path (no padding key, not the causal diagonal, no ragged query tile).
-template <bool kWriteP, bool kMasked>
-__device__ __forceinline__ void softmax_grad_block(uint32_t lane_addr, const uint8_t* flags, int key0, int row, bool row_ok,
-                                                   int causal, float scale, float m, float inv, float delta,
-                                                   uint32_t p_base, uint32_t ds_base, int tid) {
-  const float c1 = scale * kL2E, mc = m * kL2E;
+//   P~  = keep/(1-p) . P      (tile for dV += P~^T dO; equals P without dropout)
+//   dS  = P . (keep/(1-p) . dP - delta)
+// words: this thread's attend bits of the 4 chunks (key bits AND causal limit; existing keys when the row has no
+// attended key).  plain = interior block: all attended, no bias.
+template <bool kWriteP>
+__device__ __forceinline__ void softmax_grad_block(const AttnParams& p, uint32_t lane_addr, const uint32_t (&words)[4],
+                                                   bool plain, const float* bias_row, int key0, bool row_ok, float m,
+                                                   float inv, float delta, int64_t drow, uint32_t p_base,
+                                                   uint32_t ds_base, int tid) {
+  const bool flat = !(m > -FLT_MAX) || !row_ok;   // no attended key (uniform row) or a row beyond the sequence (p = 0)
+  const float c1 = flat ? 0.f : p.scale * kL2E, mc = flat ? 0.f : m * kL2E, bsc = flat ? 0.f : kL2E;
+  const float inv_ok = row_ok ? inv : 0.f;
+  const int64_t dgroups = (p.seq_k + 7) >> 3;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t rs[32], rp[32];
     tmem_ld_32x32(lane_addr + c * 32, rs);
     tmem_ld_32x32(lane_addr + 128 + c * 32, rp);
     tmem_ld_wait();
+    const uint32_t mw = plain ? 0xffffffffu : words[c];
+    const bool drop = p.drop_thresh != 0;
+    const uint32_t keep = drop ? keep_word(p, drow, key0 + c * 32, dgroups) : 0xffffffffu;
+    const float ks = drop ? p.drop_scale : 1.f;
     uint32_t pk[16], dk[16];
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float pv[2], dv[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        float p;
-        if (kMasked) {
-          const float x = masked_score(__uint_as_float(rs[e + u]), scale, flags[c * 32 + e + u], key0 + c * 32 + e + u, row, causal);
-          p = row_ok ? exp2f((x - m) * kL2E) * inv : 0.f;
-        } else {
-          p = exp2f(fmaf(__uint_as_float(rs[e + u]), c1, -mc)) * inv;
-        }
-        pv[u] = p;
-        dv[u] = p * (__uint_as_float(rp[e + u]) - delta);
+        float off = -mc;
+        if (bias_row != nullptr) off = fmaf(__ldg(bias_row + min(key0 + c * 32 + e + u, p.seq_k - 1)), bsc, -mc);
+        float pr = ex2(fmaf(__uint_as_float(rs[e + u]), c1, off)) * inv_ok;
+        pr = (mw >> (e + u)) & 1u ? pr : 0.f;
+        const float kmul = (keep >> (e + u)) & 1u ? ks : 0.f;
+        pv[u] = pr * kmul;
+        dv[u] = pr * fmaf(__uint_as_float(rp[e + u]), kmul, -delta);
       }
       pk[e >> 1] = pack_bf16(pv[0], pv[1]);
       dk[e >> 1] = pack_bf16(dv[0], dv[1]);
@@ -329,15 +480,26 @@ __device__ __forceinline__ void softmax_grad_block(uint32_t lane_addr, const uin
   }
 }
 
+// this thread's attend words of key block j for query row (tile qt, lane tid)
+__device__ __forceinline__ void row_words(const AttnParams& p, const uint32_t* kbits4, int j, int qt, int tid, bool none,
+                                          uint32_t (&words)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t m = kbits4[c];
+    if (p.causal && j == qt) m &= low_bits(tid - c * 32 + 1);
+    if (none) m = low_bits(p.seq_k - (j * 128 + c * 32));   // uniform over the existing keys of the visited blocks
+    words[c] = m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward: dQ
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 1)
 sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                    const uint8_t* __restrict__ key_mask, const __nv_bfloat16* __restrict__ o, int64_t ldo,
+                    const __grid_constant__ AttnParams p, const __nv_bfloat16* __restrict__ o, int64_t ldo,
                     const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const float* __restrict__ stats,
-                    __nv_bfloat16* __restrict__ dq, int64_t lddq, int seq, int heads, float scale, int causal,
-                    uint32_t tmem_cols) {
+                    __nv_bfloat16* __restrict__ dq, int64_t lddq) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;   // K / V buffers
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -346,25 +508,27 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* sK = sdO + TB;
   uint8_t* sV = sK + NB * TB;
   uint8_t* sdS = sV + NB * TB;     // 2 slabs
-  uint8_t* sFlag = sdS + 32768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sFlag + 256);   // q, kv0, kv1, a, b
+  const int nbk = (p.seq_k + 127) / 128;
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(sdS + 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk + ((4 * nbk) & 1));   // q, kv0, kv1, a, b
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int ntiles = (seq + 127) / 128;
-  const int qt = ntiles - 1 - (int)blockIdx.x;
+  const int ntq = (p.seq_q + 127) / 128;
+  const int qt = ntq - 1 - (int)blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int r0 = qt * 128, row = r0 + tid;
-  const bool row_ok = row < seq;
-  const int nblk = causal ? qt + 1 : ntiles;
-  const int colq = h * D, rowb = b * seq;
+  const bool row_ok = row < p.seq_q;
+  const int nblk = p.causal ? qt + 1 : nbk;
+  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -375,23 +539,26 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], 2 * TB);
-    tma_tile<D>(sQ, &map_q, &bars[0], colq, rowb + r0);
-    tma_tile<D>(sdO, &map_do, &bars[0], colq, rowb + r0);
+    tma_tile<D>(sQ, &map_q, &bars[0], colq, rowq + r0);
+    tma_tile<D>(sdO, &map_do, &bars[0], colq, rowq + r0);
     mbar_arrive_expect_tx(&bars[1], 2 * TB);
-    tma_tile<D>(sK, &map_k, &bars[1], colq, rowb);
-    tma_tile<D>(sV, &map_v, &bars[1], colq, rowb);
+    tma_tile<D>(sK, &map_k, &bars[1], colq, rowk);
+    tma_tile<D>(sV, &map_v, &bars[1], colq, rowk);
   }
   float m, inv, delta;
-  row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, heads, seq, row, m, inv, delta);
+  row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, p.heads, p.seq_q, row, m, inv, delta);
+  const bool none = !(m > -FLT_MAX);
+  const bool has_bias = p.rel_bias != nullptr;
+  const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+  const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
 
   for (int j = 0; j < nblk; ++j) {
     const int buf = (NB == 2) ? (j & 1) : 0;
-    load_key_flags(sFlag + (j & 1) * 128, key_mask, b, seq, j * 128, tid);
     if (tid == 0) {
       if (NB == 2 && j + 1 < nblk) {
         mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
-        tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowb + (j + 1) * 128);
-        tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowb + (j + 1) * 128);
+        tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
+        tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
       }
       if (j == 0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
@@ -400,15 +567,14 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
       umma_commit(&bars[3]);
     }
-    const bool masked = __syncthreads_or(sFlag[(j & 1) * 128 + tid] != 0) || (causal && j == qt) || (r0 + 128 > seq);
+    const bool plain = !has_bias && !(p.causal && j == qt) && block_all_attended(kbits, j);
+    uint32_t words[4];
+    row_words(p, kbits + 4 * j, j, qt, tid, none, words);
+    __syncwarp();
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    if (masked)
-      softmax_grad_block<false, true>(lane_addr, sFlag + (j & 1) * 128, j * 128, row, row_ok, causal, scale, m, inv, delta, 0,
-                                      smem_u32(sdS), tid);
-    else
-      softmax_grad_block<false, false>(lane_addr, sFlag + (j & 1) * 128, j * 128, row, row_ok, causal, scale, m, inv, delta,
-                                       0, smem_u32(sdS), tid);
+    softmax_grad_block<false>(p, lane_addr, words, plain, bias_row, j * 128, row_ok, m, inv, delta, drow, 0,
+                              smem_u32(sdS), tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -419,8 +585,8 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (NB == 1 && j + 1 < nblk) {   // single buffer: reload K / V once this block's MMAs have drained
         mbar_wait(&bars[4], bphase & 1);
         mbar_arrive_expect_tx(&bars[1], 2 * TB);
-        tma_tile<D>(sK, &map_k, &bars[1], colq, rowb + (j + 1) * 128);
-        tma_tile<D>(sV, &map_v, &bars[1], colq, rowb + (j + 1) * 128);
+        tma_tile<D>(sK, &map_k, &bars[1], colq, rowk + (j + 1) * 128);
+        tma_tile<D>(sV, &map_v, &bars[1], colq, rowk + (j + 1) * 128);
       }
     }
     __syncwarp();
@@ -432,22 +598,21 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint32_t r[32];
     tmem_ld_32x32(lane_addr + cdQ + c * 32, r);
     tmem_ld_wait();
-    if (row_ok) store_row_bf16(dq + ((int64_t)rowb + row) * lddq + colq + c * 32, r, scale);
+    if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + c * 32, r, p.scale);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, tmem_cols);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 1)
 sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                      const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                     const uint8_t* __restrict__ key_mask, const __nv_bfloat16* __restrict__ o, int64_t ldo,
+                     const __grid_constant__ AttnParams p, const __nv_bfloat16* __restrict__ o, int64_t ldo,
                      const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const float* __restrict__ stats,
-                     __nv_bfloat16* __restrict__ dk, int64_t lddk, __nv_bfloat16* __restrict__ dv, int64_t lddv,
-                     int seq, int heads, float scale, int causal, uint32_t tmem_cols) {
+                     __nv_bfloat16* __restrict__ dk, int64_t lddk, __nv_bfloat16* __restrict__ dv, int64_t lddv) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;   // Q / dO buffers
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -457,52 +622,59 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* sdO = sQ + NB * TB;
   uint8_t* sP = sdO + NB * TB;     // 2 slabs
   uint8_t* sdS = sP + 32768;       // 2 slabs
-  uint8_t* sFlag = sdS + 32768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sFlag + 128);   // kv, q0, q1, a, b
+  uint32_t* kbits4 = reinterpret_cast<uint32_t*>(sdS + 32768);   // the 4 words of this key block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits4 + 4);     // kv, q0, q1, a, b
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int ntiles = (seq + 127) / 128;
+  const int ntq = (p.seq_q + 127) / 128;
   const int kb = blockIdx.x;   // key block; early key blocks see the most query tiles and come first
   const int h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
-  const int i0 = causal ? kb : 0;
-  const int colq = h * D, rowb = b * seq;
+  const int warp = threadIdx.x >> 5, tid = threadIdx.x, lane = threadIdx.x & 31;
+  const int i0 = p.causal ? kb : 0;
+  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
-  load_key_flags(sFlag, key_mask, b, seq, kb * 128, tid);
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  {
+    const int key = kb * 128 + tid;
+    const bool a = key < p.seq_k && (p.key_mask == nullptr || p.key_mask[(int64_t)b * p.seq_k + key] != 0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) kbits4[warp] = bits;
+  }
   tc_fence_before();
-  const bool blk_flagged = __syncthreads_or(sFlag[tid] != 0);
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const uint32_t cdV = 256, cdK = 256 + D;
   uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0;
+  const bool has_bias = p.rel_bias != nullptr;
+  const bool blk_all = (kbits4[0] & kbits4[1] & kbits4[2] & kbits4[3]) == 0xffffffffu;
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], 2 * TB);
-    tma_tile<D>(sK, &map_k, &bars[0], colq, rowb + kb * 128);
-    tma_tile<D>(sV, &map_v, &bars[0], colq, rowb + kb * 128);
+    tma_tile<D>(sK, &map_k, &bars[0], colq, rowk + kb * 128);
+    tma_tile<D>(sV, &map_v, &bars[0], colq, rowk + kb * 128);
     mbar_arrive_expect_tx(&bars[1], 2 * TB);
-    tma_tile<D>(sQ, &map_q, &bars[1], colq, rowb + i0 * 128);
-    tma_tile<D>(sdO, &map_do, &bars[1], colq, rowb + i0 * 128);
+    tma_tile<D>(sQ, &map_q, &bars[1], colq, rowq + i0 * 128);
+    tma_tile<D>(sdO, &map_do, &bars[1], colq, rowq + i0 * 128);
   }
-  for (int i = i0; i < ntiles; ++i) {
+  for (int i = i0; i < ntq; ++i) {
     const int it = i - i0;
     const int buf = (NB == 2) ? (it & 1) : 0;
     const int row = i * 128 + tid;
-    const bool row_ok = row < seq;
+    const bool row_ok = row < p.seq_q;
     float m, inv, delta;
-    row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, heads, seq, row, m, inv, delta);
+    row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, p.heads, p.seq_q, row, m, inv, delta);
     if (tid == 0) {
-      if (NB == 2 && i + 1 < ntiles) {
+      if (NB == 2 && i + 1 < ntq) {
         mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
-        tma_tile<D>(sQ + (buf ^ 1) * TB, &map_q, &bars[1 + (buf ^ 1)], colq, rowb + (i + 1) * 128);
-        tma_tile<D>(sdO + (buf ^ 1) * TB, &map_do, &bars[1 + (buf ^ 1)], colq, rowb + (i + 1) * 128);
+        tma_tile<D>(sQ + (buf ^ 1) * TB, &map_q, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
+        tma_tile<D>(sdO + (buf ^ 1) * TB, &map_do, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
       }
       if (it == 0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1 + buf], quse[buf] & 1); quse[buf]++;
@@ -511,28 +683,30 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mma_qk<D>(tmem_base + 128, smem_u32(sdO + buf * TB), smem_u32(sV));   // dP = dO_i V_j^T
       umma_commit(&bars[3]);
     }
+    const bool none = !(m > -FLT_MAX);
+    const bool plain = !has_bias && blk_all && !(p.causal && i == kb);
+    uint32_t words[4];
+    row_words(p, kbits4, kb, i, tid, none, words);
+    const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+    const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
     __syncwarp();
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    if (blk_flagged || (causal && i == kb) || (i * 128 + 128 > seq))
-      softmax_grad_block<true, true>(lane_addr, sFlag, kb * 128, row, row_ok, causal, scale, m, inv, delta, smem_u32(sP),
-                                     smem_u32(sdS), tid);
-    else
-      softmax_grad_block<true, false>(lane_addr, sFlag, kb * 128, row, row_ok, causal, scale, m, inv, delta, smem_u32(sP),
-                                      smem_u32(sdS), tid);
+    softmax_grad_block<true>(p, lane_addr, words, plain, bias_row, kb * 128, row_ok, m, inv, delta, drow, smem_u32(sP),
+                             smem_u32(sdS), tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_tn<D>(tmem_base + cdV, smem_u32(sP), smem_u32(sdO + buf * TB), it != 0);    // dV_j += P^T dO_i
+      mma_tn<D>(tmem_base + cdV, smem_u32(sP), smem_u32(sdO + buf * TB), it != 0);    // dV_j += P~^T dO_i
       mma_tn<D>(tmem_base + cdK, smem_u32(sdS), smem_u32(sQ + buf * TB), it != 0);    // dK_j += dS^T Q_i
       umma_commit(&bars[4]);
-      if (NB == 1 && i + 1 < ntiles) {
+      if (NB == 1 && i + 1 < ntq) {
         mbar_wait(&bars[4], bphase & 1);
         mbar_arrive_expect_tx(&bars[1], 2 * TB);
-        tma_tile<D>(sQ, &map_q, &bars[1], colq, rowb + (i + 1) * 128);
-        tma_tile<D>(sdO, &map_do, &bars[1], colq, rowb + (i + 1) * 128);
+        tma_tile<D>(sQ, &map_q, &bars[1], colq, rowq + (i + 1) * 128);
+        tma_tile<D>(sdO, &map_do, &bars[1], colq, rowq + (i + 1) * 128);
       }
     }
     __syncwarp();
@@ -545,74 +719,87 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     uint32_t r[32];
     tmem_ld_32x32(lane_addr + cdV + c * 32, r);
     tmem_ld_wait();
-    if (key < seq) store_row_bf16(dv + ((int64_t)rowb + key) * lddv + colq + c * 32, r, 1.f);
+    if (key < p.seq_k) store_row_bf16(dv + ((int64_t)rowk + key) * lddv + colq + c * 32, r, 1.f);
     tmem_ld_32x32(lane_addr + cdK + c * 32, r);
     tmem_ld_wait();
-    if (key < seq) store_row_bf16(dk + ((int64_t)rowb + key) * lddk + colq + c * 32, r, scale);
+    if (key < p.seq_k) store_row_bf16(dk + ((int64_t)rowk + key) * lddk + colq + c * 32, r, p.scale);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, tmem_cols);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 struct Maps { CUtensorMap q, k, v, d_o; };
 
 int build_maps(Maps& mp, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-               int64_t lddo, int64_t batch, int64_t seq, int64_t heads, int d) {
+               int64_t lddo, int64_t batch, int64_t seq_q, int64_t seq_k, int64_t heads, int d) {
   int rc;
-  const uint64_t cols = (uint64_t)(heads * d), rows = (uint64_t)(batch * seq);
-  if ((rc = make_tensor_map_2d(&mp.q, q, cols, rows, (uint64_t)ldq, 64, 128))) return rc;
-  if ((rc = make_tensor_map_2d(&mp.k, k, cols, rows, (uint64_t)ldk, 64, 128))) return rc;
-  if ((rc = make_tensor_map_2d(&mp.v, v, cols, rows, (uint64_t)ldv, 64, 128))) return rc;
-  if (d_o != nullptr && (rc = make_tensor_map_2d(&mp.d_o, d_o, cols, rows, (uint64_t)lddo, 64, 128))) return rc;
+  const uint64_t cols = (uint64_t)(heads * d), rows_q = (uint64_t)(batch * seq_q), rows_k = (uint64_t)(batch * seq_k);
+  if ((rc = make_tensor_map_2d(&mp.q, q, cols, rows_q, (uint64_t)ldq, 64, 128))) return rc;
+  if ((rc = make_tensor_map_2d(&mp.k, k, cols, rows_k, (uint64_t)ldk, 64, 128))) return rc;
+  if ((rc = make_tensor_map_2d(&mp.v, v, cols, rows_k, (uint64_t)ldv, 64, 128))) return rc;
+  if (d_o != nullptr && (rc = make_tensor_map_2d(&mp.d_o, d_o, cols, rows_q, (uint64_t)lddo, 64, 128))) return rc;
   return 0;
 }
 
+size_t kbits_bytes(int64_t seq_k) {
+  const size_t words = 4 * (size_t)((seq_k + 127) / 128);
+  return (words + (words & 1)) * 4;
+}
+
 template <int D>
-int launch_fwd(const Maps& mp, const uint8_t* key_mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq,
-               int64_t heads, float scale, int causal, cudaStream_t stream) {
+int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float* stats, int64_t batch, cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
-  const size_t smem = 5 * (size_t)TB + 32768 + 256 + 64;
-  const uint32_t tmem_cols = 256;   // S 128 + O D
+  constexpr int NS = (D == 64) ? 3 : 1;
+  const size_t smem = (2 + 2 * NS) * (size_t)TB + 65536 + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16;
   auto kern = sattn_fwd_kernel<D>;
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((seq + 127) / 128), (unsigned)heads, (unsigned)batch);
-  kern<<<grid, 128, smem, stream>>>(mp.q, mp.k, mp.v, key_mask, (__nv_bfloat16*)o, ldo, stats, (int)seq, (int)heads, scale,
-                                    causal, tmem_cols);
-  return check_launch("mmgl_sattn_fwd");
+  const int ntq = (p.seq_q + 127) / 128;
+  dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
+  kern<<<grid, 320, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
+  return check_launch("mmgl_attn_fwd");
 }
 
 template <int D>
-int launch_bwd(const Maps& mp, const uint8_t* key_mask, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+int launch_bwd(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
                const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch,
-               int64_t seq, int64_t heads, float scale, int causal, cudaStream_t stream) {
+               cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;
-  dim3 grid((unsigned)((seq + 127) / 128), (unsigned)heads, (unsigned)batch);
   {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 256 + 64;
+    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
     auto kern = sattn_bwd_dq_kernel<D>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, key_mask, (const __nv_bfloat16*)o, ldo,
-                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq, (int)seq, (int)heads,
-                                      scale, causal, 512u);
-    if (int rc = check_launch("mmgl_sattn_bwd(dq)")) return rc;
+    dim3 grid((unsigned)((p.seq_q + 127) / 128), (unsigned)p.heads, (unsigned)batch);
+    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
+                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq);
+    if (int rc = check_launch("mmgl_attn_bwd(dq)")) return rc;
   }
   {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 65536 + 128 + 64;
+    const size_t smem = (2 + 2 * NB) * (size_t)TB + 65536 + 16 + 5 * 8 + 16;
     auto kern = sattn_bwd_dkv_kernel<D>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, key_mask, (const __nv_bfloat16*)o, ldo,
-                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv,
-                                      (int)seq, (int)heads, scale, causal, 512u);
-    return check_launch("mmgl_sattn_bwd(dkv)");
+    dim3 grid((unsigned)((p.seq_k + 127) / 128), (unsigned)p.heads, (unsigned)batch);
+    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
+                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv);
+    return check_launch("mmgl_attn_bwd(dkv)");
   }
 }
 
-int check_args(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t d) {
-  MMGL_REQUIRE(batch > 0 && seq > 0 && heads > 0, "%s: empty problem", who);
-  MMGL_REQUIRE(d == 64 || d == 128, "%s: head_dim must be 64 or 128 (got %lld)", who, (long long)d);
-  MMGL_REQUIRE(batch < 65536 && heads < 65536, "%s: batch/heads too large for the grid", who);
+int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
+  MMGL_REQUIRE(a->batch > 0 && a->seq_q > 0 && a->seq_k > 0 && a->heads > 0, "%s: empty problem", who);
+  MMGL_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "%s: head_dim must be 64 or 128 (got %lld)", who, (long long)a->head_dim);
+  MMGL_REQUIRE(a->batch < 65536 && a->heads < 65536, "%s: batch/heads too large for the grid", who);
+  MMGL_REQUIRE(a->seq_k <= 8192 && a->seq_q <= (1 << 20), "%s: seq_k must be <= 8192", who);
+  MMGL_REQUIRE(!a->causal || a->seq_q == a->seq_k, "%s: causal needs seq_q == seq_k", who);
+  MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
+  MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
+  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias;
+  p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal;
+  p.scale = a->scale;
+  p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
+  p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
+  p.drop_seed = a->dropout_seed;
   return 0;
 }
 
@@ -621,18 +808,49 @@ int check_args(const char* who, int64_t batch, int64_t seq, int64_t heads, int64
 
 using namespace mmgl;
 
+extern "C" int mmgl_attn_fwd(const mmgl_attn_args* a, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_REQUIRE(a != nullptr, "mmgl_attn_fwd: null args");
+  MMGL_BIND(a->q, "mmgl_attn_fwd");
+  AttnParams p;
+  if (int rc = fill_params("mmgl_attn_fwd", a, p)) return rc;
+  MMGL_REQUIRE(a->k && a->v && a->o && a->stats && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) &&
+               a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0,
+               "mmgl_attn_fwd: pointers must be 16B aligned, leading dims %% 8 == 0");
+  Maps mp;
+  if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, nullptr, 0, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim)) return rc;
+  if (a->head_dim == 64) return launch_fwd<64>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
+  return launch_fwd<128>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
+}
+
+extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
+                             int64_t lddk, void* dv, int64_t lddv, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  MMGL_REQUIRE(a != nullptr, "mmgl_attn_bwd: null args");
+  MMGL_BIND(a->q, "mmgl_attn_bwd");
+  AttnParams p;
+  if (int rc = fill_params("mmgl_attn_bwd", a, p)) return rc;
+  MMGL_REQUIRE(d_o && a->k && a->v && a->o && a->stats && dq && dk && dv, "mmgl_attn_bwd: null pointer");
+  MMGL_REQUIRE(aligned16(d_o) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(dq) &&
+               aligned16(dk) && aligned16(dv), "mmgl_attn_bwd: pointers must be 16B aligned");
+  MMGL_REQUIRE(lddo % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && lddq % 8 == 0 &&
+               lddk % 8 == 0 && lddv % 8 == 0, "mmgl_attn_bwd: leading dims must be multiples of 8");
+  Maps mp;
+  if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, d_o, lddo, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim)) return rc;
+  if (a->head_dim == 64)
+    return launch_bwd<64>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, a->batch, s);
+  return launch_bwd<128>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, a->batch, s);
+}
+
+// the self-attention special case (seq_q == seq_k, no bias, no dropout) kept as its own entry points
 extern "C" int mmgl_sattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               const uint8_t* key_mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq,
                               int64_t heads, int64_t d, float scale, int32_t causal, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  MMGL_BIND(q, "mmgl_sattn_fwd");
-  if (int rc = check_args("mmgl_sattn_fwd", batch, seq, heads, d)) return rc;
-  MMGL_REQUIRE(k && v && o && stats && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && ldq % 8 == 0 &&
-               ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "mmgl_sattn_fwd: pointers must be 16B aligned, leading dims %% 8 == 0");
-  Maps mp;
-  if (int rc = build_maps(mp, q, ldq, k, ldk, v, ldv, nullptr, 0, batch, seq, heads, (int)d)) return rc;
-  if (d == 64) return launch_fwd<64>(mp, key_mask, o, ldo, stats, batch, seq, heads, scale, causal, s);
-  return launch_fwd<128>(mp, key_mask, o, ldo, stats, batch, seq, heads, scale, causal, s);
+  mmgl_attn_args a{};
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.key_mask = key_mask; a.o = o; a.ldo = ldo;
+  a.stats = stats; a.batch = batch; a.seq_q = seq; a.seq_k = seq; a.heads = heads; a.head_dim = d; a.scale = scale;
+  a.causal = causal;
+  return mmgl_attn_fwd(&a, stream_);
 }
 
 extern "C" int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
@@ -640,17 +858,9 @@ extern "C" int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int6
                               const uint8_t* key_mask, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
                               int64_t lddv, int64_t batch, int64_t seq, int64_t heads, int64_t d, float scale,
                               int32_t causal, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  MMGL_BIND(q, "mmgl_sattn_bwd");
-  if (int rc = check_args("mmgl_sattn_bwd", batch, seq, heads, d)) return rc;
-  MMGL_REQUIRE(d_o && k && v && o && stats && dq && dk && dv, "mmgl_sattn_bwd: null pointer");
-  MMGL_REQUIRE(aligned16(d_o) && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(dq) &&
-               aligned16(dk) && aligned16(dv), "mmgl_sattn_bwd: pointers must be 16B aligned");
-  MMGL_REQUIRE(lddo % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 &&
-               lddk % 8 == 0 && lddv % 8 == 0, "mmgl_sattn_bwd: leading dims must be multiples of 8");
-  Maps mp;
-  if (int rc = build_maps(mp, q, ldq, k, ldk, v, ldv, d_o, lddo, batch, seq, heads, (int)d)) return rc;
-  if (d == 64)
-    return launch_bwd<64>(mp, key_mask, o, ldo, d_o, lddo, stats, dq, lddq, dk, lddk, dv, lddv, batch, seq, heads, scale, causal, s);
-  return launch_bwd<128>(mp, key_mask, o, ldo, d_o, lddo, stats, dq, lddq, dk, lddk, dv, lddv, batch, seq, heads, scale, causal, s);
+  mmgl_attn_args a{};
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.key_mask = key_mask; a.o = const_cast<void*>(o);
+  a.ldo = ldo; a.stats = const_cast<float*>(stats); a.batch = batch; a.seq_q = seq; a.seq_k = seq; a.heads = heads;
+  a.head_dim = d; a.scale = scale; a.causal = causal;
+  return mmgl_attn_bwd(&a, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, stream_);
 }

@@ -405,42 +405,84 @@ def xattn_core(q, k, v, mask, heads):
     return XAttnCoreFn.apply(q, k, v, mask, heads)
 
 
+def _key_mask_u8(key_mask):
+    if key_mask is None:
+        return None
+    km = key_mask if key_mask.dtype == torch.uint8 else (key_mask != 0).to(torch.uint8)
+    return km.contiguous()
+
+
 class SelfAttnFn(torch.autograd.Function):
     """Causal / key-padded self-attention over a fused QKV projection [B,S,3H] (thirds = Q | K | V, heads interleaved
     in H): model/modelling_cross_attention.py:201-275 with the mask of :455-476.  Q is NOT pre-scaled: ``scale`` is
     applied to the scores inside the kernel.  Backward writes dQ | dK | dV straight into one [B,S,3H] buffer."""
 
     @staticmethod
-    def forward(ctx, qkv, key_mask, heads, causal, scale):
+    def forward(ctx, qkv, key_mask, heads, causal, scale, dropout_p):
         b, s, h3 = qkv.shape
         h = h3 // 3
         qkv2 = _as2d(qkv)
-        km = None
-        if key_mask is not None:
-            km = key_mask if key_mask.dtype == torch.uint8 else (key_mask != 0).to(torch.uint8)
-            km = km.contiguous()
+        km = _key_mask_u8(key_mask)
         o = _new(b * s, h, qkv2)
         stats = torch.empty((b, heads, s, 2), dtype=F32, device=qkv.device)
-        K.sattn_fwd(qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], km, o, stats, b, s, heads, h // heads, scale, causal)
+        seed = next_dropout_seed() if dropout_p > 0.0 else 0
+        K.attn_fwd(qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], km, None, o, stats, b, s, s, heads, h // heads, scale,
+                   causal, dropout_p, seed)
         ctx.save_for_backward(qkv2, o, stats, km)
-        ctx.cfg = (b, s, h, heads, bool(causal), float(scale))
+        ctx.cfg = (b, s, h, heads, bool(causal), float(scale), dropout_p, seed)
         return o.reshape(b, s, h)
 
     @staticmethod
     def backward(ctx, d_o):
         qkv2, o, stats, km = ctx.saved_tensors
-        b, s, h, heads, causal, scale = ctx.cfg
+        b, s, h, heads, causal, scale, dropout_p, seed = ctx.cfg
         dqkv = torch.empty_like(qkv2)
-        K.sattn_bwd(_as2d(d_o), qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], o, stats, km, dqkv[:, :h], dqkv[:, h:2 * h],
-                    dqkv[:, 2 * h:], b, s, heads, h // heads, scale, causal)
-        return dqkv.reshape(b, s, 3 * h), None, None, None, None
+        K.attn_bwd(_as2d(d_o), qkv2[:, :h], qkv2[:, h:2 * h], qkv2[:, 2 * h:], km, None, o, stats, dqkv[:, :h],
+                   dqkv[:, h:2 * h], dqkv[:, 2 * h:], b, s, s, heads, h // heads, scale, causal, dropout_p, seed)
+        return dqkv.reshape(b, s, 3 * h), None, None, None, None, None
 
 
-def self_attention(qkv, key_mask, heads, causal=True, scale=None):
+def self_attention(qkv, key_mask, heads, causal=True, scale=None, dropout_p=0.0):
     """qkv [B,S,3H] bf16 -> [B,S,H]; key_mask [B,S] (1 = real token) or None."""
     if scale is None:
         scale = (qkv.shape[-1] // 3 // heads) ** -0.5
-    return SelfAttnFn.apply(qkv, key_mask, heads, bool(causal), float(scale))
+    return SelfAttnFn.apply(qkv, key_mask, heads, bool(causal), float(scale), float(dropout_p))
+
+
+class AttnFn(torch.autograd.Function):
+    """General attention core over separate projections: q [B,Sq,H], k / v [B,Sk,H] (heads interleaved in H),
+    key_mask [B,Sk], optional additive relative-position bias rel_bias fp32 [heads, Sq+Sk-1] (bias of (row, key) =
+    rel_bias[h, key - row + Sq - 1]; treated as a constant) and dropout on the probabilities.  This is the attention of
+    the HF T5 / OPT language model that the concat path runs (model/modelling_self_attention.py:332): T5 uses
+    scale = 1, a bucketed relative-position bias and, in the decoder, cross-attention with Sq != Sk."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, rel_bias, heads, causal, scale, dropout_p):
+        b, sq, h = q.shape
+        sk = k.shape[1]
+        q2, k2, v2 = _as2d(q), _as2d(k), _as2d(v)
+        km = _key_mask_u8(key_mask)
+        rb = None if rel_bias is None else rel_bias.detach().to(F32).contiguous()
+        o = _new(b * sq, h, q2)
+        stats = torch.empty((b, heads, sq, 2), dtype=F32, device=q.device)
+        seed = next_dropout_seed() if dropout_p > 0.0 else 0
+        K.attn_fwd(q2, k2, v2, km, rb, o, stats, b, sq, sk, heads, h // heads, scale, causal, dropout_p, seed)
+        ctx.save_for_backward(q2, k2, v2, o, stats, km, rb)
+        ctx.cfg = (b, sq, sk, h, heads, bool(causal), float(scale), dropout_p, seed)
+        return o.reshape(b, sq, h)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q2, k2, v2, o, stats, km, rb = ctx.saved_tensors
+        b, sq, sk, h, heads, causal, scale, dropout_p, seed = ctx.cfg
+        dq, dk, dv = torch.empty_like(q2), torch.empty_like(k2), torch.empty_like(v2)
+        K.attn_bwd(_as2d(d_o), q2, k2, v2, km, rb, o, stats, dq, dk, dv, b, sq, sk, heads, h // heads, scale, causal,
+                   dropout_p, seed)
+        return dq.reshape(b, sq, h), dk.reshape(b, sk, h), dv.reshape(b, sk, h), None, None, None, None, None, None
+
+
+def attention(q, k, v, key_mask=None, rel_bias=None, heads=1, causal=False, scale=1.0, dropout_p=0.0):
+    return AttnFn.apply(q, k, v, key_mask, rel_bias, heads, bool(causal), float(scale), float(dropout_p))
 
 
 # --------------------------------------------------------------------------------------------- gated cross layer

@@ -121,6 +121,63 @@ def xattn_core(q: Tensor, k: Tensor, v: Tensor, mask: Tensor, num_heads: int) ->
     return o.transpose(1, 2).reshape(b, s, h), lse
 
 
+def attention_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int, scale: float = 1.0,
+                   key_mask: Optional[Tensor] = None, causal: bool = False, position_bias: Optional[Tensor] = None,
+                   prob_multiplier: Optional[Tensor] = None) -> Tensor:
+    """General attention core of the language models on the concat path: Q[B,Sq,H], K,V[B,Sk,H] (heads interleaved),
+    byte key mask [B,Sk], additive position bias [1|B, nh, Sq, Sk], optional dropout multiplier [B,nh,Sq,Sk] applied to
+    the probabilities.  Restates HF T5Attention (HF: models/t5/modeling_t5.py:253-345 -- scores = q k^T with NO scaling,
+    += position_bias (+ mask), softmax in fp32, dropout, @ v) and the OPT / MPT self branch
+    (model/modelling_cross_attention.py:201-275: scaled q, additive finfo.min masks, clamp)."""
+    b, sq, h = q.shape
+    sk = k.shape[1]
+    d = h // num_heads
+    qh = q.view(b, sq, num_heads, d).transpose(1, 2)
+    kh = k.view(b, sk, num_heads, d).transpose(1, 2)
+    vh = v.view(b, sk, num_heads, d).transpose(1, 2)
+    w = (qh * scale) @ kh.transpose(-1, -2)
+    if position_bias is not None:
+        w = w + position_bias
+    add = torch.zeros(b, 1, sq, sk, dtype=w.dtype)
+    if key_mask is not None:
+        add = add + expand_mask(key_mask, w.dtype, sq)
+    if causal:
+        add = add + causal_mask(b, sq, w.dtype)
+    w = torch.max(w + add, torch.tensor(torch.finfo(w.dtype).min))
+    pr = F.softmax(w, dim=-1)
+    if prob_multiplier is not None:
+        pr = pr * prob_multiplier
+    return (pr @ vh).transpose(1, 2).reshape(b, sq, h)
+
+
+def t5_relative_position_bucket(relative_position: Tensor, bidirectional: bool, num_buckets: int = 32,
+                                max_distance: int = 128) -> Tensor:
+    """HF: models/t5/modeling_t5.py T5Attention._relative_position_bucket (relative_position = key - query)."""
+    rp = relative_position
+    buckets = torch.zeros_like(rp)
+    if bidirectional:
+        num_buckets //= 2
+        buckets = buckets + (rp > 0).long() * num_buckets
+        rp = rp.abs()
+    else:
+        rp = -torch.min(rp, torch.zeros_like(rp))
+    max_exact = num_buckets // 2
+    is_small = rp < max_exact
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (num_buckets - max_exact)).long()
+    large = torch.min(large, torch.full_like(large, num_buckets - 1))
+    return buckets + torch.where(is_small, rp, large)
+
+
+def t5_position_bias(table: Tensor, sq: int, sk: int, bidirectional: bool, num_buckets: int = 32,
+                     max_distance: int = 128) -> Tensor:
+    """[1, nh, sq, sk] additive bias from the [num_buckets, nh] embedding table (T5Attention.compute_bias)."""
+    ctx = torch.arange(sq)[:, None]
+    mem = torch.arange(sk)[None, :]
+    bucket = t5_relative_position_bucket(mem - ctx, bidirectional, num_buckets, max_distance)
+    return table[bucket].permute(2, 0, 1)[None]
+
+
 # ----------------------------------------------------------------------------
 # dropout (nn.functional.dropout, model/modelling_cross_attention.py:332, :356)
 # ----------------------------------------------------------------------------

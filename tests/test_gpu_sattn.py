@@ -80,3 +80,98 @@ def test_padding_keys_have_zero_influence():
     qkv2[:, 100:140, h:] = 55.0       # K and V of padding keys
     o2 = ops.self_attention(qkv2, key_mask.cuda(), heads)
     assert torch.equal(o1, o2)
+
+
+# ------------------------------------------------------------------------------------------------ general form
+def _rel_vec(gen, heads, sq, sk):
+    """a relative-position bias given as its per-distance vector [heads, sq + sk - 1] and as the dense [1,nh,sq,sk]"""
+    vec = torch.randn(heads, sq + sk - 1, generator=gen) * 1.5
+    idx = torch.arange(sk)[None, :] - torch.arange(sq)[:, None] + sq - 1
+    return vec, vec[:, idx][None]
+
+
+@pytest.mark.parametrize("b,sq,sk,heads,d,causal,bias,pad", [
+    (2, 128, 576, 2, 64, False, False, True),    # T5 decoder cross-attention: 128 queries over the encoder output
+    (2, 100, 333, 2, 64, False, False, True),
+    (1, 300, 300, 2, 64, True, True, False),     # T5 decoder self-attention: causal + relative bias
+    (2, 576, 576, 2, 64, False, True, True),     # T5 encoder self-attention: bidirectional bias + key padding
+    (2, 140, 140, 3, 64, True, True, True),
+    (1, 640, 640, 2, 64, True, False, True),     # 5 query tiles: pairs (4,3) (2,1) (0,-)
+    (1, 384, 384, 2, 64, False, False, False),   # 3 query tiles, all blocks interior
+    (1, 200, 130, 1, 128, False, True, True),    # head_dim 128
+])
+def test_general_attention_forward_backward(b, sq, sk, heads, d, causal, bias, pad):
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(sq * 7 + sk + d)
+    h = heads * d
+    scale = 1.0 if bias else d ** -0.5
+    mag = 0.35 if bias else 1.0           # T5 scores are unscaled: keep q.k in a softmax-friendly range
+    q, k, v = (randn(gen, b, n, h, scale=mag).to(BF16) for n in (sq, sk, sk))
+    d_o = randn(gen, b, sq, h).to(BF16)
+    key_mask = None
+    if pad:
+        key_mask = torch.ones(b, sk, dtype=torch.bool)
+        key_mask[0, int(sk * 0.55):int(sk * 0.7)] = False
+        key_mask[-1, int(sk * 0.9):] = False
+    vec = dense = None
+    if bias:
+        vec, dense = _rel_vec(gen, heads, sq, sk)
+    xs = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    o = ops.attention(*xs, key_mask=None if key_mask is None else key_mask.cuda(),
+                      rel_bias=None if vec is None else vec.cuda(), heads=heads, causal=causal, scale=scale)
+    o.backward(d_o)
+    rs = [t.float().cpu().requires_grad_(True) for t in (q, k, v)]
+    o_ref = O.attention_core(*rs, heads, scale, key_mask, causal, dense)
+    o_ref.backward(d_o.float().cpu())
+    rep = Report()
+    rep.close("O", o, o_ref, 4e-3)
+    for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
+        rep.close(name, x.grad, r.grad, 1e-2)
+    rep.finish()
+
+
+@pytest.mark.parametrize("b,sq,sk,heads,causal,p", [(2, 200, 200, 2, True, 0.1), (1, 128, 300, 2, False, 0.25)])
+def test_attention_probability_dropout(b, sq, sk, heads, causal, p):
+    """Dropout on the probabilities (HF T5Attention): the kernel's counter-based keep mask is restated in integers by
+    oracle.dropout_multiplier over the [B*nh*Sq, Sk] probability matrix; given that mask the result must equal the
+    reference semantics softmax(.) * keep / (1 - p) @ V, forward and backward."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    d = 64
+    h = heads * d
+    q, k, v = (randn(gen, b, n, h).to(BF16) for n in (sq, sk, sk))
+    d_o = randn(gen, b, sq, h).to(BF16)
+    key_mask = torch.ones(b, sk, dtype=torch.bool)
+    key_mask[0, sk - 37:] = False
+    seed = ops.peek_dropout_seeds(1)[0]
+    xs = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    o = ops.attention(*xs, key_mask=key_mask.cuda(), heads=heads, causal=causal, scale=d ** -0.5, dropout_p=p)
+    o.backward(d_o)
+    mult = O.dropout_multiplier(seed, p, b * heads * sq, sk).reshape(b, heads, sq, sk)
+    frac = float((mult == 0).float().mean())
+    assert abs(frac - p) < 0.01, frac
+    rs = [t.float().cpu().requires_grad_(True) for t in (q, k, v)]
+    o_ref = O.attention_core(*rs, heads, d ** -0.5, key_mask, causal, None, mult)
+    o_ref.backward(d_o.float().cpu())
+    rep = Report()
+    rep.close("O", o, o_ref, 5e-3)
+    for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
+        rep.close(name, x.grad, r.grad, 1.2e-2)
+    rep.finish()
+
+
+def test_rows_without_any_attended_key_are_uniform():
+    """A sample whose keys are ALL padding: the reference's clamp makes every score finfo.min -> uniform attention
+    (non-causal: over all keys, exactly the reference)."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    b, sq, sk, heads, d = 2, 130, 200, 2, 64
+    h = heads * d
+    q, k, v = (randn(gen, b, n, h).to(BF16) for n in (sq, sk, sk))
+    key_mask = torch.ones(b, sk, dtype=torch.bool)
+    key_mask[1] = False
+    o = ops.attention(q, k, v, key_mask=key_mask.cuda(), heads=heads, causal=False, scale=d ** -0.5)
+    o_ref = O.attention_core(q.float().cpu(), k.float().cpu(), v.float().cpu(), heads, d ** -0.5, key_mask, False)
+    rep = Report()
+    rep.close("O", o, o_ref, 4e-3)
+    rep.finish()
