@@ -138,6 +138,74 @@ __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, u
   for (int j = 0; j < D / 64; ++j) tma_load_2d(dst + j * 16384, map, bar, col0 + 64 * j, row0);
 }
 
+
+// ---- per-chunk softmax pieces (one thread = one score row, rc = 32 consecutive keys of it) ------------------------------
+// pass 1: running maxima.  raw_mx: unscaled, over attended keys (no-bias paths); mx: natural units (bias path).
+// full = every lane of the warp attends all 32 keys.  bk points at the bias of this chunk's first key, valid up to [lim].
+template <bool kBias>
+__device__ __forceinline__ void max_chunk(const uint32_t (&rc)[32], uint32_t m, bool full, const float* bk, int lim,
+                                          float scale, float& mx, float& raw_mx) {
+  if (kBias) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float x = fmaf(__uint_as_float(rc[e]), scale, __ldg(bk + min(e, lim)));
+      mx = fmaxf(mx, (m >> e) & 1u ? x : -FLT_MAX);
+    }
+  } else if (full) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) raw_mx = fmaxf(raw_mx, fmaxf(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1])));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, (m >> e) & 1u ? __uint_as_float(rc[e]) : -FLT_MAX);
+  }
+}
+// pass 2: rc <- p = 2^(s * c1 + bias * bsc - mxc) on attended keys, 0 elsewhere; returns the chunk's sum.
+// empty = no lane of the warp attends any of the 32 keys.
+template <bool kBias>
+__device__ __forceinline__ float exp_chunk(uint32_t (&rc)[32], uint32_t m, bool full, bool empty, const float* bk, int lim,
+                                           float c1, float mxc, float bsc) {
+  float sum = 0.f;
+  if (empty) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) rc[e] = 0u;
+  } else if (kBias) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, fmaf(__ldg(bk + min(e, lim)), bsc, -mxc)));
+      pe = (m >> e) & 1u ? pe : 0.f;
+      sum += pe;
+      rc[e] = __float_as_uint(pe);
+    }
+  } else if (full) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
+      sum += pe;
+      rc[e] = __float_as_uint(pe);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
+      pe = (m >> e) & 1u ? pe : 0.f;
+      sum += pe;
+      rc[e] = __float_as_uint(pe);
+    }
+  }
+  return sum;
+}
+// 32 fp32 values of one row -> bf16, into the 128B-swizzled [128][128] tile (2 slabs of 64 columns) at chunk c
+__device__ __forceinline__ void store_chunk_bf16(uint32_t tile_base, int tid, int c, const uint32_t (&rc)[32]) {
+  const uint32_t slab = tile_base + (c >> 1) * 16384;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    sts128(swz(slab, tid, (c & 1) * 4 + g),
+           pack_bf16(__uint_as_float(rc[8 * g]), __uint_as_float(rc[8 * g + 1])),
+           pack_bf16(__uint_as_float(rc[8 * g + 2]), __uint_as_float(rc[8 * g + 3])),
+           pack_bf16(__uint_as_float(rc[8 * g + 4]), __uint_as_float(rc[8 * g + 5])),
+           pack_bf16(__uint_as_float(rc[8 * g + 6]), __uint_as_float(rc[8 * g + 7])));
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // barrier indices of the forward kernel
 template <int NS> struct FwdBars {
@@ -146,14 +214,14 @@ template <int NS> struct FwdBars {
   static constexpr int kfree = 2 + NS;       // [NS] every MMA reading the K stage has completed
   static constexpr int vfull = 2 + 2 * NS;   // [NS]
   static constexpr int vfree = 2 + 3 * NS;   // [NS]
-  static constexpr int sfull = 2 + 4 * NS;   // [2]  S_t = Q_t K_j^T complete in TMEM
-  static constexpr int sfree = 4 + 4 * NS;   // [2]  pass 1: tile t's 128 threads have read S_t
-  static constexpr int pfull = 6 + 4 * NS;   // [2]  pass 2: tile t's P block is in shared memory (128 arrivals)
-  static constexpr int pfree = 8 + 4 * NS;   // [2]  P_t V_j complete: P buffer reusable, O_t updated
-  static constexpr int count = 10 + 4 * NS;
+  static constexpr int sfull = 2 + 4 * NS;   // [2 buffers][2 tiles]  S_t = Q_t K_j^T complete in TMEM buffer (index 2 * buf + t)
+  static constexpr int sfree = 6 + 4 * NS;   // [2 buffers][2 tiles]  pass 1: tile t's 128 threads have read that S buffer
+  static constexpr int pfull = 10 + 4 * NS;  // [2]  pass 2: tile t's P block is in shared memory (128 arrivals)
+  static constexpr int pfree = 12 + 4 * NS;  // [2]  P_t V_j complete: P buffer reusable, O_t updated
+  static constexpr int count = 14 + 4 * NS;
 };
 
-template <int D>
+template <int D, bool kBias, bool kDrop>
 __global__ void __launch_bounds__(320, 1)
 sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p,
@@ -184,7 +252,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < B::count; ++i) {
-      const bool wide = (i >= B::sfree && i < B::sfree + 2) || (i >= B::pfull && i < B::pfull + 2);
+      const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 2);
       mbar_init(&bars[i], wide ? 128 : 1);
     }
     fence_barrier_init();
@@ -227,26 +295,31 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const uint32_t cO[2] = {tmem_base + 256, tmem_base + 256 + D};
       for (int t = 0; t < 2; ++t)
         if (nblk[t] > 0) mbar_wait(&bars[B::qfull + t], 0);
-      // pass 1: S_t(j) for the row maxima
+      // pass 1: S_t(j) for the row maxima, double-buffered (block j at column offset (j & 1) * 256; the O columns are
+      // not in use yet), so the tensor core runs one block ahead of the max reduction
       for (int j = 0; j < nbmax; ++j) {
         const int s = j % NS;
         mbar_wait(&bars[B::kfull + s], (j / NS) & 1);
         for (int t = 0; t < 2; ++t)
           if (j < nblk[t]) {
-            if (j > 0) mbar_wait(&bars[B::sfree + t], (j - 1) & 1);
+            if (j >= 2) mbar_wait(&bars[B::sfree + 2 * (j & 1) + t], ((j >> 1) - 1) & 1);
             tc_fence_after();
-            mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
-            umma_commit(&bars[B::sfull + t]);
+            mma_qk<D>(cS[t] + (j & 1) * 256, q_addr[t], smem_u32(sK + s * TB));
+            umma_commit(&bars[B::sfull + 2 * (j & 1) + t]);
           }
         umma_commit(&bars[B::kfree + s]);
       }
-      // pass 2 prologue: S_t(0)
+      // pass 2 prologue: S_t(0) once tile t's pass-1 reads are all done (phases are consumed in order)
       {
         const int n = nbmax, s = n % NS;
         mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
         for (int t = 0; t < 2; ++t)
           if (nblk[t] > 0) {
-            mbar_wait(&bars[B::sfree + t], (nblk[t] - 1) & 1);
+            for (int jj = max(nblk[t] - 2, 0); jj < nblk[t]; ++jj)   // the last read of each S buffer
+              mbar_wait(&bars[B::sfree + 2 * (jj & 1) + t], (jj >> 1) & 1);
+          }
+        for (int t = 0; t < 2; ++t)
+          if (nblk[t] > 0) {
             tc_fence_after();
             mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
             umma_commit(&bars[B::sfull + t]);
@@ -288,47 +361,42 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       const uint32_t cS = lane_addr + t * 128, cO = lane_addr + 256 + t * D;
       const float scale = p.scale;
-      const bool has_bias = p.rel_bias != nullptr;
+      constexpr bool has_bias = kBias;
       // bias of (row, key) = bias_row[key]  (bias_row points at the entry of key 0; negative offsets are valid memory)
       const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
-      uint32_t sphase = 0;
-      // ---------------- pass 1: row maximum
-      float mx = -FLT_MAX;     // natural units (bias / masked paths)
-      float raw_mx = -FLT_MAX; // unscaled (interior path)
+      const float* bias0 = has_bias ? bias_row : nullptr;
+      // ---------------- pass 1: row maximum (S double-buffered in TMEM: block j lives at column offset (j & 1) * 256)
+      float mx = -FLT_MAX;     // natural units (bias path)
+      float raw_mx = -FLT_MAX; // unscaled (paths without bias)
       for (int j = 0; j < nb; ++j) {
         const bool diag = p.causal && j == qt;
-        const bool plain = !has_bias && !diag && block_all_attended(kbits, j);
-        mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
+        const uint32_t cSj = cS + (j & 1) * 256;
+        mbar_wait(&bars[B::sfull + 2 * (j & 1) + t], (j >> 1) & 1);
         tc_fence_after();
-        uint32_t r[2][32];
-        tmem_ld_32x32(cS, r[0]);
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(cSj, ra);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_32x32(cS + (c + 1) * 32, r[(c + 1) & 1]);
-          const uint32_t(&rc)[32] = r[c & 1];
-          if (plain) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) raw_mx = fmaxf(raw_mx, fmaxf(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1])));
-          } else {
+          for (int u = 0; u < 2; ++u) {
+            const int c = 2 * cc + u;
+            tmem_ld_wait();
+            if (u == 0) tmem_ld_32x32(cSj + (c + 1) * 32, rb);
+            else if (cc == 0) tmem_ld_32x32(cSj + 64, ra);
             uint32_t m = kbits[4 * j + c];
             if (diag) m &= low_bits(tid - c * 32 + 1);
+            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
             const int key0 = j * 128 + c * 32;
-            if (has_bias) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                const float x = fmaf(__uint_as_float(rc[e]), scale, __ldg(bias_row + min(key0 + e, p.seq_k - 1)));
-                mx = fmaxf(mx, (m >> e) & 1u ? x : -FLT_MAX);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, (m >> e) & 1u ? __uint_as_float(rc[e]) : -FLT_MAX);
-            }
+            const float* bk = has_bias ? bias0 + min(key0, p.seq_k - 1) : nullptr;
+            const int lim = max(p.seq_k - 1 - key0, 0);
+            if (u == 0) max_chunk<kBias>(ra, m, full, bk, lim, scale, mx, raw_mx);
+            else max_chunk<kBias>(rb, m, full, bk, lim, scale, mx, raw_mx);
           }
         }
         tc_fence_before();
-        mbar_arrive(&bars[B::sfree + t]);
+        mbar_arrive(&bars[B::sfree + 2 * (j & 1) + t]);
       }
+      uint32_t sphase = (nb + 1) >> 1;   // pass 2 reuses S buffer 0: its barrier has completed ceil(nb / 2) phases
       if (raw_mx > -FLT_MAX) mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
       // A row with no attended key at all (mx == -FLT_MAX): the reference's clamp makes every existing key's score
       // finfo.min, i.e. uniform attention -> p = 1 on the existing keys of the visited blocks.
@@ -341,52 +409,36 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int64_t dgroups = (p.seq_k + 7) >> 3;
       for (int j = 0; j < nb; ++j) {
         const bool diag = p.causal && j == qt;
-        const bool plain = !has_bias && !diag && block_all_attended(kbits, j);
         mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
         tc_fence_after();
-        uint32_t r[2][32];
-        tmem_ld_32x32(cS, r[0]);
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(cS, ra);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_32x32(cS + (c + 1) * 32, r[(c + 1) & 1]);
-          uint32_t(&rc)[32] = r[c & 1];
-          const int key0 = j * 128 + c * 32;
-          if (plain) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
-              sum += pe;
-              rc[e] = __float_as_uint(pe);
-            }
-          } else {
+          for (int u = 0; u < 2; ++u) {
+            const int c = 2 * cc + u;
+            tmem_ld_wait();
+            if (u == 0) tmem_ld_32x32(cS + (c + 1) * 32, rb);
+            else if (cc == 0) tmem_ld_32x32(cS + 64, ra);
+            const int key0 = j * 128 + c * 32;
             uint32_t m = kbits[4 * j + c];
             if (diag) m &= low_bits(tid - c * 32 + 1);
             if (none) m = low_bits(p.seq_k - key0);
+            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
+            const bool empty = __all_sync(0xffffffffu, m == 0u);
+            const float* bk = has_bias ? bias0 + min(key0, p.seq_k - 1) : nullptr;
+            const int lim = max(p.seq_k - 1 - key0, 0);
+            uint32_t(&rc)[32] = u == 0 ? ra : rb;
+            sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
+            if (kDrop) {
+              const uint32_t keep = keep_word(p, drow, key0, dgroups);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float off = -mxc;
-              if (has_bias) off = fmaf(__ldg(bias_row + min(key0 + e, p.seq_k - 1)), bsc, -mxc);
-              float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, off));
-              pe = (m >> e) & 1u ? pe : 0.f;
-              sum += pe;
-              rc[e] = __float_as_uint(pe);
+              for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
             }
+            if (c == 0 && j > 0) mbar_wait(&bars[B::pfree + t], (j - 1) & 1);   // P_t(j-1) V done: buffer reusable
+            store_chunk_bf16(p_base, tid, c, rc);
           }
-          if (p.drop_thresh != 0) {
-            const uint32_t keep = keep_word(p, drow, key0, dgroups);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
-          }
-          if (c == 0 && j > 0) mbar_wait(&bars[B::pfree + t], (j - 1) & 1);   // P_t(j-1) V done: buffer reusable
-          const uint32_t slab = p_base + (c >> 1) * 16384;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            sts128(swz(slab, tid, (c & 1) * 4 + g),
-                   pack_bf16(__uint_as_float(rc[8 * g]), __uint_as_float(rc[8 * g + 1])),
-                   pack_bf16(__uint_as_float(rc[8 * g + 2]), __uint_as_float(rc[8 * g + 3])),
-                   pack_bf16(__uint_as_float(rc[8 * g + 4]), __uint_as_float(rc[8 * g + 5])),
-                   pack_bf16(__uint_as_float(rc[8 * g + 6]), __uint_as_float(rc[8 * g + 7])));
         }
         fence_proxy_async();
         tc_fence_before();
@@ -752,7 +804,9 @@ int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float*
   constexpr int TB = (D / 64) * 16384;
   constexpr int NS = (D == 64) ? 3 : 1;
   const size_t smem = (2 + 2 * NS) * (size_t)TB + 65536 + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16;
-  auto kern = sattn_fwd_kernel<D>;
+  const bool bias = p.rel_bias != nullptr, drop = p.drop_thresh != 0;
+  auto kern = bias ? (drop ? sattn_fwd_kernel<D, true, true> : sattn_fwd_kernel<D, true, false>)
+                   : (drop ? sattn_fwd_kernel<D, false, true> : sattn_fwd_kernel<D, false, false>);
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntq = (p.seq_q + 127) / 128;
   dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
