@@ -107,35 +107,29 @@ int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
                    int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t head_dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Causal / key-padded self-attention of the (frozen) decoder layers -- SURVEY 8f row f1.
- *   O = softmax(max(scale * Q K^T + causal + key padding, finfo.min)) V   per (sample, head); Q, K, V, O [B,S,nh*d] bf16
- *   (views with leading dims: the three thirds of one fused [B*S, 3*nh*d] QKV projection work in place).
- * key_mask [B,S] bytes (1 = real token, 0 = padding; NULL = no padding); causal != 0 masks keys > query.
- * 128 x 128 score blocks on tcgen05 with TMEM accumulators, TMA-staged tiles, two-pass fp32 softmax; only blocks at or
- * below the diagonal are visited when causal.  stats [B,nh,S,2] = (row max of the masked scaled scores, 1 / row sum).
- * Backward = a dQ kernel (per query tile) + a dK/dV kernel (per key block), both recomputing P from stats.
- * Replaces MPTAttention's self branch model/modelling_cross_attention.py:201-275 with the mask of :455-476.
- * A query whose keys are ALL masked (never the case with the reference's right-padded batches) attends uniformly over the
- * visited blocks rather than over all S keys. */
-int mmgl_sattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                   const uint8_t* key_mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq, int64_t heads,
-                   int64_t head_dim, float scale, int32_t causal, void* stream);
-int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                   int64_t ldv, const void* o, int64_t ldo, const float* stats, const uint8_t* key_mask, void* dq,
-                   int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch, int64_t seq, int64_t heads,
-                   int64_t head_dim, float scale, int32_t causal, void* stream);
-
-/* General form of the above: queries and keys of different lengths, an additive relative-position bias and dropout
- * on the probabilities -- the attention of the HF T5 / OPT language model that the concat path runs
- * (model/modelling_self_attention.py:332; HF models/t5/modeling_t5.py T5Attention: scores are NOT scaled by d^-1/2,
- * position_bias[h, i, j] depends on j - i only, nn.functional.dropout on the softmax output; the decoder's
- * cross-attention has seq_q = decoder length, seq_k = encoder length, no bias, key padding from the encoder mask).
+ * Self-attention core of the decoder / encoder layers and of the language model on the concat path
+ * (SURVEY 8f row f1, row a7):
  *   P = softmax(max(scale * Q K^T + rel_bias[h][key - row + seq_q - 1] + causal + key padding, finfo.min))
- *   O = (keep / (1 - dropout_p) . P) V     keep = the counter-based mask of mmgl_dropout_apply over the
- *                                          [batch*heads*seq_q, seq_k] probability matrix, row = (b*heads + h)*seq_q + i
- * q, o [B,seq_q,nh*d]; k, v [B,seq_k,nh*d] (views with leading dims); key_mask [B,seq_k] bytes or NULL;
- * rel_bias fp32 [heads, seq_q + seq_k - 1] or NULL; stats [B,nh,seq_q,2].  causal needs seq_q == seq_k.
- * seq_k <= 8192.  Backward returns dQ, dK, dV (the bias is treated as a constant: its table is frozen under LoRA). */
+ *   O = (keep / (1 - dropout_p) . P) V     per (sample, head)
+ * q, o [B,seq_q,nh*d]; k, v [B,seq_k,nh*d] bf16 (views with leading dims: the three thirds of one fused
+ * [B*S, 3*nh*d] QKV projection work in place); key_mask [B,seq_k] bytes (1 = real token) or NULL; causal != 0 masks
+ * keys > query (needs seq_q == seq_k); rel_bias fp32 [heads, seq_q + seq_k - 1] or NULL; stats [B,nh,seq_q,2] =
+ * (row max of the masked scores, 1 / row sum) saved for backward.  head_dim in {64,128}; seq_k <= 8192.
+ * keep = the counter-based mask of mmgl_dropout_apply over the [batch*heads*seq_q, seq_k] probability matrix,
+ * row = (b*heads + h)*seq_q + i.
+ *
+ * 128 x 128 score blocks on tcgen05 with TMEM accumulators, TMA-staged tiles, two-pass fp32 softmax; only blocks at
+ * or below the diagonal are visited when causal.  Forward: two query tiles per CTA in ping-pong (8 softmax warps, two
+ * MMA-issuing warps, one TMA warp).  Backward = a dQ kernel (per query tile) + a dK/dV kernel (per key block), both
+ * recomputing P from stats, four threads per score row; the bias is treated as a constant (its table is frozen
+ * under LoRA).
+ *
+ * Replaces MPTAttention's self branch model/modelling_cross_attention.py:201-275 with the mask of :455-476, and the
+ * attention of the HF T5 / OPT language model that model/modelling_self_attention.py:332 runs (HF
+ * models/t5/modeling_t5.py T5Attention: scores NOT scaled by d^-1/2, position_bias[h,i,j] a function of j - i,
+ * nn.functional.dropout on the softmax output; decoder cross-attention with seq_q != seq_k, no bias).
+ * A query whose keys are ALL masked (never the case with the reference's right-padded batches) attends uniformly over
+ * the existing keys of the visited blocks rather than over all S keys. */
 typedef struct mmgl_attn_args {
   const void* q; int64_t ldq; const void* k; int64_t ldk; const void* v; int64_t ldv;
   const uint8_t* key_mask; const float* rel_bias;
@@ -144,9 +138,12 @@ typedef struct mmgl_attn_args {
   float scale; int32_t causal; float dropout_p; int32_t reserved; uint64_t dropout_seed;
 } mmgl_attn_args;
 int mmgl_attn_fwd(const mmgl_attn_args* args, void* stream);
-/* o and stats in args are the forward outputs (read here) */
+/* o and stats in args are the forward outputs (read here).  workspace: caller-owned fp32 scratch of
+ * mmgl_attn_bwd_workspace_bytes() (rowsum(dO . O), written by the dQ kernel and read by the dK/dV kernel). */
+size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t heads);
 int mmgl_attn_bwd(const mmgl_attn_args* args, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
-                  int64_t lddk, void* dv, int64_t lddv, void* stream);
+                  int64_t lddk, void* dv, int64_t lddv, void* workspace, size_t workspace_bytes, void* stream);
+
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -85,13 +85,9 @@ SIGNATURES = {
     "mmgl_xattn_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
                                  c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
-    "mmgl_sattn_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp,
-                                 c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp]),
-    "mmgl_sattn_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
-                                 c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
-                                 c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp]),
     "mmgl_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
-    "mmgl_attn_bwd": (c_i32, [C.POINTER(AttnArgs), c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mmgl_attn_bwd_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "mmgl_attn_bwd": (c_i32, [C.POINTER(AttnArgs), c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "mmgl_layernorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
     "mmgl_layernorm_bwd_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_layernorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz,
@@ -297,25 +293,6 @@ def xattn_bwd(d_o, q, k, v, o, stats, mask, dq, dk, dv, batch, seq, nk, heads, h
                                     batch, seq, nk, heads, head_dim, _stream()), "mmgl_xattn_bwd")
 
 
-def sattn_fwd(q, k, v, key_mask, o, stats, batch, seq, heads, head_dim, scale, causal):
-    """q, k, v, o: [B*S, H] views (e.g. thirds of a fused QKV buffer); key_mask u8 [B,S] or None."""
-    _req_cuda(q, k, v, key_mask, o, stats)
-    h = heads * head_dim
-    # algorithmic bytes: read Q, K, V, write O (K/V re-reads across query tiles are L2 traffic)
-    with _Timed("sattn_fwd", float(batch * seq * h * 2 * 4)):
-        _check(lib().mmgl_sattn_fwd(_p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(key_mask), _p(o), _ld(o), _p(stats),
-                                    batch, seq, heads, head_dim, float(scale), int(causal), _stream()), "mmgl_sattn_fwd")
-
-
-def sattn_bwd(d_o, q, k, v, o, stats, key_mask, dq, dk, dv, batch, seq, heads, head_dim, scale, causal):
-    _req_cuda(d_o, q, k, v, o, stats, key_mask, dq, dk, dv)
-    h = heads * head_dim
-    with _Timed("sattn_bwd", float(batch * seq * h * 2 * 8)):
-        _check(lib().mmgl_sattn_bwd(_p(d_o), _ld(d_o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(stats),
-                                    _p(key_mask), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv), batch, seq, heads,
-                                    head_dim, float(scale), int(causal), _stream()), "mmgl_sattn_bwd")
-
-
 def _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
                dropout_seed):
     a = AttnArgs()
@@ -348,9 +325,10 @@ def attn_bwd(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv, batch, seq_
     h = heads * head_dim
     a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
                    dropout_seed)
+    ws = torch.empty(batch * heads * seq_q, dtype=torch.float32, device=q.device)
     with _Timed("sattn_bwd", float(batch * (seq_q + seq_k) * h * 2 * 4)):
         _check(lib().mmgl_attn_bwd(C.byref(a), _p(d_o), _ld(d_o), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
-                                   _stream()), "mmgl_attn_bwd")
+                                   _p(ws), ws.numel() * 4, _stream()), "mmgl_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------- layernorm

@@ -11,7 +11,7 @@ LIB = os.path.join(LIB_DIR, "libmmgl_b200.so")
 SOURCES = ["capi.cu", "gemm_sm100.cu", "xattn.cu", "xattn_sm100.cu", "sattn_sm100.cu", "rowops.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"] + os.environ.get("MMGL_EXTRA_FLAGS", "").split()
 
 
 def _digest():

@@ -52,9 +52,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a pipeline bug must surface as a trap (an error the host sees), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // try_wait suspends the thread in hardware up to a system time limit per call, so the poll count is the timeout:
+  // no clock reads in the loop (spinning issuer lanes share their scheduler with the compute warps)
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (++polls > (1u << 26)) {
       printf("mmgl: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }

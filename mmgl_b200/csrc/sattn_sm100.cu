@@ -37,6 +37,22 @@ namespace {
 
 constexpr float kL2E = 1.4426950408889634f;
 
+// Development trace (compiled in only with -DMMGL_TRACE): CTA (0,0,0) stamps (tag, clock) pairs per role into a global
+// buffer read back by mmgl_debug_trace(); tools/attn_trace.py prints the timeline.
+#ifdef MMGL_TRACE
+__device__ unsigned long long g_trace[4 * 1024];
+#define TR(role, idx_var, tag)                                                          \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx_var) < 511) {     \
+      g_trace[(role) * 1024 + 2 * (idx_var)] = (unsigned long long)(tag);               \
+      g_trace[(role) * 1024 + 2 * (idx_var) + 1] = clock64();                           \
+      ++(idx_var);                                                                      \
+    }                                                                                   \
+  } while (0)
+#else
+#define TR(role, idx_var, tag) do { } while (0)
+#endif
+
 struct AttnParams {
   const uint8_t* key_mask;   // [B, seq_k] or null
   const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
@@ -132,6 +148,22 @@ __device__ __forceinline__ void mma_tn(uint32_t tmem, uint32_t a_base, uint32_t 
     umma_f16_ss(tmem, da, db, idesc, (accumulate || k != 0) ? 1u : 0u);
   }
 }
+// the same contractions from precomputed descriptor bases (descriptor of addr + delta = descriptor of addr + (delta >> 4)):
+// the issuing thread adds compile-time constants instead of rebuilding two descriptors per instruction
+__host__ __device__ constexpr uint64_t kslab_off(int k) { return (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4); }
+template <int D>
+__device__ __forceinline__ void mma_qk_desc(uint32_t tmem, uint64_t da0, uint64_t db0) {
+  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+  for (int k = 0; k < D / 16; ++k) umma_f16_ss(tmem, da0 + kslab_off(k), db0 + kslab_off(k), idesc, k != 0 ? 1u : 0u);
+}
+template <int D>
+__device__ __forceinline__ void mma_pv_desc(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_f16_ss(tmem, da0 + kslab_off(k), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
+}
 template <int D>
 __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0) {
 #pragma unroll
@@ -145,18 +177,23 @@ __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, u
 template <bool kBias>
 __device__ __forceinline__ void max_chunk(const uint32_t (&rc)[32], uint32_t m, bool full, const float* bk, int lim,
                                           float scale, float& mx, float& raw_mx) {
+  // four independent running maxima: with one or two warps per scheduler a single dependent chain of 32 is latency-bound
+  float a[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
   if (kBias) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const float x = fmaf(__uint_as_float(rc[e]), scale, __ldg(bk + min(e, lim)));
-      mx = fmaxf(mx, (m >> e) & 1u ? x : -FLT_MAX);
+      a[e & 3] = fmaxf(a[e & 3], (m >> e) & 1u ? x : -FLT_MAX);
     }
+    mx = fmaxf(fmaxf(mx, fmaxf(a[0], a[1])), fmaxf(a[2], a[3]));
   } else if (full) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 2) raw_mx = fmaxf(raw_mx, fmaxf(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1])));
+    for (int e = 0; e < 32; e += 2) a[(e >> 1) & 3] = fmaxf(a[(e >> 1) & 3], fmaxf(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1])));
+    raw_mx = fmaxf(fmaxf(raw_mx, fmaxf(a[0], a[1])), fmaxf(a[2], a[3]));
   } else {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) raw_mx = fmaxf(raw_mx, (m >> e) & 1u ? __uint_as_float(rc[e]) : -FLT_MAX);
+    for (int e = 0; e < 32; ++e) a[e & 3] = fmaxf(a[e & 3], (m >> e) & 1u ? __uint_as_float(rc[e]) : -FLT_MAX);
+    raw_mx = fmaxf(fmaxf(raw_mx, fmaxf(a[0], a[1])), fmaxf(a[2], a[3]));
   }
 }
 // pass 2: rc <- p = 2^(s * c1 + bias * bsc - mxc) on attended keys, 0 elsewhere; returns the chunk's sum.
@@ -164,7 +201,7 @@ __device__ __forceinline__ void max_chunk(const uint32_t (&rc)[32], uint32_t m, 
 template <bool kBias>
 __device__ __forceinline__ float exp_chunk(uint32_t (&rc)[32], uint32_t m, bool full, bool empty, const float* bk, int lim,
                                            float c1, float mxc, float bsc) {
-  float sum = 0.f;
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
   if (empty) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) rc[e] = 0u;
@@ -173,14 +210,14 @@ __device__ __forceinline__ float exp_chunk(uint32_t (&rc)[32], uint32_t m, bool 
     for (int e = 0; e < 32; ++e) {
       float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, fmaf(__ldg(bk + min(e, lim)), bsc, -mxc)));
       pe = (m >> e) & 1u ? pe : 0.f;
-      sum += pe;
+      sum[e & 3] += pe;
       rc[e] = __float_as_uint(pe);
     }
   } else if (full) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
-      sum += pe;
+      sum[e & 3] += pe;
       rc[e] = __float_as_uint(pe);
     }
   } else {
@@ -188,11 +225,11 @@ __device__ __forceinline__ float exp_chunk(uint32_t (&rc)[32], uint32_t m, bool 
     for (int e = 0; e < 32; ++e) {
       float pe = ex2(fmaf(__uint_as_float(rc[e]), c1, -mxc));
       pe = (m >> e) & 1u ? pe : 0.f;
-      sum += pe;
+      sum[e & 3] += pe;
       rc[e] = __float_as_uint(pe);
     }
   }
-  return sum;
+  return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 // 32 fp32 values of one row -> bf16, into the 128B-swizzled [128][128] tile (2 slabs of 64 columns) at chunk c
 __device__ __forceinline__ void store_chunk_bf16(uint32_t tile_base, int tid, int c, const uint32_t (&rc)[32]) {
@@ -222,7 +259,7 @@ template <int NS> struct FwdBars {
 };
 
 template <int D, bool kBias, bool kDrop>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p,
                  __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats) {
@@ -242,6 +279,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const int ntq = (p.seq_q + 127) / 128;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tri = 0; (void)tri;
+  if (threadIdx.x == 0) TR(0, tri, 1);
   // tile 0 of the pair is the later (heavier when causal) query tile; tile 1 the one before it (absent if < 0)
   const int qt0 = ntq - 1 - 2 * (int)blockIdx.x;
   const int qts[2] = {qt0, qt0 - 1};
@@ -253,7 +292,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < B::count; ++i) {
       const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 2);
-      mbar_init(&bars[i], wide ? 128 : 1);
+      const bool two = (i >= B::kfree && i < B::kfree + NS) || (i >= B::vfree && i < B::vfree + NS);
+      mbar_init(&bars[i], wide ? 128 : (two ? 2 : 1));
     }
     fence_barrier_init();
   }
@@ -263,8 +303,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) TR(0, tri, 2);
 
-  if (warp == 9) {
+  if (warp == 10) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int t = 0; t < 2; ++t)
@@ -277,6 +318,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (n >= NS) mbar_wait(&bars[B::kfree + s], ((n / NS) - 1) & 1);
         mbar_arrive_expect_tx(&bars[B::kfull + s], TB);
         tma_tile<D>(sK + s * TB, &map_k, &bars[B::kfull + s], colq, rowk + j * 128);
+        TR(3, tri, 100 + n);
         if (n >= nbmax) {                               // pass 2: V block j rides along
           const int sv = j % NS;
           if (j >= NS) mbar_wait(&bars[B::vfree + sv], ((j / NS) - 1) & 1);
@@ -286,67 +328,71 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t q_addr[2] = {smem_u32(sQ), smem_u32(sQ + TB)};
-      const uint32_t p_addr[2] = {smem_u32(sP), smem_u32(sP + 32768)};
-      const uint32_t cS[2] = {tmem_base, tmem_base + 128};
-      const uint32_t cO[2] = {tmem_base + 256, tmem_base + 256 + D};
-      for (int t = 0; t < 2; ++t)
-        if (nblk[t] > 0) mbar_wait(&bars[B::qfull + t], 0);
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ MMA issuers: warp 8 -> tile 0, warp 9 -> tile 1
+    const int t = warp - 8;
+    const int nb = nblk[t];
+    if (lane == 0 && nb > 0) {
+      const uint64_t dq = make_smem_desc(smem_u32(sQ + t * TB), 16, 1024);
+      const uint64_t dp = make_smem_desc(smem_u32(sP + t * 32768), 16, 1024);
+      const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t dv0 = make_smem_desc(smem_u32(sV), 16384, 1024);
+      const uint32_t cS = tmem_base + t * 128, cO = tmem_base + 256 + t * D;
+      // a K / V stage is released by two arrivals, one per tile; the only tile using a block arrives twice
+      auto release = [&](uint64_t* bar, int j) {
+        umma_commit(bar);
+        if (j >= nblk[1]) umma_commit(bar);
+      };
+      mbar_wait(&bars[B::qfull + t], 0);
+      if (t == 0) TR(2, tri, 10);
       // pass 1: S_t(j) for the row maxima, double-buffered (block j at column offset (j & 1) * 256; the O columns are
       // not in use yet), so the tensor core runs one block ahead of the max reduction
-      for (int j = 0; j < nbmax; ++j) {
+      for (int j = 0; j < nb; ++j) {
         const int s = j % NS;
         mbar_wait(&bars[B::kfull + s], (j / NS) & 1);
-        for (int t = 0; t < 2; ++t)
-          if (j < nblk[t]) {
-            if (j >= 2) mbar_wait(&bars[B::sfree + 2 * (j & 1) + t], ((j >> 1) - 1) & 1);
-            tc_fence_after();
-            mma_qk<D>(cS[t] + (j & 1) * 256, q_addr[t], smem_u32(sK + s * TB));
-            umma_commit(&bars[B::sfull + 2 * (j & 1) + t]);
-          }
-        umma_commit(&bars[B::kfree + s]);
+        if (j >= 2) mbar_wait(&bars[B::sfree + 2 * (j & 1) + t], ((j >> 1) - 1) & 1);
+        tc_fence_after();
+        if (t == 0) TR(2, tri, 100 + j);
+        mma_qk_desc<D>(cS + (j & 1) * 256, dq, dk0 + (uint64_t)((s * TB) >> 4));
+        umma_commit(&bars[B::sfull + 2 * (j & 1) + t]);
+        release(&bars[B::kfree + s], j);
+        if (t == 0) TR(2, tri, 150 + j);
       }
-      // pass 2 prologue: S_t(0) once tile t's pass-1 reads are all done (phases are consumed in order)
+      // pass 2 prologue: S_t(0) once BOTH tiles' pass-1 reads are done (tile 0's O columns alias tile 1's second S buffer
+      // and vice versa); barrier phases are consumed in order
+      for (int tt = 0; tt < 2; ++tt)
+        for (int jj = max(nblk[tt] - 2, 0); jj < nblk[tt]; ++jj)
+          mbar_wait(&bars[B::sfree + 2 * (jj & 1) + tt], (jj >> 1) & 1);
       {
         const int n = nbmax, s = n % NS;
+        if (t == 0) TR(2, tri, 198);
         mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
-        for (int t = 0; t < 2; ++t)
-          if (nblk[t] > 0) {
-            for (int jj = max(nblk[t] - 2, 0); jj < nblk[t]; ++jj)   // the last read of each S buffer
-              mbar_wait(&bars[B::sfree + 2 * (jj & 1) + t], (jj >> 1) & 1);
-          }
-        for (int t = 0; t < 2; ++t)
-          if (nblk[t] > 0) {
-            tc_fence_after();
-            mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
-            umma_commit(&bars[B::sfull + t]);
-          }
-        umma_commit(&bars[B::kfree + s]);
+        tc_fence_after();
+        mma_qk_desc<D>(cS, dq, dk0 + (uint64_t)((s * TB) >> 4));
+        umma_commit(&bars[B::sfull + t]);
+        release(&bars[B::kfree + s], 0);
+        if (t == 0) TR(2, tri, 199);
       }
-      // pass 2: per tile, O_t += P_t(j) V_j followed at once by S_t(j + 1), so tile t's warps wait for two MMAs only
-      for (int j = 0; j < nbmax; ++j) {
+      // pass 2: O_t += P_t(j) V_j followed at once by S_t(j + 1), so tile t's warps wait for two MMAs only
+      for (int j = 0; j < nb; ++j) {
         const int sv = j % NS;
-        for (int t = 0; t < 2; ++t)
-          if (j < nblk[t]) {
-            const bool last_user = (t == 1) || (j >= nblk[1]);   // last tile that reads K / V block j (and j + 1)
-            mbar_wait(&bars[B::pfull + t], j & 1);
-            mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
-            tc_fence_after();
-            mma_pv<D>(cO[t], p_addr[t], smem_u32(sV + sv * TB), j != 0);
-            umma_commit(&bars[B::pfree + t]);
-            if (last_user) umma_commit(&bars[B::vfree + sv]);
-            if (j + 1 < nblk[t]) {
-              const int n = nbmax + j + 1, s = n % NS;
-              mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
-              tc_fence_after();
-              mma_qk<D>(cS[t], q_addr[t], smem_u32(sK + s * TB));
-              umma_commit(&bars[B::sfull + t]);
-              if ((t == 1) || (j + 1 >= nblk[1])) umma_commit(&bars[B::kfree + s]);
-            }
-          }
+        mbar_wait(&bars[B::pfull + t], j & 1);
+        if (t == 0) TR(2, tri, 200 + j);
+        mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
+        tc_fence_after();
+        if (t == 0) TR(2, tri, 250 + j);
+        mma_pv_desc<D>(cO, dp, dv0 + (uint64_t)((sv * TB) >> 4), j != 0);
+        umma_commit(&bars[B::pfree + t]);
+        release(&bars[B::vfree + sv], j);
+        if (j + 1 < nb) {
+          const int n = nbmax + j + 1, s = n % NS;
+          mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
+          tc_fence_after();
+          mma_qk_desc<D>(cS, dq, dk0 + (uint64_t)((s * TB) >> 4));
+          umma_commit(&bars[B::sfull + t]);
+          release(&bars[B::kfree + s], j + 1);
+        }
+        if (t == 0) TR(2, tri, 300 + j);
       }
     }
     __syncwarp();
@@ -373,6 +419,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const uint32_t cSj = cS + (j & 1) * 256;
         mbar_wait(&bars[B::sfull + 2 * (j & 1) + t], (j >> 1) & 1);
         tc_fence_after();
+        if (threadIdx.x == 0) TR(0, tri, 100 + j);
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(cSj, ra);
 #pragma unroll 1
@@ -395,6 +442,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         tc_fence_before();
         mbar_arrive(&bars[B::sfree + 2 * (j & 1) + t]);
+        if (threadIdx.x == 0) TR(0, tri, 150 + j);
       }
       uint32_t sphase = (nb + 1) >> 1;   // pass 2 reuses S buffer 0: its barrier has completed ceil(nb / 2) phases
       if (raw_mx > -FLT_MAX) mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
@@ -411,6 +459,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const bool diag = p.causal && j == qt;
         mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
         tc_fence_after();
+        if (threadIdx.x == 0) TR(0, tri, 200 + j);
+        if (threadIdx.x == 96) TR(1, tri, 200 + j);
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(cS, ra);
 #pragma unroll 1
@@ -418,7 +468,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int c = 2 * cc + u;
+            if (threadIdx.x == 0) TR(0, tri, 1000 + 10 * j + c);
             tmem_ld_wait();
+            if (threadIdx.x == 0) TR(0, tri, 2000 + 10 * j + c);
             if (u == 0) tmem_ld_32x32(cS + (c + 1) * 32, rb);
             else if (cc == 0) tmem_ld_32x32(cS + 64, ra);
             const int key0 = j * 128 + c * 32;
@@ -438,14 +490,18 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             if (c == 0 && j > 0) mbar_wait(&bars[B::pfree + t], (j - 1) & 1);   // P_t(j-1) V done: buffer reusable
             store_chunk_bf16(p_base, tid, c, rc);
+            if (threadIdx.x == 0) TR(0, tri, 3000 + 10 * j + c);
           }
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars[B::pfull + t]);
+        if (threadIdx.x == 0) TR(0, tri, 250 + j);
+        if (threadIdx.x == 96) TR(1, tri, 250 + j);
       }
       mbar_wait(&bars[B::pfree + t], (nb - 1) & 1);   // all of O_t accumulated
       tc_fence_after();
+      if (threadIdx.x == 0) TR(0, tri, 900);
       const float inv = 1.f / sum;
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
@@ -458,100 +514,103 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         *reinterpret_cast<float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2) = make_float2(mx, inv);
     }
   }
+  if (threadIdx.x == 0) TR(0, tri, 990);
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<512>(tmem_base);
+  if (threadIdx.x == 0) TR(0, tri, 999);
 }
 
-// per-row backward inputs of this thread: (max, 1/sum) and delta = rowsum(dO * O)
+// ------------------------------------------------------------------------------------------------ backward
+// Both backward kernels run 512 threads per CTA: FOUR threads per score row (thread = (row, quarter); quarter = the
+// 32-key chunk of every 128-key block it owns), so one block costs each thread a single 32-element chunk and 16 warps
+// hide each other's TMEM / MUFU latency.  Warp w = 4 * quarter + row / 32 reads TMEM lanes 32 * (w & 3) as required.
+//
+// delta[row] = rowsum(dO . O): computed once by the dQ kernel (which sees every query row exactly once), parked in a
+// caller-provided fp32 workspace [B, nh, seq_q] and read back by the dK/dV kernel (launched after it on the same stream).
 template <int D>
-__device__ __forceinline__ void row_stats_delta(const float* stats, const __nv_bfloat16* o, int64_t ldo,
-                                                const __nv_bfloat16* d_o, int64_t lddo, int b, int h, int heads, int seq_q,
-                                                int row, float& m, float& inv, float& delta) {
-  m = 0.f; inv = 0.f; delta = 0.f;
-  if (row >= seq_q) return;
-  const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * seq_q + row) * 2);
-  m = st.x; inv = st.y;
-  const uint4* po = reinterpret_cast<const uint4*>(o + ((int64_t)b * seq_q + row) * ldo + h * D);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + ((int64_t)b * seq_q + row) * lddo + h * D);
+__device__ __forceinline__ float delta_partial(const __nv_bfloat16* o, int64_t ldo, const __nv_bfloat16* d_o, int64_t lddo,
+                                               int64_t grow, int col0) {
+  // this thread's quarter of the row: D / 4 columns starting at col0
+  const uint4* po = reinterpret_cast<const uint4*>(o + grow * ldo + col0);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + grow * lddo + col0);
+  float acc = 0.f;
 #pragma unroll
-  for (int i = 0; i < D / 8; ++i) {
+  for (int i = 0; i < D / 32; ++i) {
     const uint4 vo = __ldg(po + i), vd = __ldg(pd + i);
     const uint32_t wo[4] = {vo.x, vo.y, vo.z, vo.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) delta += bf16lo(wo[e]) * bf16lo(wd[e]) + bf16hi(wo[e]) * bf16hi(wd[e]);
+    for (int e = 0; e < 4; ++e) acc += bf16lo(wo[e]) * bf16lo(wd[e]) + bf16hi(wo[e]) * bf16hi(wd[e]);
   }
+  return acc;
 }
 
-// P and dS of this thread's row for one 128-key block: reads S (col 0) and dP (col 128) from TMEM, writes bf16 tiles.
+// P~ and dS of this thread's 32-key chunk c of one 128-key block: reads S (col 32c) and dP (col 128 + 32c) from TMEM,
+// writes bf16 into the swizzled [128][128] tiles.
 //   P~  = keep/(1-p) . P      (tile for dV += P~^T dO; equals P without dropout)
 //   dS  = P . (keep/(1-p) . dP - delta)
-// words: this thread's attend bits of the 4 chunks (key bits AND causal limit; existing keys when the row has no
-// attended key).  plain = interior block: all attended, no bias.
-template <bool kWriteP>
-__device__ __forceinline__ void softmax_grad_block(const AttnParams& p, uint32_t lane_addr, const uint32_t (&words)[4],
-                                                   bool plain, const float* bias_row, int key0, bool row_ok, float m,
-                                                   float inv, float delta, int64_t drow, uint32_t p_base,
-                                                   uint32_t ds_base, int tid) {
+// mw: attend bits of the chunk for this row (key bits AND causal limit; the existing keys when the row attends nothing).
+template <bool kWriteP, bool kBias, bool kDrop>
+__device__ __forceinline__ void softmax_grad_chunk(const AttnParams& p, uint32_t lane_addr, int c, uint32_t mw,
+                                                   const float* bias_row, int key0, bool row_ok, float m, float inv,
+                                                   float delta, int64_t drow, uint32_t p_base, uint32_t ds_base, int row_in_tile) {
   const bool flat = !(m > -FLT_MAX) || !row_ok;   // no attended key (uniform row) or a row beyond the sequence (p = 0)
   const float c1 = flat ? 0.f : p.scale * kL2E, mc = flat ? 0.f : m * kL2E, bsc = flat ? 0.f : kL2E;
   const float inv_ok = row_ok ? inv : 0.f;
-  const int64_t dgroups = (p.seq_k + 7) >> 3;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t rs[32], rp[32];
-    tmem_ld_32x32(lane_addr + c * 32, rs);
-    tmem_ld_32x32(lane_addr + 128 + c * 32, rp);
-    tmem_ld_wait();
-    const uint32_t mw = plain ? 0xffffffffu : words[c];
-    const bool drop = p.drop_thresh != 0;
-    const uint32_t keep = drop ? keep_word(p, drow, key0 + c * 32, dgroups) : 0xffffffffu;
-    const float ks = drop ? p.drop_scale : 1.f;
-    uint32_t pk[16], dk[16];
+  uint32_t rs[32], rp[32];
+  tmem_ld_32x32(lane_addr + c * 32, rs);
+  tmem_ld_32x32(lane_addr + 128 + c * 32, rp);
+  uint32_t keep = 0xffffffffu;
+  if (kDrop) keep = keep_word(p, drow, key0, (p.seq_k + 7) >> 3);
+  const float ks = kDrop ? p.drop_scale : 1.f;
+  const int lim = max(p.seq_k - 1 - key0, 0);
+  const float* bk = kBias ? bias_row + min(key0, p.seq_k - 1) : nullptr;
+  tmem_ld_wait();
+  uint32_t pk[16], dk[16];
 #pragma unroll
-    for (int e = 0; e < 32; e += 2) {
-      float pv[2], dv[2];
+  for (int e = 0; e < 32; e += 2) {
+    float pv[2], dv[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float off = -mc;
-        if (bias_row != nullptr) off = fmaf(__ldg(bias_row + min(key0 + c * 32 + e + u, p.seq_k - 1)), bsc, -mc);
-        float pr = ex2(fmaf(__uint_as_float(rs[e + u]), c1, off)) * inv_ok;
-        pr = (mw >> (e + u)) & 1u ? pr : 0.f;
+    for (int u = 0; u < 2; ++u) {
+      float off = -mc;
+      if (kBias) off = fmaf(__ldg(bk + min(e + u, lim)), bsc, -mc);
+      float pr = ex2(fmaf(__uint_as_float(rs[e + u]), c1, off)) * inv_ok;
+      pr = (mw >> (e + u)) & 1u ? pr : 0.f;
+      if (kDrop) {
         const float kmul = (keep >> (e + u)) & 1u ? ks : 0.f;
         pv[u] = pr * kmul;
         dv[u] = pr * fmaf(__uint_as_float(rp[e + u]), kmul, -delta);
+      } else {
+        pv[u] = pr;
+        dv[u] = pr * (__uint_as_float(rp[e + u]) - delta);
       }
-      pk[e >> 1] = pack_bf16(pv[0], pv[1]);
-      dk[e >> 1] = pack_bf16(dv[0], dv[1]);
     }
+    pk[e >> 1] = pack_bf16(pv[0], pv[1]);
+    dk[e >> 1] = pack_bf16(dv[0], dv[1]);
+  }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (kWriteP) sts128(swz(p_base + (c >> 1) * 16384, tid, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      sts128(swz(ds_base + (c >> 1) * 16384, tid, (c & 1) * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-    }
+  for (int g = 0; g < 4; ++g) {
+    if (kWriteP) sts128(swz(p_base + (c >> 1) * 16384, row_in_tile, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    sts128(swz(ds_base + (c >> 1) * 16384, row_in_tile, (c & 1) * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
   }
 }
 
-// this thread's attend words of key block j for query row (tile qt, lane tid)
-__device__ __forceinline__ void row_words(const AttnParams& p, const uint32_t* kbits4, int j, int qt, int tid, bool none,
-                                          uint32_t (&words)[4]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t m = kbits4[c];
-    if (p.causal && j == qt) m &= low_bits(tid - c * 32 + 1);
-    if (none) m = low_bits(p.seq_k - (j * 128 + c * 32));   // uniform over the existing keys of the visited blocks
-    words[c] = m;
-  }
+// attend word of chunk c of key block j for query row (tile qt, row_in_tile)
+__device__ __forceinline__ uint32_t row_word(const AttnParams& p, uint32_t kword, int j, int qt, int row_in_tile, int c, bool none) {
+  uint32_t m = kword;
+  if (p.causal && j == qt) m &= low_bits(row_in_tile - c * 32 + 1);
+  if (none) m = low_bits(p.seq_k - (j * 128 + c * 32));   // uniform over the existing keys of the visited blocks
+  return m;
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-template <int D>
-__global__ void __launch_bounds__(128, 1)
+template <int D, bool kBias, bool kDrop>
+__global__ void __launch_bounds__(512, 1)
 sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                     const __grid_constant__ AttnParams p, const __nv_bfloat16* __restrict__ o, int64_t ldo,
                     const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const float* __restrict__ stats,
-                    __nv_bfloat16* __restrict__ dq, int64_t lddq) {
+                    __nv_bfloat16* __restrict__ dq, int64_t lddq, float* __restrict__ delta_ws) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;   // K / V buffers
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -561,15 +620,17 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* sV = sK + NB * TB;
   uint8_t* sdS = sV + NB * TB;     // 2 slabs
   const int nbk = (p.seq_k + 127) / 128;
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(sdS + 32768);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk + ((4 * nbk) & 1));   // q, kv0, kv1, a, b
+  float* sDelta = reinterpret_cast<float*>(sdS + 32768);   // [4][128] partial row sums
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(sDelta + 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk);   // q, kv0, kv1, a, b
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int ntq = (p.seq_q + 127) / 128;
   const int qt = ntq - 1 - (int)blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
-  const int r0 = qt * 128, row = r0 + tid;
+  const int rit = tid & 127, quarter = tid >> 7;          // row in tile, owned chunk
+  const int r0 = qt * 128, row = r0 + rit;
   const bool row_ok = row < p.seq_q;
   const int nblk = p.causal ? qt + 1 : nbk;
   const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
@@ -581,11 +642,12 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
   build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
+  sDelta[quarter * 128 + rit] = row_ok ? delta_partial<D>(o, ldo, d_o, lddo, (int64_t)rowq + row, colq + quarter * (D / 4)) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdQ = 256;
   uint32_t kvuse[2] = {0, 0}, aphase = 0, bphase = 0;
 
@@ -597,11 +659,15 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tma_tile<D>(sK, &map_k, &bars[1], colq, rowk);
     tma_tile<D>(sV, &map_v, &bars[1], colq, rowk);
   }
-  float m, inv, delta;
-  row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, p.heads, p.seq_q, row, m, inv, delta);
+  float m = 0.f, inv = 0.f;
+  const float delta = (sDelta[rit] + sDelta[128 + rit]) + (sDelta[256 + rit] + sDelta[384 + rit]);
+  if (row_ok) {
+    const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2);
+    m = st.x; inv = st.y;
+    if (quarter == 0) delta_ws[((int64_t)b * p.heads + h) * p.seq_q + row] = delta;
+  }
   const bool none = !(m > -FLT_MAX);
-  const bool has_bias = p.rel_bias != nullptr;
-  const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+  const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
   const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
 
   for (int j = 0; j < nblk; ++j) {
@@ -619,14 +685,12 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
       umma_commit(&bars[3]);
     }
-    const bool plain = !has_bias && !(p.causal && j == qt) && block_all_attended(kbits, j);
-    uint32_t words[4];
-    row_words(p, kbits + 4 * j, j, qt, tid, none, words);
+    const uint32_t mw = row_word(p, kbits[4 * j + quarter], j, qt, rit, quarter, none);
     __syncwarp();
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    softmax_grad_block<false>(p, lane_addr, words, plain, bias_row, j * 128, row_ok, m, inv, delta, drow, 0,
-                              smem_u32(sdS), tid);
+    softmax_grad_chunk<false, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, j * 128 + quarter * 32, row_ok, m, inv,
+                                            delta, drow, 0, smem_u32(sdS), rit);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -645,12 +709,31 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     mbar_wait(&bars[4], bphase & 1); bphase++;
     tc_fence_after();
   }
-#pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + cdQ + c * 32, r);
+  // dQ tile: quarter q stores columns [q * D/4, (q + 1) * D/4)
+  if (D == 64) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(lane_addr + cdQ + quarter * 16) : "memory");
     tmem_ld_wait();
-    if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + c * 32, r, p.scale);
+    if (row_ok) {
+      __nv_bfloat16* dst = dq + ((int64_t)rowq + row) * lddq + colq + quarter * 16;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(r[8 * g]) * p.scale, __uint_as_float(r[8 * g + 1]) * p.scale);
+        v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * p.scale, __uint_as_float(r[8 * g + 3]) * p.scale);
+        v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * p.scale, __uint_as_float(r[8 * g + 5]) * p.scale);
+        v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * p.scale, __uint_as_float(r[8 * g + 7]) * p.scale);
+        *reinterpret_cast<uint4*>(dst + 8 * g) = v;
+      }
+    }
+  } else {
+    uint32_t r[32];
+    tmem_ld_32x32(lane_addr + cdQ + quarter * 32, r);
+    tmem_ld_wait();
+    if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + quarter * 32, r, p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -658,13 +741,13 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-template <int D>
-__global__ void __launch_bounds__(128, 1)
+template <int D, bool kBias, bool kDrop>
+__global__ void __launch_bounds__(512, 1)
 sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                      const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                     const __grid_constant__ AttnParams p, const __nv_bfloat16* __restrict__ o, int64_t ldo,
-                     const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const float* __restrict__ stats,
-                     __nv_bfloat16* __restrict__ dk, int64_t lddk, __nv_bfloat16* __restrict__ dv, int64_t lddv) {
+                     const __grid_constant__ AttnParams p, const float* __restrict__ stats,
+                     const float* __restrict__ delta_ws, __nv_bfloat16* __restrict__ dk, int64_t lddk,
+                     __nv_bfloat16* __restrict__ dv, int64_t lddv) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;   // Q / dO buffers
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -682,6 +765,7 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int kb = blockIdx.x;   // key block; early key blocks see the most query tiles and come first
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x, lane = threadIdx.x & 31;
+  const int rit = tid & 127, quarter = tid >> 7;
   const int i0 = p.causal ? kb : 0;
   const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
@@ -691,7 +775,7 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  {
+  if (tid < 128) {
     const int key = kb * 128 + tid;
     const bool a = key < p.seq_k && (p.key_mask == nullptr || p.key_mask[(int64_t)b * p.seq_k + key] != 0);
     const uint32_t bits = __ballot_sync(0xffffffffu, a);
@@ -701,11 +785,10 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdV = 256, cdK = 256 + D;
   uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0;
-  const bool has_bias = p.rel_bias != nullptr;
-  const bool blk_all = (kbits4[0] & kbits4[1] & kbits4[2] & kbits4[3]) == 0xffffffffu;
+  const uint32_t kword = kbits4[quarter];
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], 2 * TB);
@@ -718,10 +801,15 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   for (int i = i0; i < ntq; ++i) {
     const int it = i - i0;
     const int buf = (NB == 2) ? (it & 1) : 0;
-    const int row = i * 128 + tid;
+    const int row = i * 128 + rit;
     const bool row_ok = row < p.seq_q;
-    float m, inv, delta;
-    row_stats_delta<D>(stats, o, ldo, d_o, lddo, b, h, p.heads, p.seq_q, row, m, inv, delta);
+    float m = 0.f, inv = 0.f, delta = 0.f;
+    if (row_ok) {
+      const int64_t sidx = ((int64_t)b * p.heads + h) * p.seq_q + row;
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + sidx * 2));
+      m = st.x; inv = st.y;
+      delta = __ldg(delta_ws + sidx);
+    }
     if (tid == 0) {
       if (NB == 2 && i + 1 < ntq) {
         mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
@@ -736,16 +824,14 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       umma_commit(&bars[3]);
     }
     const bool none = !(m > -FLT_MAX);
-    const bool plain = !has_bias && blk_all && !(p.causal && i == kb);
-    uint32_t words[4];
-    row_words(p, kbits4, kb, i, tid, none, words);
-    const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+    const uint32_t mw = row_word(p, kword, kb, i, rit, quarter, none);
+    const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
     const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
     __syncwarp();
     mbar_wait(&bars[3], aphase & 1); aphase++;
     tc_fence_after();
-    softmax_grad_block<true>(p, lane_addr, words, plain, bias_row, kb * 128, row_ok, m, inv, delta, drow, smem_u32(sP),
-                             smem_u32(sdS), tid);
+    softmax_grad_chunk<true, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, kb * 128 + quarter * 32, row_ok, m, inv,
+                                           delta, drow, smem_u32(sP), smem_u32(sdS), rit);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -765,16 +851,21 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_wait(&bars[4], bphase & 1); bphase++;
     tc_fence_after();
   }
-  const int key = kb * 128 + tid;
+  // quarters 0,1 store dV, quarters 2,3 store dK; each stores half of the D columns of its key row
+  {
+    const int key = kb * 128 + rit;
+    const bool is_k = quarter >= 2;
+    const int half = quarter & 1;
+    const uint32_t src = lane_addr + (is_k ? cdK : cdV) + half * (D / 2);
+    __nv_bfloat16* dst = (is_k ? dk + ((int64_t)rowk + key) * lddk : dv + ((int64_t)rowk + key) * lddv) + colq + half * (D / 2);
+    const float mul = is_k ? p.scale : 1.f;
 #pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + cdV + c * 32, r);
-    tmem_ld_wait();
-    if (key < p.seq_k) store_row_bf16(dv + ((int64_t)rowk + key) * lddv + colq + c * 32, r, 1.f);
-    tmem_ld_32x32(lane_addr + cdK + c * 32, r);
-    tmem_ld_wait();
-    if (key < p.seq_k) store_row_bf16(dk + ((int64_t)rowk + key) * lddk + colq + c * 32, r, p.scale);
+    for (int c = 0; c < D / 64; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(src + c * 32, r);
+      tmem_ld_wait();
+      if (key < p.seq_k) store_row_bf16(dst + c * 32, r, mul);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -810,34 +901,45 @@ int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float*
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntq = (p.seq_q + 127) / 128;
   dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
-  kern<<<grid, 320, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
+  kern<<<grid, 352, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
   return check_launch("mmgl_attn_fwd");
 }
 
-template <int D>
-int launch_bwd(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
-               const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch,
-               cudaStream_t stream) {
+template <int D, bool kBias, bool kDrop>
+int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                 const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* delta_ws,
+                 int64_t batch, cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;
   {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
-    auto kern = sattn_bwd_dq_kernel<D>;
+    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 2048 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
+    auto kern = sattn_bwd_dq_kernel<D, kBias, kDrop>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.seq_q + 127) / 128), (unsigned)p.heads, (unsigned)batch);
-    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
-                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq);
+    kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
+                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq, delta_ws);
     if (int rc = check_launch("mmgl_attn_bwd(dq)")) return rc;
   }
   {
     const size_t smem = (2 + 2 * NB) * (size_t)TB + 65536 + 16 + 5 * 8 + 16;
-    auto kern = sattn_bwd_dkv_kernel<D>;
+    auto kern = sattn_bwd_dkv_kernel<D, kBias, kDrop>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.seq_k + 127) / 128), (unsigned)p.heads, (unsigned)batch);
-    kern<<<grid, 128, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
-                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv);
+    kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, stats, delta_ws, (__nv_bfloat16*)dk, lddk,
+                                      (__nv_bfloat16*)dv, lddv);
     return check_launch("mmgl_attn_bwd(dkv)");
   }
+}
+
+template <int D>
+int launch_bwd(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+               const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* delta_ws,
+               int64_t batch, cudaStream_t stream) {
+  const bool bias = p.rel_bias != nullptr, drop = p.drop_thresh != 0;
+#define MMGL_BWD(B_, R_) launch_bwd_v<D, B_, R_>(mp, p, o, ldo, d_o, lddo, stats, dq, lddq, dk, lddk, dv, lddv, delta_ws, batch, stream)
+  if (bias) return drop ? MMGL_BWD(true, true) : MMGL_BWD(true, false);
+  return drop ? MMGL_BWD(false, true) : MMGL_BWD(false, false);
+#undef MMGL_BWD
 }
 
 int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
@@ -862,6 +964,13 @@ int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
 
 using namespace mmgl;
 
+#ifdef MMGL_TRACE
+extern "C" int mmgl_debug_trace(unsigned long long* host_dst) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_dst, g_trace, sizeof(g_trace));
+}
+#endif
+
 extern "C" int mmgl_attn_fwd(const mmgl_attn_args* a, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a != nullptr, "mmgl_attn_fwd: null args");
@@ -877,44 +986,28 @@ extern "C" int mmgl_attn_fwd(const mmgl_attn_args* a, void* stream_) {
   return launch_fwd<128>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
 }
 
+extern "C" size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t heads) {
+  return (size_t)(batch * seq_q * heads) * sizeof(float);
+}
+
 extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
-                             int64_t lddk, void* dv, int64_t lddv, void* stream_) {
+                             int64_t lddk, void* dv, int64_t lddv, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a != nullptr, "mmgl_attn_bwd: null args");
   MMGL_BIND(a->q, "mmgl_attn_bwd");
   AttnParams p;
   if (int rc = fill_params("mmgl_attn_bwd", a, p)) return rc;
   MMGL_REQUIRE(d_o && a->k && a->v && a->o && a->stats && dq && dk && dv, "mmgl_attn_bwd: null pointer");
+  MMGL_REQUIRE(workspace != nullptr && workspace_bytes >= mmgl_attn_bwd_workspace_bytes(a->batch, a->seq_q, a->heads),
+               "mmgl_attn_bwd: workspace too small (need mmgl_attn_bwd_workspace_bytes)");
   MMGL_REQUIRE(aligned16(d_o) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(dq) &&
                aligned16(dk) && aligned16(dv), "mmgl_attn_bwd: pointers must be 16B aligned");
   MMGL_REQUIRE(lddo % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && lddq % 8 == 0 &&
                lddk % 8 == 0 && lddv % 8 == 0, "mmgl_attn_bwd: leading dims must be multiples of 8");
   Maps mp;
   if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, d_o, lddo, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim)) return rc;
+  float* ws = reinterpret_cast<float*>(workspace);
   if (a->head_dim == 64)
-    return launch_bwd<64>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, a->batch, s);
-  return launch_bwd<128>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, a->batch, s);
-}
-
-// the self-attention special case (seq_q == seq_k, no bias, no dropout) kept as its own entry points
-extern "C" int mmgl_sattn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                              const uint8_t* key_mask, void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq,
-                              int64_t heads, int64_t d, float scale, int32_t causal, void* stream_) {
-  mmgl_attn_args a{};
-  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.key_mask = key_mask; a.o = o; a.ldo = ldo;
-  a.stats = stats; a.batch = batch; a.seq_q = seq; a.seq_k = seq; a.heads = heads; a.head_dim = d; a.scale = scale;
-  a.causal = causal;
-  return mmgl_attn_fwd(&a, stream_);
-}
-
-extern "C" int mmgl_sattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
-                              const void* v, int64_t ldv, const void* o, int64_t ldo, const float* stats,
-                              const uint8_t* key_mask, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
-                              int64_t lddv, int64_t batch, int64_t seq, int64_t heads, int64_t d, float scale,
-                              int32_t causal, void* stream_) {
-  mmgl_attn_args a{};
-  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.key_mask = key_mask; a.o = const_cast<void*>(o);
-  a.ldo = ldo; a.stats = const_cast<float*>(stats); a.batch = batch; a.seq_q = seq; a.seq_k = seq; a.heads = heads;
-  a.head_dim = d; a.scale = scale; a.causal = causal;
-  return mmgl_attn_bwd(&a, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, stream_);
+    return launch_bwd<64>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, ws, a->batch, s);
+  return launch_bwd<128>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, ws, a->batch, s);
 }

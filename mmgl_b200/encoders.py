@@ -37,7 +37,7 @@ def _attention(qkv, key_mask, b, s, heads, d, scale):
     h = heads * d
     o = torch.empty((b * s, h), dtype=BF16, device=qkv.device)
     stats = torch.empty((b, heads, s, 2), dtype=F32, device=qkv.device)
-    K.sattn_fwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], key_mask, o, stats, b, s, heads, d, scale, False)
+    K.attn_fwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], key_mask, None, o, stats, b, s, s, heads, d, scale, False)
     return o
 
 

@@ -1,4 +1,4 @@
-"""Causal / key-padded self-attention kernels (mmgl_sattn_fwd / mmgl_sattn_bwd) against the CPU
+"""Self-attention kernels (mmgl_attn_fwd / mmgl_attn_bwd) against the CPU
 oracle's mpt_attention core: the reference's MPTAttention self branch with the additive causal + padding mask
 (model/modelling_cross_attention.py:201-275, :455-476), fp32 on the bf16-rounded inputs.
 

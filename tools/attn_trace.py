@@ -1,0 +1,36 @@
+"""Timeline of CTA (0,0,0) of the attention forward kernel (needs a library built with -DMMGL_TRACE:
+MMGL_EXTRA_FLAGS=-DMMGL_TRACE python -m mmgl_b200.build --force).  Development tool."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmgl_b200 import _capi as K  # noqa: E402
+
+b, s, heads, d = int(sys.argv[1]) if len(sys.argv) > 1 else 8, int(sys.argv[2]) if len(sys.argv) > 2 else 640, 32, 64
+causal = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
+h = heads * d
+qkv = torch.randn(b * s, 3 * h, device="cuda").to(torch.bfloat16)
+o = torch.empty(b * s, h, dtype=torch.bfloat16, device="cuda")
+stats = torch.empty(b, heads, s, 2, dtype=torch.float32, device="cuda")
+for _ in range(3):
+    K.attn_fwd(qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:], None, None, o, stats, b, s, s, heads, d, d ** -0.5, causal)
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * 4096)()
+fn = C.CDLL(K.LIB_PATH).mmgl_debug_trace
+fn.argtypes = [C.c_void_p]
+fn(buf)
+ev = []
+for role in range(4):
+    for i in range(511):
+        tag, clk = buf[role * 1024 + 2 * i], buf[role * 1024 + 2 * i + 1]
+        if tag == 0:
+            break
+        ev.append((clk, role, tag))
+ev.sort()
+t0 = ev[0][0]
+names = {0: "softmax0", 1: "softmax0.w3", 2: "mma0", 3: "tma"}
+for clk, role, tag in ev:
+    print(f"{clk - t0:8d}  {names.get(role, role):9s} {tag}")
