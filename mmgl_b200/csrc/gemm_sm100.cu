@@ -66,23 +66,48 @@ struct GemmParams {
 };
 
 // activation codes of mmgl_gemm_args.relu: 1 = ReLU, 2 = GELU (erf form, nn.GELU / HF "gelu"), 3 = quick-GELU (CLIP)
+__device__ __forceinline__ float act_gelu(float v) {
+  // 0.5 v (1 + erf(v / sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding
+  // of the output): one rcp + one ex2 and no branches, ~3x fewer issue slots than erff() in a short-K epilogue.
+  // q = 1 - erf(z), z = |v| / sqrt2, is formed directly so the negative side does not cancel.
+  const float z = fabsf(v) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float ez;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ez) : "f"(-1.4426950408889634f * z * z));
+  const float q = poly * t * ez;
+  const float hv = 0.5f * v;
+  return v >= 0.f ? fmaf(-hv, q, v) : hv * q;
+}
+__device__ __forceinline__ float act_quick_gelu(float v) {
+  // v * sigmoid(1.702 v) = v / (1 + 2^(-1.702 log2e v))
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return v * r;
+}
+// the activation switch sits OUTSIDE the element loop: one uniform branch per chunk, straight-line code per element
+template <int N>
+__device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == 2) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = act_gelu(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = act_quick_gelu(v[j]);
+  }
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) {
-    // 0.5 v (1 + erf(v / sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding
-    // of the output): one rcp + one ex2 and no branches, ~3x fewer issue slots than erff() in a short-K epilogue.
-    // q = 1 - erf(z), z = |v| / sqrt2, is formed directly so the negative side does not cancel.
-    const float z = fabsf(v) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float q = poly * t * exp2f(-1.4426950408889634f * z * z);
-    const float hv = 0.5f * v;
-    return v >= 0.f ? fmaf(-hv, q, v) : hv * q;
-  }
-  return v / (1.f + __expf(-1.702f * v));
+  if (act == 2) return act_gelu(v);
+  return act_quick_gelu(v);
 }
 
 // 8 consecutive output columns of one row: fused epilogue + store.
@@ -96,10 +121,7 @@ __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
-  if (p.relu) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.relu);
-  }
+  if (p.relu) apply_act_vec<8>(v, p.relu);
   if (p.relu_mask != nullptr) {
     const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + row * p.ldmask + col));
     const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
@@ -211,12 +233,12 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
     for (int g = 0; g < 4; ++g) { res[g] = res_n[g]; msk[g] = msk_n[g]; }
     if (fast && c + 1 < c_end) prefetch(c + 1);
     tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     const int64_t col0 = n0 + c * 32;
     if (!row_ok || col0 >= p.n) continue;
     if (fast && col0 + 32 <= p.n) {
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       if (p.bias != nullptr) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -228,10 +250,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
       }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.relu);
-      }
+      if (p.relu) apply_act_vec<32>(v, p.relu);
       if (p.relu_mask != nullptr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -283,15 +302,15 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
     } else if (p.vec_ok && col0 + 32 <= p.n) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float v[8];
+        float v8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-        epilogue_store8(p, v, row, col0 + g * 8, gate_t);
+        for (int j = 0; j < 8; ++j) v8[j] = v[g * 8 + j];
+        epilogue_store8(p, v8, row, col0 + g * 8, gate_t);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.n) epilogue_store1(p, __uint_as_float(r[j]), row, col0 + j, gate_t);
+        if (col0 + j < p.n) epilogue_store1(p, v[j], row, col0 + j, gate_t);
     }
   }
 }

@@ -145,12 +145,34 @@ def bench_rowops():
                       "GBs": round(rows * 8192 * 2 / med / 1e6, 1)}), flush=True)
 
 
+def bench_encoder_gemm():
+    """short-K GEMMs of the frozen RoBERTa / CLIP encoders: activation cost in the epilogue, tile choices"""
+    for m, n, k, label in [(21504, 3072, 768, "roberta fc1"), (21504, 2304, 768, "roberta qkv"), (21504, 768, 3072, "roberta fc2"),
+                           (21504, 768, 768, "roberta out"), (4728, 3072, 768, "clip fc1")]:
+        a = torch.randn(m, k, device="cuda").to(BF16)
+        b = torch.randn(n, k, device="cuda").to(BF16)
+        out = torch.empty((m, n), dtype=BF16, device="cuda")
+        bias = torch.randn(n, device="cuda")
+        flops = 2.0 * m * n * k
+        r = {"kernel": "encoder_gemm", "label": label, "m": m, "n": n, "k": k}
+        for act in (0, 1, 2, 3):
+            for name, extra in (("auto", {}), ("s192", dict(block_n=192, pair=1)), ("s256", dict(block_n=256, pair=1)),
+                                ("p256", dict(block_n=256, pair=2))):
+                med, _ = time_it(lambda: K.gemm(a, b, out, bias=bias, relu=act, **extra))
+                r[f"act{act}_{name}"] = round(flops / med / 1e9, 1)
+        med, _ = time_it(lambda: torch.nn.functional.linear(a, b, bias.to(BF16)))
+        r["cublas"] = round(flops / med / 1e9, 1)
+        print(json.dumps(r), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
     if "gemm" in which:
         bench_gemm()
     if "epilogue" in which:
         bench_epilogue()
+    if "encoder" in which:
+        bench_encoder_gemm()
     if "xattn" in which:
         bench_xattn()
     if "rowops" in which:
