@@ -160,6 +160,16 @@ int mmgl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
                        const void* d_res, void* dx, float* dgamma, float* dbeta, int32_t accumulate,
                        void* workspace, size_t workspace_bytes, int64_t rows, int64_t hidden, void* stream);
 
+/* T5-style RMSNorm (HF models/t5/modeling_t5.py T5LayerNorm, the norm of the T5 language model on the concat path,
+ * model/modelling_self_attention.py:68): y = gamma * x * rsqrt(mean(x^2) + eps); no mean subtraction, no shift.
+ * Same kernels as LayerNorm in their mean-free mode; rstd [rows] saved for backward; dgamma may be NULL (frozen).
+ * workspace >= mmgl_layernorm_bwd_workspace_bytes. */
+int mmgl_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* rstd, int64_t rows, int64_t hidden, float eps,
+                     void* stream);
+int mmgl_rmsnorm_bwd(const void* dy, const void* x, const float* gamma, const float* rstd, const void* d_res, void* dx,
+                     float* dgamma, int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows,
+                     int64_t hidden, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Reductions used by the backward pass.
  * colsum:   out[n] (+)= scale * tanh?(gate) * sum_m x[m,n]      (bias gradients; x bf16 [M,N] ld)

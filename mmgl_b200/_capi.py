@@ -92,6 +92,8 @@ SIGNATURES = {
     "mmgl_layernorm_bwd_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_layernorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz,
                                      c_i64, c_i64, c_vp]),
+    "mmgl_rmsnorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
+    "mmgl_rmsnorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz, c_i64, c_i64, c_vp]),
     "mmgl_reduce_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_colsum": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_f32, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
     "mmgl_gate_grad": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
@@ -356,6 +358,25 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, d_res, dx, dgamma=None, dbeta=None, 
     _check(lib().mmgl_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(d_res), _p(dx), _p(dgamma),
                                     _p(dbeta), int(accumulate), _p(ws), nbytes, rows, hidden, _stream()),
            "mmgl_layernorm_bwd")
+
+
+def rmsnorm_fwd(x, gamma, y, rstd, eps):
+    _req_cuda(x, gamma, y, rstd)
+    rows, hidden = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and gamma.dtype == torch.float32
+    _check(lib().mmgl_rmsnorm_fwd(_p(x), _p(gamma), _p(y), _p(rstd), rows, hidden, eps, _stream()), "mmgl_rmsnorm_fwd")
+
+
+def rmsnorm_bwd(dy, x, gamma, rstd, d_res, dx, dgamma=None, accumulate=False):
+    _req_cuda(dy, x, gamma, rstd, dx)
+    rows, hidden = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and dx.is_contiguous() and (d_res is None or d_res.is_contiguous())
+    ws, nbytes = None, 0
+    if dgamma is not None:
+        nbytes = lib().mmgl_layernorm_bwd_workspace_bytes(rows, hidden)
+        ws = _workspace(nbytes, x.device)
+    _check(lib().mmgl_rmsnorm_bwd(_p(dy), _p(x), _p(gamma), _p(rstd), _p(d_res), _p(dx), _p(dgamma), int(accumulate),
+                                  _p(ws), nbytes, rows, hidden, _stream()), "mmgl_rmsnorm_bwd")
 
 
 # ------------------------------------------------------------------------------------------- reductions

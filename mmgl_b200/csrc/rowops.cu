@@ -42,7 +42,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
       for (int e = 0; e < 8; ++e) sum += f[e];
     }
   }
-  const float mu = warp_sum(sum) / hidden;
+  const bool rms = mean == nullptr;   // T5-style RMSNorm: no mean subtraction, no shift
+  const float mu = rms ? 0.f : warp_sum(sum) / hidden;
   float var = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -61,7 +62,11 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     if (idx < nvec) {
       float f[8]; unpack8(buf[i], f);
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + idx * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + idx * 2 + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2 + 1);
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (beta != nullptr) {
+        b0 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2);
+        b1 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2 + 1);
+      }
       const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -69,7 +74,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
       yr[idx] = pack8(f);
     }
   }
-  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  if (lane == 0) { if (!rms) mean[row] = mu; rstd[row] = rs; }
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm backward (dx)
@@ -85,7 +90,8 @@ layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
   const int nvec = hidden >> 3;
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * hidden);
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * hidden);
-  const float mu = mean[row], rs = rstd[row];
+  const bool rms = mean == nullptr;
+  const float mu = rms ? 0.f : mean[row], rs = rstd[row];
   uint4 bg[MAXV], bx[MAXV];  // g = dy*gamma (kept as bf16-packed? no: keep dy and x packed, recompute)
   float c1 = 0.f, c2 = 0.f;
 #pragma unroll
@@ -105,7 +111,7 @@ layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
       }
     }
   }
-  c1 = warp_sum(c1) / hidden;
+  c1 = rms ? 0.f : warp_sum(c1) / hidden;   // RMSNorm has no mean term
   c2 = warp_sum(c2) / hidden;
   uint4* dxr = reinterpret_cast<uint4*>(dx + row * hidden);
   const uint4* rr = d_res ? reinterpret_cast<const uint4*>(d_res + row * hidden) : nullptr;
@@ -159,7 +165,7 @@ col_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_
 #pragma unroll
         for (int e = 0; e < 8; ++e) fx[e] = (col + e < n) ? __bfloat162float(x[r * ldx + col + e]) : 0.f;
       }
-      const float mu = mean[r], rs = rstd[r];
+      const float mu = mean != nullptr ? mean[r] : 0.f, rs = rstd[r];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += fa[e] * (fx[e] - mu) * rs;
     } else {
@@ -526,21 +532,32 @@ static int reduce_chunks(int64_t m) {
 
 using namespace mmgl;
 
-extern "C" int mmgl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                                  float* rstd, int64_t rows, int64_t hidden, float eps, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  MMGL_BIND(x, "mmgl_layernorm_fwd");
-  MMGL_REQUIRE(x && gamma && beta && y && mean && rstd, "mmgl_layernorm_fwd: null pointer");
+static int norm_fwd(const char* who, const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                    float* rstd, int64_t rows, int64_t hidden, float eps, cudaStream_t s) {
   MMGL_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && hidden <= 8192,
-               "mmgl_layernorm_fwd: hidden must be a multiple of 8 and <= 8192 (got %lld)", (long long)hidden);
-  MMGL_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "mmgl_layernorm_fwd: unaligned");
+               "%s: hidden must be a multiple of 8 and <= 8192 (got %lld)", who, (long long)hidden);
+  MMGL_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && (!beta || aligned16(beta)), "%s: unaligned", who);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
   if (hidden <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
   else if (hidden <= 2048) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
   else if (hidden <= 4096) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
   else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
-  return check_launch("mmgl_layernorm_fwd");
+  return check_launch(who);
+}
+
+extern "C" int mmgl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, int64_t rows, int64_t hidden, float eps, void* stream_) {
+  MMGL_BIND(x, "mmgl_layernorm_fwd");
+  MMGL_REQUIRE(x && gamma && beta && y && mean && rstd, "mmgl_layernorm_fwd: null pointer");
+  return norm_fwd("mmgl_layernorm_fwd", x, gamma, beta, y, mean, rstd, rows, hidden, eps, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mmgl_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* rstd, int64_t rows, int64_t hidden,
+                                float eps, void* stream_) {
+  MMGL_BIND(x, "mmgl_rmsnorm_fwd");
+  MMGL_REQUIRE(x && gamma && y && rstd, "mmgl_rmsnorm_fwd: null pointer");
+  return norm_fwd("mmgl_rmsnorm_fwd", x, gamma, nullptr, y, nullptr, rstd, rows, hidden, eps, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" size_t mmgl_reduce_workspace_bytes(int64_t m, int64_t n) {
@@ -551,45 +568,59 @@ extern "C" size_t mmgl_layernorm_bwd_workspace_bytes(int64_t rows, int64_t hidde
   return mmgl_reduce_workspace_bytes(rows, hidden);
 }
 
-extern "C" int mmgl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
-                                  const float* rstd, const void* d_res, void* dx, float* dgamma, float* dbeta,
-                                  int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows,
-                                  int64_t hidden, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  MMGL_BIND(x, "mmgl_layernorm_bwd");
-  MMGL_REQUIRE(dy && x && gamma && mean && rstd && dx, "mmgl_layernorm_bwd: null pointer");
+static int norm_bwd(const char* who, const void* dy, const void* x, const float* gamma, const float* mean,
+                    const float* rstd, const void* d_res, void* dx, float* dgamma, float* dbeta, int32_t accumulate,
+                    void* workspace, size_t workspace_bytes, int64_t rows, int64_t hidden, cudaStream_t s) {
   MMGL_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && hidden <= 4096,
-               "mmgl_layernorm_bwd: hidden must be a multiple of 8 and <= 4096 (got %lld)", (long long)hidden);
+               "%s: hidden must be a multiple of 8 and <= 4096 (got %lld)", who, (long long)hidden);
   MMGL_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!d_res || aligned16(d_res)),
-               "mmgl_layernorm_bwd: unaligned");
+               "%s: unaligned", who);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const auto DY = (const __nv_bfloat16*)dy; const auto X = (const __nv_bfloat16*)x;
   const auto R = (const __nv_bfloat16*)d_res; auto DX = (__nv_bfloat16*)dx;
   if (hidden <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden);
   else if (hidden <= 2048) layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden);
   else layernorm_bwd_dx_kernel<16><<<grid, 256, 0, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden);
-  if (int rc = check_launch("mmgl_layernorm_bwd(dx)")) return rc;
+  if (int rc = check_launch(who)) return rc;
   if (dgamma != nullptr || dbeta != nullptr) {
-    MMGL_REQUIRE(workspace && workspace_bytes >= mmgl_layernorm_bwd_workspace_bytes(rows, hidden),
-                 "mmgl_layernorm_bwd: workspace too small");
+    MMGL_REQUIRE(workspace && workspace_bytes >= mmgl_layernorm_bwd_workspace_bytes(rows, hidden), "%s: workspace too small", who);
     const int chunks = reduce_chunks(rows);
     const int64_t rpc = (rows + chunks - 1) / chunks;
     dim3 g((unsigned)((hidden + 2047) / 2048), (unsigned)chunks);
     float* ws = reinterpret_cast<float*>(workspace);
     if (dgamma) {
       col_partial_kernel<1><<<g, 256, 0, s>>>(DY, hidden, X, hidden, mean, rstd, ws, rows, hidden, rpc);
-      if (int rc = check_launch("mmgl_layernorm_bwd(dgamma)")) return rc;
+      if (int rc = check_launch(who)) return rc;
       col_final_kernel<<<(unsigned)((hidden + 255) / 256), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dgamma, accumulate);
-      if (int rc = check_launch("mmgl_layernorm_bwd(dgamma final)")) return rc;
+      if (int rc = check_launch(who)) return rc;
     }
     if (dbeta) {
       col_partial_kernel<0><<<g, 256, 0, s>>>(DY, hidden, nullptr, 0, nullptr, nullptr, ws, rows, hidden, rpc);
-      if (int rc = check_launch("mmgl_layernorm_bwd(dbeta)")) return rc;
+      if (int rc = check_launch(who)) return rc;
       col_final_kernel<<<(unsigned)((hidden + 255) / 256), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dbeta, accumulate);
-      if (int rc = check_launch("mmgl_layernorm_bwd(dbeta final)")) return rc;
+      if (int rc = check_launch(who)) return rc;
     }
   }
   return 0;
+}
+
+extern "C" int mmgl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                  const float* rstd, const void* d_res, void* dx, float* dgamma, float* dbeta,
+                                  int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t rows,
+                                  int64_t hidden, void* stream_) {
+  MMGL_BIND(x, "mmgl_layernorm_bwd");
+  MMGL_REQUIRE(dy && x && gamma && mean && rstd && dx, "mmgl_layernorm_bwd: null pointer");
+  return norm_bwd("mmgl_layernorm_bwd", dy, x, gamma, mean, rstd, d_res, dx, dgamma, dbeta, accumulate, workspace,
+                  workspace_bytes, rows, hidden, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mmgl_rmsnorm_bwd(const void* dy, const void* x, const float* gamma, const float* rstd, const void* d_res,
+                                void* dx, float* dgamma, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                int64_t rows, int64_t hidden, void* stream_) {
+  MMGL_BIND(x, "mmgl_rmsnorm_bwd");
+  MMGL_REQUIRE(dy && x && gamma && rstd && dx, "mmgl_rmsnorm_bwd: null pointer");
+  return norm_bwd("mmgl_rmsnorm_bwd", dy, x, gamma, nullptr, rstd, d_res, dx, dgamma, nullptr, accumulate, workspace,
+                  workspace_bytes, rows, hidden, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, float scale, const float* gate,

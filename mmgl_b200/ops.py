@@ -283,6 +283,59 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
 
 
+class RMSNormFn(torch.autograd.Function):
+    """T5LayerNorm (HF models/t5/modeling_t5.py:46-70): y = weight * x * rsqrt(mean(x^2) + eps), fp32 statistics."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        x2 = _as2d(x)
+        y = torch.empty_like(x2)
+        rstd = torch.empty(x2.shape[0], dtype=F32, device=x2.device)
+        K.rmsnorm_fwd(x2, f32(weight), y, rstd, eps)
+        ctx.save_for_backward(x2, weight, rstd)
+        ctx.x_shape = x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, rstd = ctx.saved_tensors
+        dx = torch.empty_like(x2)
+        dg = torch.empty(x2.shape[1], dtype=F32, device=x2.device) if ctx.needs_input_grad[1] else None
+        K.rmsnorm_bwd(_as2d(dy), x2, f32(weight), rstd, None, dx, dg)
+        if dg is not None and weight.dtype != F32:
+            dg = dg.to(weight.dtype)
+        return dx.reshape(ctx.x_shape), dg, None
+
+
+def rms_norm(x, weight, eps=1e-6):
+    return RMSNormFn.apply(x, weight, float(eps))
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout on an activation tensor with the library's counter-based mask (no mask tensor is stored)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x2 = _as2d(x)
+        seed = next_dropout_seed()
+        y = torch.empty_like(x2)
+        K.dropout_apply(x2, y, p, seed)
+        ctx.drop = (p, seed)
+        ctx.x_shape = x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _undrop(_as2d(dy), *ctx.drop).reshape(ctx.x_shape), None
+
+
+def dropout(x, p):
+    """x (bf16 [..., H]) -> dropout(x); identity when p == 0."""
+    if p <= 0.0:
+        return x
+    return DropoutFn.apply(x, float(p))
+
+
 # --------------------------------------------------------------------------------------------- cross-entropy
 class CrossEntropyFn(torch.autograd.Function):
     """mean softmax cross-entropy over bf16 logits [rows, V] with int64 labels [rows] (ignore_index rows skipped):
@@ -328,14 +381,16 @@ def shifted_cross_entropy(logits, labels, ignore_index=-100):
 
 # --------------------------------------------------------------------------------------------- MLP
 class MLPFn(torch.autograd.Function):
-    """y = residual + dropout(fc2(relu(fc1(x)))): model/modelling_cross_attention.py:352-361 (non-gated form).
-    ReLU, its backward mask and the dropout live in the GEMM epilogues; no [M,F] elementwise pass touches HBM."""
+    """y = residual + dropout(fc2(dropout_h(relu(fc1(x))))): model/modelling_cross_attention.py:352-361 (non-gated form;
+    dropout_h = 0) and HF T5DenseActDense + T5LayerFF (dropout on the hidden activation as well).  ReLU, its backward
+    mask and both dropouts live in the GEMM epilogues; no [M,F] elementwise pass touches HBM."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, residual, dropout_p):
+    def forward(ctx, x, w1, b1, w2, b2, residual, dropout_p, hidden_dropout_p):
         x2 = _as2d(x)
         f = _new(x2.shape[0], w1.shape[0], x2)
-        K.gemm(x2, w16(w1), f, bias=f32(b1), relu=True)
+        seed_h = next_dropout_seed() if hidden_dropout_p > 0.0 else 0
+        K.gemm(x2, w16(w1), f, bias=f32(b1), relu=True, dropout_p=hidden_dropout_p, dropout_seed=seed_h)
         y = _new(x2.shape[0], w2.shape[0], x2)
         r2 = _as2d(residual) if residual is not None else None
         seed = next_dropout_seed() if dropout_p > 0.0 else 0
@@ -343,6 +398,7 @@ class MLPFn(torch.autograd.Function):
         ctx.save_for_backward(x2, f, w1, b1, w2, b2)
         ctx.has_res = residual is not None
         ctx.drop = (dropout_p, seed)
+        ctx.drop_h = (hidden_dropout_p, seed_h)
         ctx.x_shape = x.shape
         return y.reshape(*x.shape[:-1], w2.shape[0])
 
@@ -351,7 +407,8 @@ class MLPFn(torch.autograd.Function):
         x2, f, w1, b1, w2, b2 = ctx.saved_tensors
         dy2 = _undrop(_as2d(dy), *ctx.drop)
         df = torch.empty_like(f)
-        K.gemm(dy2, w16(w2), df, b_t=True, relu_mask=f)
+        # f = dropout_h(relu(.)) is zero where either zeroed it; the kept entries carry the 1 / (1 - p) of dropout_h
+        K.gemm(dy2, w16(w2), df, b_t=True, relu_mask=f, dropout_p=ctx.drop_h[0], dropout_seed=ctx.drop_h[1])
         dx = dw1 = db1 = dw2 = db2 = dres = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
@@ -367,11 +424,11 @@ class MLPFn(torch.autograd.Function):
             db2 = _bgrad(dy2, b2)
         if ctx.has_res and ctx.needs_input_grad[5]:
             dres = dy
-        return dx, dw1, db1, dw2, db2, dres, None
+        return dx, dw1, db1, dw2, db2, dres, None, None
 
 
-def mlp(x, w1, b1, w2, b2, residual=None, dropout_p=0.0):
-    return MLPFn.apply(x, w1, b1, w2, b2, residual, float(dropout_p))
+def mlp(x, w1, b1, w2, b2, residual=None, dropout_p=0.0, hidden_dropout_p=0.0):
+    return MLPFn.apply(x, w1, b1, w2, b2, residual, float(dropout_p), float(hidden_dropout_p))
 
 
 # --------------------------------------------------------------------------------------------- attention core

@@ -1,11 +1,14 @@
 """SelfAttentionModel: the concatenated-embedding path (reference: model/modelling_self_attention.py:48-336).
 
 Neighbor embeddings (projected, packed, optionally shifted by the Laplacian-PE projection or the GCN) are appended
-to the token embeddings and the whole sequence runs through a HuggingFace T5 / OPT language model.  On this path the
-package's CUDA kernels are: the neighbor projections, the ragged bank packing with the fused position-embedding /
-LPE add (ops.bank_pack), the GCN (ops.gcn) and the LoRA linears on the LM's q / v projections (ops.lora_linear: the
-rank-r update accumulates into the same TMEM tile as the base product).  The LM's own attention / norm / FFN
-arithmetic stays in HF ``transformers`` exactly as in the reference (third-party code there as well).
+to the token embeddings and the whole sequence runs through a T5 / OPT language model.  On this path the package's CUDA
+kernels are: the neighbor projections, the ragged bank packing with the fused position-embedding / LPE add
+(ops.bank_pack), the GCN (ops.gcn), the LoRA linears on the LM's q / v projections (ops.lora_linear: the rank-r update
+accumulates into the same TMEM tile as the base product) and the language model's own layer stack -- attention with the
+T5 relative-position bias or the OPT causal / padding mask, RMSNorm / LayerNorm, FFN, lm_head and the loss
+(mmgl_b200/lm.py, which reads the weights of the HF module in place).  Models that file cannot run (gated-GELU T5,
+head dims other than 64 / 128, a trainable relative-position table under peft "none") fall back to the HF module's own
+forward, as in the reference (third-party code there as well).
 
 peft is not importable in this image and its source is absent, so LoRA / prompt tuning are restated from their
 published definitions (parity unpinned, see oracle/mmgl_oracle.py:lora_linear); module and state-dict names follow
@@ -23,6 +26,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import lm as lm_kernels
 from . import ops
 from .modules import BF16, GCN, _load_or_init, _NeighborEncoderMixin
 
@@ -66,6 +70,7 @@ class _PeftShim(nn.Module):
     def __init__(self, model, prompt_tokens: int = 0):
         super().__init__()
         self.base_model = _PeftHolder(model)
+        self.use_kernel_lm = True
         self.num_virtual_tokens = prompt_tokens
         if prompt_tokens:
             dim = model.get_input_embeddings().embedding_dim
@@ -88,7 +93,22 @@ class _PeftShim(nn.Module):
             if labels is not None and not lm.config.is_encoder_decoder:
                 pad = torch.full((b, self.num_virtual_tokens), -100, dtype=labels.dtype, device=labels.device)
                 labels = torch.cat((pad, labels), 1)
-        return lm(input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds, labels=labels, **kw)
+        return run_language_model(lm, self.use_kernel_lm, input_ids=input_ids, attention_mask=attention_mask,
+                                  inputs_embeds=inputs_embeds, labels=labels, **kw)
+
+
+def run_language_model(lm, use_kernels=True, **kw):
+    """The LM call of the concat path (model/modelling_self_attention.py:246, :261, :280, :332).  HF T5 / OPT models
+    that ``lm_kernels.supports`` run their layer stack on this package's kernels (mmgl_b200/lm.py); anything else (and
+    the peft shim, which forwards to its base model through this function) goes through the module's own forward --
+    HF library code under bf16 autocast, as in the reference."""
+    if isinstance(lm, _PeftShim):
+        lm.use_kernel_lm = use_kernels
+        return lm(**kw)
+    if use_kernels and kw.get("labels") is not None and lm_kernels.supports(lm):
+        return lm_kernels.forward(lm, **kw)
+    with torch.autocast("cuda", dtype=BF16):
+        return lm(**kw)
 
 
 def apply_lora(model: nn.Module, r: int, alpha: float, dropout: float) -> int:
@@ -167,9 +187,10 @@ class SelfAttentionModel(nn.Module, _NeighborEncoderMixin):
         self._freeze_modes()
         return self
 
+    use_kernel_lm = True
+
     def _run_lm(self, **kw):
-        with torch.autocast("cuda", dtype=BF16):
-            return self.lm(**kw)
+        return run_language_model(self.lm, self.use_kernel_lm, **kw)
 
     def forward(self, input_ids, attention_mask, labels, images=None, image_positions=None, neighbor_input_ids=None,
                 neighbor_attention_mask=None, neighbor_pos_ids=None, text_locations=None, neighbor_images=None,
