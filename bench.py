@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="sections per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "tiny"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
     ap.add_argument("--profile-step", action="store_true",
@@ -56,6 +56,10 @@ WORKLOADS = {
     # configs[3]: <=32 neighbors + graph positional encodings (Laplacian)
     "cfg4": dict(lm="opt-1.3b", text="roberta-base", visual="clip-vit-base-patch16", s_in=512, s_out=128, t=22, i=10,
                  position_type="laplacian"),
+    # configs[2]: T5-base, concat (self-attention) path, PEFT = LoRA -- a parity-test configuration, timed on request only
+    # (python bench.py --workload cfg3); the judged line is cfg2
+    "cfg3": dict(kind="self", lm="t5-base", text="roberta-base", visual="clip-vit-base-patch16", s_in=512, s_out=128, t=11,
+                 i=5, position_type="none"),
     # plumbing-size model for quick checks
     "tiny": dict(lm="opt-125m", text="roberta-base", visual="clip-vit-base-patch16", s_in=128, s_out=128, t=3, i=2,
                  position_type="none"),
@@ -63,6 +67,12 @@ WORKLOADS = {
 
 
 def make_args(w):
+    if w.get("kind") == "self":
+        return types.SimpleNamespace(
+            context="all", neighbor_mode="embedding", peft_type="lora", n_text_tokens=4, n_visual_tokens=4,
+            model_name_or_path=w["lm"], text_model=w["text"], visual_model=w["visual"], max_output_length=w["s_out"],
+            freeze_lm=False, lora_r=64, lora_alpha=1, lora_dropout=0.0, position_type=w["position_type"],
+            max_text_neighbors=w["t"], max_image_neighbors=w["i"], decoder_only="t5" not in w["lm"])
     return types.SimpleNamespace(
         context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=4, n_visual_tokens=4,
         model_name_or_path=w["lm"], text_model=w["text"], visual_model=w["visual"], max_output_length=w["s_out"],
@@ -72,9 +82,12 @@ def make_args(w):
 
 def spec_for(w, batch):
     from mmgl_b200 import synth
+    extra = {}
+    if w.get("kind") == "self" and "t5" in w["lm"]:
+        extra = dict(vocab_size=32128, decoder_only=False, pad_token_id=0)
     return synth.BatchSpec(batch=batch, max_input_length=w["s_in"], max_output_length=w["s_out"], text_neighbors=w["t"],
                            image_neighbors=w["i"], with_lpe=w["position_type"] == "laplacian",
-                           with_graph=w["position_type"] == "gnn")
+                           with_graph=w["position_type"] == "gnn", **extra)
 
 
 def peaks():
@@ -157,7 +170,8 @@ def run_reference(a, w):
 
 
 def workload_name(a, w):
-    return (f"{a.workload}: {w['lm']} context=all neighbor_mode=embedding PEFT=flamingo + {w['text']} + {w['visual']}, "
+    peft = "lora (concat / self-attention path)" if w.get("kind") == "self" else "flamingo"
+    return (f"{a.workload}: {w['lm']} context=all neighbor_mode=embedding PEFT={peft} + {w['text']} + {w['visual']}, "
             f"seq {w['s_in']}+{w['s_out']}, {w['t']} text + {w['i']} image neighbors x 4 tokens, "
             f"position_type={w['position_type']}")
 
@@ -179,8 +193,13 @@ def run_ours(a, w):
 
     torch.manual_seed(1234)
     args = make_args(w)
+    self_path = w.get("kind") == "self"
     with torch.device(dev):
-        model = modules.CrossAttentionModel(args, tokenizer=None)
+        if self_path:
+            from mmgl_b200.self_attention import SelfAttentionModel
+            model = SelfAttentionModel(args, tokenizer=None)
+        else:
+            model = modules.CrossAttentionModel(args, tokenizer=None)
     with torch.no_grad():
         for n, p in model.named_parameters():
             if "gating" in n:
@@ -212,7 +231,7 @@ def run_ours(a, w):
         out.loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return float(out.loss)                          # D2H read of the step's loss
+        return float(out.loss.detach())                 # D2H read of the step's loss
 
     def barrier():
         torch.cuda.synchronize()
@@ -298,11 +317,12 @@ def run_ours(a, w):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
         "roofline": roofline, "roofline_attention": extra,
-        "roofline_block": block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev), "clocks": clocks,
+        "roofline_block": None if self_path else block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev),
+        "clocks": clocks,
         "loss": [float(loss_res), float(loss_e2e)],
         "trainable_params": sum(p.numel() for p in params),
     }
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and not self_path:
         line["cpu_baseline"] = cpu_baseline(a, w)
     print(json.dumps(line), flush=True)
     if world > 1:

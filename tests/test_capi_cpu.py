@@ -28,7 +28,8 @@ def test_header_declares_expected_entry_points():
     syms = _declared_symbols()
     for must in ("mmgl_gemm_bf16", "mmgl_xattn_fwd", "mmgl_xattn_bwd", "mmgl_layernorm_fwd", "mmgl_layernorm_bwd",
                  "mmgl_bank_pack_fwd", "mmgl_bank_pack_bwd", "mmgl_gcn_concat_fwd", "mmgl_gcn_combine_bwd",
-                 "mmgl_last_error_string", "mmgl_version", "mmgl_launch_count"):
+                 "mmgl_attn_fwd", "mmgl_attn_bwd", "mmgl_attn_bwd_workspace_bytes", "mmgl_rmsnorm_fwd", "mmgl_rmsnorm_bwd",
+                 "mmgl_ce_fwd", "mmgl_ce_bwd", "mmgl_last_error_string", "mmgl_version", "mmgl_launch_count"):
         assert must in syms
 
 
@@ -54,12 +55,14 @@ def test_struct_layouts_match_header():
     from mmgl_b200 import _capi
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
-        open(src, "w").write('#include <stdio.h>\n#include "mmgl_b200.h"\nint main(){printf("%zu %zu %zu\\n", '
-                             'sizeof(mmgl_gemm_args), sizeof(mmgl_bank_args), sizeof(mmgl_bank_bwd_args));return 0;}\n')
+        open(src, "w").write('#include <stdio.h>\n#include "mmgl_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", '
+                             'sizeof(mmgl_gemm_args), sizeof(mmgl_bank_args), sizeof(mmgl_bank_bwd_args), '
+                             'sizeof(mmgl_attn_args));return 0;}\n')
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(_capi.GemmArgs), ctypes.sizeof(_capi.BankArgs), ctypes.sizeof(_capi.BankBwdArgs)]
+    assert sizes == [ctypes.sizeof(_capi.GemmArgs), ctypes.sizeof(_capi.BankArgs), ctypes.sizeof(_capi.BankBwdArgs),
+                     ctypes.sizeof(_capi.AttnArgs)]
 
 
 def test_product_never_imports_oracle():
