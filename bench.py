@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- sections/sec of MMGL's neighbor-fusion training step on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--workload cfg2|cfg4|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|tiny]
     (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 A "step" is one optimisation step of CrossAttentionModel on one synthetic WikiWeb2M-shaped micro-batch per GPU:

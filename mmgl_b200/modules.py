@@ -9,9 +9,10 @@ What runs where
   * gated cross-attention layers (``MPTDecoderLayer(cross_attention=True)``), the neighbor projections, the ragged
     bank packing (+ Laplacian-PE projection), the GCN, LoRA linears and every nn.Linear / LayerNorm / FFN of the
     frozen decoder layers: this package's CUDA kernels (``ops``), forward and backward.
-  * the causal self-attention *core* of the frozen OPT layers, the frozen RoBERTa / CLIP encoders and the
-    SelfAttentionModel's HF language model: PyTorch / HF library code for now ("next").
-    The lm_head projection and the shifted cross-entropy (row f3) run in this package's kernels.
+  * the causal self-attention core of the frozen OPT layers (``ops.self_attention``), the frozen RoBERTa / CLIP
+    encoders (``encoders``: HF weights read in place), the lm_head projection and the shifted cross-entropy: this
+    package's kernels as well.  Library fallbacks remain only for shapes the kernels do not cover (head dims other than
+    64 / 128, arbitrary 4-D masks handed in by other callers).
 There is no CPU path: modules raise on CPU tensors.
 
 Reference defects that are deliberately NOT inherited: D1 (``neighbor_layer_wise`` vs
@@ -113,7 +114,7 @@ def _allowed_from_additive(mask: Optional[torch.Tensor]) -> Optional[torch.Tenso
 class MPTAttention(nn.Module):
     """model/modelling_cross_attention.py:148-275.  Cross branch: q/k/v projections (bias and the d^-1/2 scale in
     the GEMM epilogue) + the fused attention core + out_proj.  Self branch (frozen OPT layers): projections through
-    the same GEMM kernel, causal core through torch SDPA."""
+    the same GEMM kernel (one fused QKV GEMM when frozen), causal / key-padded core through ops.self_attention."""
 
     def __init__(self, config, cross_attention):
         super().__init__()
