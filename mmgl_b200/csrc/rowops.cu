@@ -149,7 +149,39 @@ col_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_
   const int64_t r1 = min(m, r0 + rows_per_chunk);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool full = col + 8 <= n;
-  for (int64_t r = r0; r < r1; ++r) {
+  int64_t r = r0;
+  if (full && MODE == 0) {
+    // four rows per trip: independent 16-byte loads in flight (this kernel is pure bandwidth; one load per trip left it
+    // latency-bound at ~1 TB/s)
+    for (; r + 4 <= r1; r += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(a + (r + u) * lda + col));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8]; unpack8(v[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+  } else if (full) {
+    for (; r + 2 <= r1; r += 2) {
+      uint4 va[2], vx[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        va[u] = __ldg(reinterpret_cast<const uint4*>(a + (r + u) * lda + col));
+        vx[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u) * ldx + col));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float fa2[8], fx2[8]; unpack8(va[u], fa2); unpack8(vx[u], fx2);
+        const float mu = mean != nullptr ? mean[r + u] : 0.f, rs = rstd[r + u];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += fa2[e] * (fx2[e] - mu) * rs;
+      }
+    }
+  }
+  for (; r < r1; ++r) {
     float fa[8];
     if (full) {
       unpack8(__ldg(reinterpret_cast<const uint4*>(a + r * lda + col)), fa);
@@ -178,16 +210,27 @@ col_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_
   for (int e = 0; e < 8; ++e) if (col + e < n) p[e] = acc[e];
 }
 
+// block = 32 columns x 8 chunk lanes: lane y sums chunks y, y+8, ... (coalesced 128-byte reads), then a fixed-order
+// shared-memory reduction over the 8 lanes -> deterministic
 __global__ void __launch_bounds__(256)
 col_final_kernel(const float* __restrict__ partial, int chunks, int64_t n, float scale, const float* __restrict__ gate,
                  float* __restrict__ out, int accumulate) {
-  const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (col >= n) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * n + col];
-  if (gate != nullptr) s *= tanhf(__ldg(gate));
-  s *= scale;
-  out[col] = accumulate ? out[col] + s : s;
+  if (col < n)
+    for (int c = ty; c < chunks; c += 8) s += partial[(int64_t)c * n + col];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][tx];
+    if (gate != nullptr) t *= tanhf(__ldg(gate));
+    t *= scale;
+    out[col] = accumulate ? out[col] + t : t;
+  }
 }
 
 // dot over all elements of two [m,n] bf16 matrices -> per-block partials -> scalar
@@ -522,8 +565,8 @@ gcn_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dc, const float* __rest
 }
 
 static int reduce_chunks(int64_t m) {
-  int64_t c = (m + 31) / 32;
-  if (c > 296) c = 296;
+  int64_t c = (m + 15) / 16;   // 16 rows per chunk: >= 2 CTAs per SM at the step's M = 5120
+  if (c > 1024) c = 1024;
   if (c < 1) c = 1;
   return (int)c;
 }
@@ -591,13 +634,13 @@ static int norm_bwd(const char* who, const void* dy, const void* x, const float*
     if (dgamma) {
       col_partial_kernel<1><<<g, 256, 0, s>>>(DY, hidden, X, hidden, mean, rstd, ws, rows, hidden, rpc);
       if (int rc = check_launch(who)) return rc;
-      col_final_kernel<<<(unsigned)((hidden + 255) / 256), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dgamma, accumulate);
+      col_final_kernel<<<(unsigned)((hidden + 31) / 32), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dgamma, accumulate);
       if (int rc = check_launch(who)) return rc;
     }
     if (dbeta) {
       col_partial_kernel<0><<<g, 256, 0, s>>>(DY, hidden, nullptr, 0, nullptr, nullptr, ws, rows, hidden, rpc);
       if (int rc = check_launch(who)) return rc;
-      col_final_kernel<<<(unsigned)((hidden + 255) / 256), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dbeta, accumulate);
+      col_final_kernel<<<(unsigned)((hidden + 31) / 32), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dbeta, accumulate);
       if (int rc = check_launch(who)) return rc;
     }
   }
@@ -636,7 +679,7 @@ extern "C" int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, flo
   float* ws = reinterpret_cast<float*>(workspace);
   col_partial_kernel<0><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, ws, m, n, rpc);
   if (int rc = check_launch("mmgl_colsum(partial)")) return rc;
-  col_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws, chunks, n, scale, gate, out, accumulate);
+  col_final_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(ws, chunks, n, scale, gate, out, accumulate);
   return check_launch("mmgl_colsum(final)");
 }
 

@@ -165,6 +165,26 @@ def bench_encoder_gemm():
         print(json.dumps(r), flush=True)
 
 
+def bench_tiles():
+    """tile / pair choices on the step's forward shapes (B K-major)"""
+    for m, n, k, label in [(5120, 2048, 8192, "fc2"), (5120, 2048, 2048, "out_proj"), (5120, 6144, 2048, "qkv"),
+                           (5120, 8192, 2048, "fc1"), (21504, 3072, 768, "roberta fc1"), (21504, 2304, 768, "roberta qkv"),
+                           (21504, 768, 3072, "roberta fc2"), (21504, 768, 768, "roberta out"), (4728, 3072, 768, "clip fc1"),
+                           (4608, 768, 768, "t5 proj"), (5120, 50272, 2048, "lm_head")]:
+        a = torch.randn(m, k, device="cuda").to(BF16)
+        b = torch.randn(n, k, device="cuda").to(BF16)
+        out = torch.empty((m, n), dtype=BF16, device="cuda")
+        bias = torch.randn(n, device="cuda")
+        flops = 2.0 * m * n * k
+        r = {"kernel": "tiles", "label": label, "m": m, "n": n, "k": k}
+        for name, extra in (("auto", {}), ("s128", dict(block_n=128, pair=1)), ("s192", dict(block_n=192, pair=1)),
+                            ("s256", dict(block_n=256, pair=1)), ("p128", dict(block_n=128, pair=2)),
+                            ("p192", dict(block_n=192, pair=2)), ("p256", dict(block_n=256, pair=2))):
+            med, _ = time_it(lambda: K.gemm(a, b, out, bias=bias, relu=1, **extra))
+            r[name] = round(flops / med / 1e9, 1)
+        print(json.dumps(r), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
     if "gemm" in which:
@@ -173,6 +193,8 @@ if __name__ == "__main__":
         bench_epilogue()
     if "encoder" in which:
         bench_encoder_gemm()
+    if "tiles" in which:
+        bench_tiles()
     if "xattn" in which:
         bench_xattn()
     if "rowops" in which:
