@@ -113,7 +113,8 @@ int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
  *   O = (keep / (1 - dropout_p) . P) V     per (sample, head)
  * q, o [B,seq_q,nh*d]; k, v [B,seq_k,nh*d] bf16 (views with leading dims: the three thirds of one fused
  * [B*S, 3*nh*d] QKV projection work in place); key_mask [B,seq_k] bytes (1 = real token) or NULL; causal != 0 masks
- * keys > query (needs seq_q == seq_k); rel_bias fp32 [heads, seq_q + seq_k - 1] or NULL; stats [B,nh,seq_q,2] =
+ * keys > query + (seq_k - seq_q) (needs seq_q <= seq_k: the queries sit at the END of the key range, as with the
+ * virtual-token K/V that peft prefix tuning prepends, model/modelling_self_attention.py:88-92); rel_bias fp32 [heads, seq_q + seq_k - 1] or NULL; stats [B,nh,seq_q,2] =
  * (row max of the masked scores, 1 / row sum) saved for backward.  head_dim in {64,128}; seq_k <= 8192.
  * keep = the counter-based mask of mmgl_dropout_apply over the [batch*heads*seq_q, seq_k] probability matrix,
  * row = (b*heads + h)*seq_q + i.

@@ -57,6 +57,7 @@ struct AttnParams {
   const uint8_t* key_mask;   // [B, seq_k] or null
   const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
   int seq_q, seq_k, heads, causal;
+  int coff;                  // causal: key allowed iff key <= row + coff, coff = seq_k - seq_q (bottom-right aligned; prefix K/V)
   float scale;
   uint32_t drop_thresh;      // 0: no dropout; else round(p * 65536)
   float drop_scale;          // 1 / (1 - p)
@@ -284,7 +285,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   // tile 0 of the pair is the later (heavier when causal) query tile; tile 1 the one before it (absent if < 0)
   const int qt0 = ntq - 1 - 2 * (int)blockIdx.x;
   const int qts[2] = {qt0, qt0 - 1};
-  const int nblk[2] = {p.causal ? qt0 + 1 : nbk, qt0 - 1 < 0 ? 0 : (p.causal ? qt0 : nbk)};
+  // key blocks a query tile visits: all of them, or (causal) those holding a key <= its last row + coff
+  auto blocks_of = [&](int qt) { return p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk; };
+  const int nblk[2] = {blocks_of(qt0), qt0 - 1 < 0 ? 0 : blocks_of(qt0 - 1)};
   const int nbmax = nblk[0];
   const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
@@ -415,7 +418,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       float mx = -FLT_MAX;     // natural units (bias path)
       float raw_mx = -FLT_MAX; // unscaled (paths without bias)
       for (int j = 0; j < nb; ++j) {
-        const bool diag = p.causal && j == qt;
+        const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
         const uint32_t cSj = cS + (j & 1) * 256;
         mbar_wait(&bars[B::sfull + 2 * (j & 1) + t], (j >> 1) & 1);
         tc_fence_after();
@@ -430,10 +433,10 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             tmem_ld_wait();
             if (u == 0) tmem_ld_32x32(cSj + (c + 1) * 32, rb);
             else if (cc == 0) tmem_ld_32x32(cSj + 64, ra);
-            uint32_t m = kbits[4 * j + c];
-            if (diag) m &= low_bits(tid - c * 32 + 1);
-            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
             const int key0 = j * 128 + c * 32;
+            uint32_t m = kbits[4 * j + c];
+            if (diag) m &= low_bits(row + p.coff - key0 + 1);
+            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
             const float* bk = has_bias ? bias0 + min(key0, p.seq_k - 1) : nullptr;
             const int lim = max(p.seq_k - 1 - key0, 0);
             if (u == 0) max_chunk<kBias>(ra, m, full, bk, lim, scale, mx, raw_mx);
@@ -456,7 +459,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
       const int64_t dgroups = (p.seq_k + 7) >> 3;
       for (int j = 0; j < nb; ++j) {
-        const bool diag = p.causal && j == qt;
+        const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
         mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
         tc_fence_after();
         if (threadIdx.x == 0) TR(0, tri, 200 + j);
@@ -475,7 +478,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             else if (cc == 0) tmem_ld_32x32(cS + 64, ra);
             const int key0 = j * 128 + c * 32;
             uint32_t m = kbits[4 * j + c];
-            if (diag) m &= low_bits(tid - c * 32 + 1);
+            if (diag) m &= low_bits(row + p.coff - key0 + 1);
             if (none) m = low_bits(p.seq_k - key0);
             const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
             const bool empty = __all_sync(0xffffffffu, m == 0u);
@@ -598,7 +601,7 @@ __device__ __forceinline__ void softmax_grad_chunk(const AttnParams& p, uint32_t
 // attend word of chunk c of key block j for query row (tile qt, row_in_tile)
 __device__ __forceinline__ uint32_t row_word(const AttnParams& p, uint32_t kword, int j, int qt, int row_in_tile, int c, bool none) {
   uint32_t m = kword;
-  if (p.causal && j == qt) m &= low_bits(row_in_tile - c * 32 + 1);
+  if (p.causal) m &= low_bits(qt * 128 + row_in_tile + p.coff - (j * 128 + c * 32) + 1);
   if (none) m = low_bits(p.seq_k - (j * 128 + c * 32));   // uniform over the existing keys of the visited blocks
   return m;
 }
@@ -632,7 +635,7 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int rit = tid & 127, quarter = tid >> 7;          // row in tile, owned chunk
   const int r0 = qt * 128, row = r0 + rit;
   const bool row_ok = row < p.seq_q;
-  const int nblk = p.causal ? qt + 1 : nbk;
+  const int nblk = p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk;
   const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
@@ -766,7 +769,7 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x, lane = threadIdx.x & 31;
   const int rit = tid & 127, quarter = tid >> 7;
-  const int i0 = p.causal ? kb : 0;
+  const int i0 = p.causal ? max(0, (kb * 128 - p.coff) / 128) : 0;   // first query tile with a row that may see this key block
   const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
@@ -947,11 +950,12 @@ int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
   MMGL_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "%s: head_dim must be 64 or 128 (got %lld)", who, (long long)a->head_dim);
   MMGL_REQUIRE(a->batch < 65536 && a->heads < 65536, "%s: batch/heads too large for the grid", who);
   MMGL_REQUIRE(a->seq_k <= 8192 && a->seq_q <= (1 << 20), "%s: seq_k must be <= 8192", who);
-  MMGL_REQUIRE(!a->causal || a->seq_q == a->seq_k, "%s: causal needs seq_q == seq_k", who);
+  MMGL_REQUIRE(!a->causal || a->seq_q <= a->seq_k, "%s: causal needs seq_q <= seq_k (keys = prefix + the queries' own positions)", who);
   MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
   MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
   p.key_mask = a->key_mask; p.rel_bias = a->rel_bias;
   p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal;
+  p.coff = (int)(a->seq_k - a->seq_q);
   p.scale = a->scale;
   p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
   p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;

@@ -175,3 +175,34 @@ def test_rows_without_any_attended_key_are_uniform():
     rep = Report()
     rep.close("O", o, o_ref, 4e-3)
     rep.finish()
+
+
+@pytest.mark.parametrize("b,sq,prefix,heads,pad", [(2, 200, 20, 2, True), (1, 640, 20, 2, True), (2, 128, 128, 1, False),
+                                                   (1, 300, 7, 2, False)])
+def test_causal_attention_over_prefix_keys(b, sq, prefix, heads, pad):
+    """Causal attention whose keys are `prefix` virtual tokens followed by the queries' own positions (peft prefix
+    tuning, model/modelling_self_attention.py:88-92): key j is visible to query i iff j <= i + prefix."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(sq + prefix)
+    d = 64
+    h = heads * d
+    sk = sq + prefix
+    q, k, v = (randn(gen, b, n, h).to(BF16) for n in (sq, sk, sk))
+    d_o = randn(gen, b, sq, h).to(BF16)
+    key_mask = torch.ones(b, sk, dtype=torch.bool)
+    if pad:
+        key_mask[0, prefix + int(sq * 0.5):prefix + int(sq * 0.7)] = False
+    xs = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    o = ops.attention(*xs, key_mask=key_mask.cuda() if pad else None, heads=heads, causal=True, scale=d ** -0.5)
+    o.backward(d_o)
+    # dense additive mask of the bottom-right aligned causal pattern
+    allowed = (torch.arange(sk)[None, :] <= torch.arange(sq)[:, None] + prefix)
+    bias = torch.zeros(sq, sk).masked_fill(~allowed, torch.finfo(torch.float32).min)[None, None]
+    rs = [t.float().cpu().requires_grad_(True) for t in (q, k, v)]
+    o_ref = O.attention_core(*rs, heads, d ** -0.5, key_mask if pad else None, False, bias)
+    o_ref.backward(d_o.float().cpu())
+    rep = Report()
+    rep.close("O", o, o_ref, 4e-3)
+    for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
+        rep.close(name, x.grad, r.grad, 1e-2)
+    rep.finish()

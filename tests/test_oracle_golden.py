@@ -139,3 +139,26 @@ def test_lora_identity_at_init():
     b = torch.randn(16, 8, generator=gen)
     y = O.lora_linear(x, w, None, a, b, 2.0, 8)
     torch.testing.assert_close(y, x @ (w + (2.0 / 8) * b @ a).T, rtol=1e-5, atol=1e-5)
+
+
+def test_t5_relative_position_bias_matches_hf():
+    """The compact per-distance bias vector the attention kernel takes ([heads, Sq + Sk - 1]) and the oracle's dense
+    restatement both equal HF T5Attention.compute_bias (encoder: bidirectional buckets; decoder: causal buckets)."""
+    import types
+    from transformers import T5Config
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from mmgl_b200 import lm as L
+    torch.manual_seed(0)
+    for is_decoder in (False, True):
+        cfg = T5Config(d_model=64, d_kv=16, num_heads=4, is_decoder=is_decoder, relative_attention_num_buckets=32,
+                       relative_attention_max_distance=128)
+        attn = T5Attention(cfg, has_relative_attention_bias=True, layer_idx=0)
+        with torch.no_grad():
+            attn.relative_attention_bias.weight.normal_()
+        for sq, sk in ((7, 7), (130, 130), (40, 300)):
+            dense = attn.compute_bias(sq, sk)                                   # [1, nh, sq, sk]
+            vec = L.t5_rel_bias(attn, sq, sk)                                   # [nh, sq + sk - 1]
+            idx = torch.arange(sk)[None, :] - torch.arange(sq)[:, None] + sq - 1
+            assert torch.equal(vec[:, idx][None], dense.detach()), (is_decoder, sq, sk)
+            ref = O.t5_position_bias(attn.relative_attention_bias.weight.detach(), sq, sk, not is_decoder)
+            assert torch.equal(ref, dense.detach())
