@@ -20,7 +20,8 @@ modules' own fp32 forward / backward on the same weights.
 
 ``supports(lm)`` says whether a model can run here; SelfAttentionModel falls back to the HF forward (library code, as in
 the reference) when it cannot: head_dim not in {64, 128}, gated-GELU T5 variants, a TRAINABLE relative-position table
-(peft "none": the kernels treat the bias as a constant), LayerDrop, prefix tuning.
+(peft "none": the kernels treat the bias as a constant), LayerDrop.  Prefix tuning is implemented for OPT
+(``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions); T5 prefix tuning is not.
 """
 from __future__ import annotations
 
@@ -168,11 +169,17 @@ def _opt_supported(lm) -> bool:
             and float(cfg.attention_dropout) == 0.0 and float(getattr(cfg, "layerdrop", 0.0)) == 0.0)
 
 
-def opt_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None):
+def opt_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, prefix_kv=None):
     """OPTForCausalLM.forward for training: learned positions from the attention mask (HF opt :56-70), pre- or post-LN
     decoder layers (:202-254) with causal + key-padding attention, final LayerNorm, lm_head, shifted CE
     (ignore_index -100: the concat path pads the bank positions of the labels with -100,
-    model/modelling_self_attention.py:327-330)."""
+    model/modelling_self_attention.py:327-330).
+
+    ``prefix_kv`` [n_virtual, layers, 2, H] (peft prefix tuning, model/modelling_self_attention.py:88-92; semantics
+    restated from the published method -- peft is absent, parity unpinned): layer l attends over
+    keys = [prefix_kv[:, l, 0] ; k_proj(x)], values = [prefix_kv[:, l, 1] ; v_proj(x)]; the virtual tokens are always
+    visible (mask 1, before every query) and shift the learned positions of the real tokens by n_virtual, exactly as HF
+    does when it is handed them as past_key_values."""
     dec = lm.model.decoder
     cfg = lm.config
     p = cfg.dropout if lm.training else 0.0
@@ -182,19 +189,32 @@ def opt_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, lab
     if attention_mask is None:
         attention_mask = torch.ones(b, s, dtype=torch.long, device=inputs_embeds.device)
     am = attention_mask.long()
-    pos = dec.embed_positions(am)
+    n_pre = 0 if prefix_kv is None else prefix_kv.shape[0]
+    if n_pre:
+        full = torch.cat((torch.ones(b, n_pre, dtype=am.dtype, device=am.device), am), dim=1)
+        pos = dec.embed_positions(full)[:, n_pre:]            # positions continue after the virtual tokens
+    else:
+        full = am
+        pos = dec.embed_positions(am)
     if dec.project_in is not None:
         inputs_embeds = ops.linear(inputs_embeds, dec.project_in.weight)
     h = (inputs_embeds + pos.to(inputs_embeds.dtype)).to(BF16)
-    key_mask = (am != 0).to(torch.uint8).contiguous()
+    key_mask = (full != 0).to(torch.uint8).contiguous()
     heads = cfg.num_attention_heads
     scale = (cfg.hidden_size // heads) ** -0.5
-    for layer in dec.layers:
+    for li, layer in enumerate(dec.layers):
         a = layer.self_attn
         ln1, ln2 = layer.self_attn_layer_norm, layer.final_layer_norm
         x = ops.layer_norm(h, ln1.weight, ln1.bias, ln1.eps) if layer.do_layer_norm_before else h
-        qkv = torch.cat([_proj(a.q_proj, x), _proj(a.k_proj, x), _proj(a.v_proj, x)], dim=-1)
-        o = ops.self_attention(qkv, key_mask, heads, causal=True, scale=scale)
+        if n_pre:
+            pk = prefix_kv[:, li, 0].to(BF16)[None].expand(b, -1, -1)
+            pv = prefix_kv[:, li, 1].to(BF16)[None].expand(b, -1, -1)
+            k = torch.cat((pk, _proj(a.k_proj, x)), dim=1)
+            v = torch.cat((pv, _proj(a.v_proj, x)), dim=1)
+            o = ops.attention(_proj(a.q_proj, x), k, v, key_mask=key_mask, heads=heads, causal=True, scale=scale)
+        else:
+            qkv = torch.cat([_proj(a.q_proj, x), _proj(a.k_proj, x), _proj(a.v_proj, x)], dim=-1)
+            o = ops.self_attention(qkv, key_mask, heads, causal=True, scale=scale)
         h = ops.linear(o, a.out_proj.weight, a.out_proj.bias, residual=h, dropout_p=p)
         if not layer.do_layer_norm_before:
             h = ops.layer_norm(h, ln1.weight, ln1.bias, ln1.eps)

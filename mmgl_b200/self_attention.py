@@ -10,8 +10,8 @@ T5 relative-position bias or the OPT causal / padding mask, RMSNorm / LayerNorm,
 head dims other than 64 / 128, a trainable relative-position table under peft "none") fall back to the HF module's own
 forward, as in the reference (third-party code there as well).
 
-peft is not importable in this image and its source is absent, so LoRA / prompt tuning are restated from their
-published definitions (parity unpinned, see oracle/mmgl_oracle.py:lora_linear); module and state-dict names follow
+peft is not importable in this image and its source is absent, so LoRA / prompt / prefix tuning are restated from
+their published definitions (parity unpinned, see oracle/mmgl_oracle.py:lora_linear); module and state-dict names follow
 peft's layout (``lm.base_model.model.<path>.q.lora_A.default.weight`` ...) so reference checkpoints load.
 
 Reference defects not inherited: D3 (``session``/``session_all`` typos: the documented names
@@ -67,20 +67,37 @@ class _PeftHolder(nn.Module):
 class _PeftShim(nn.Module):
     """Gives the adapted LM peft's attribute / state-dict layout: ``lm.base_model.model.<hf path>``."""
 
-    def __init__(self, model, prompt_tokens: int = 0):
+    def __init__(self, model, prompt_tokens: int = 0, prefix_tokens: int = 0):
         super().__init__()
         self.base_model = _PeftHolder(model)
         self.use_kernel_lm = True
         self.num_virtual_tokens = prompt_tokens
+        self.num_prefix_tokens = prefix_tokens
         if prompt_tokens:
             dim = model.get_input_embeddings().embedding_dim
             self.prompt_encoder = nn.ModuleDict({"default": nn.ModuleDict({"embedding": nn.Embedding(prompt_tokens, dim)})})
+        if prefix_tokens:
+            # peft PrefixEncoder without projection: Embedding(num_virtual_tokens, num_layers * 2 * token_dim); row t holds,
+            # layer by layer, the key then the value of virtual token t (peft's view(.., layers * 2, heads, head_dim))
+            cfg = model.config
+            if cfg.is_encoder_decoder:
+                raise NotImplementedError("prefix tuning is implemented for decoder-only (OPT) language models")
+            self.prefix_layers, self.prefix_dim = cfg.num_hidden_layers, cfg.hidden_size
+            self.prompt_encoder = nn.ModuleDict({"default": nn.ModuleDict(
+                {"embedding": nn.Embedding(prefix_tokens, self.prefix_layers * 2 * self.prefix_dim)})})
 
     def get_input_embeddings(self):
         return self.base_model.model.get_input_embeddings()
 
     def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, **kw):
         lm = self.base_model.model
+        if self.num_prefix_tokens:    # prefix tuning: per-layer K / V of the virtual tokens in front of every layer's keys
+            if not lm_kernels.supports(lm):
+                raise NotImplementedError("prefix tuning needs a language model the package's kernels can run")
+            w = self.prompt_encoder["default"]["embedding"].weight
+            prefix = w.view(self.num_prefix_tokens, self.prefix_layers, 2, self.prefix_dim)
+            return lm_kernels.opt_forward(lm, input_ids=input_ids, attention_mask=attention_mask,
+                                          inputs_embeds=inputs_embeds, labels=labels, prefix_kv=prefix)
         if self.num_virtual_tokens:   # prompt tuning: learned embeddings prepended to the (encoder) input
             if inputs_embeds is None:
                 inputs_embeds = lm.get_input_embeddings()(input_ids)
@@ -159,8 +176,10 @@ class SelfAttentionModel(nn.Module, _NeighborEncoderMixin):
             for p in model.parameters():
                 p.requires_grad = False
             self.lm = _PeftShim(model, prompt_tokens=20)
-        elif args.peft_type == "prefix":
-            raise NotImplementedError("prefix tuning (per-layer KV prefixes inside the HF attention) is not implemented")
+        elif args.peft_type == "prefix":                   # :88-92 PrefixTuningConfig(num_virtual_tokens=20)
+            for p in model.parameters():
+                p.requires_grad = False
+            self.lm = _PeftShim(model, prefix_tokens=20)
         else:
             raise ValueError(f"SelfAttentionModel does not support {args.peft_type}.")
         self.input_embeddings = self.lm.get_input_embeddings()

@@ -188,3 +188,84 @@ def test_self_attention_model_runs_the_lm_on_the_package_kernels(lm):
     rep.scalar("loss (kernels vs HF forward)", a.loss, bref.loss, 0.0, 3e-2)
     rep.close("logits (kernels vs HF forward)", a.logits, bref.logits, 3e-2)
     rep.finish()
+
+
+def test_opt_prefix_tuning_matches_hf_past_key_values():
+    """Prefix tuning on OPT (peft PrefixTuningConfig, model/modelling_self_attention.py:88-92; peft absent -> semantics
+    restated): the per-layer virtual-token K / V are what HF's own forward consumes when handed as past_key_values, so
+    HF fp32 with a DynamicCache built from the same prefix table is the oracle -- loss, logits, d prefix, d inputs."""
+    from transformers import DynamicCache, OPTConfig, OPTForCausalLM
+    from mmgl_b200 import lm as L
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(4)
+    cfg = OPTConfig(vocab_size=384, hidden_size=128, num_hidden_layers=3, ffn_dim=256, num_attention_heads=2,
+                    max_position_embeddings=256, word_embed_proj_dim=128, dropout=0.0)
+    product = OPTForCausalLM(cfg)
+    reference = copy.deepcopy(product).float()
+    for m in (product, reference):
+        for p in m.parameters():
+            p.requires_grad = False
+    product.cuda().eval()
+    reference.cuda().eval()
+    n_pre, b, s, heads, d = 20, 2, 150, 2, 64
+    table = (torch.randn(n_pre, cfg.num_hidden_layers, 2, cfg.hidden_size, generator=gen) * 0.5).to(BF16).float().cuda()
+    emb = (torch.randn(b, s, cfg.hidden_size, generator=gen) * 0.5).cuda()
+    am = torch.ones(b, s, dtype=torch.long)
+    am[0, 100:118] = 0
+    am[1, 140:] = 0
+    labels = torch.randint(1, cfg.vocab_size, (b, s), generator=gen)
+    labels[:, 118:] = -100
+    am, labels = am.cuda(), labels.cuda()
+
+    w = table.clone().requires_grad_(True)
+    x = emb.to(BF16).requires_grad_(True)
+    out = L.opt_forward(product, inputs_embeds=x, attention_mask=am, labels=labels, prefix_kv=w)
+    out.loss.backward()
+
+    wr = table.clone().requires_grad_(True)
+    xr = emb.to(BF16).float().requires_grad_(True)
+    cache = DynamicCache(config=cfg)
+    for l in range(cfg.num_hidden_layers):
+        k = wr[:, l, 0].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
+        v = wr[:, l, 1].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
+        cache.update(k, v, l)
+    full = torch.cat((torch.ones(b, n_pre, dtype=am.dtype, device=am.device), am), dim=1)
+    ref_out = reference(inputs_embeds=xr, attention_mask=full, past_key_values=cache, labels=labels)
+    ref_out.loss.backward()
+    rep = Report()
+    rep.scalar("loss", out.loss, ref_out.loss, 0.0, 2e-2)
+    rep.close("logits", out.logits, ref_out.logits, 2e-2)
+    rep.close("d prefix table", w.grad, wr.grad, 6e-2)
+    rep.close("d inputs_embeds", x.grad, xr.grad, 6e-2)
+    rep.finish()
+
+
+def test_self_attention_model_prefix_tuning_trains():
+    from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig
+    from mmgl_b200 import synth
+    from mmgl_b200.self_attention import SelfAttentionModel
+    torch.manual_seed(0)
+    lm_cfg = OPTConfig(vocab_size=512, hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2,
+                       max_position_embeddings=512, word_embed_proj_dim=128, dropout=0.1)
+    txt = RobertaConfig(vocab_size=512, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                        intermediate_size=256, max_position_embeddings=80, pad_token_id=1)
+    vis = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                           image_size=32, patch_size=16)
+    args = types.SimpleNamespace(context="all", decoder_only=True, neighbor_mode="embedding", position_type="none",
+                                 n_text_tokens=2, n_visual_tokens=2, model_name_or_path=lm_cfg, peft_type="prefix",
+                                 text_model=txt, visual_model=vis, max_output_length=16, freeze_lm=False,
+                                 max_text_neighbors=3, max_image_neighbors=2, lora_r=8, lora_alpha=1, lora_dropout=0.0)
+    model = SelfAttentionModel(args, tokenizer=None).cuda().train()
+    keys = list(model.state_dict())
+    assert "lm.prompt_encoder.default.embedding.weight" in keys
+    assert tuple(model.lm.prompt_encoder["default"]["embedding"].weight.shape) == (20, 2 * 2 * 128)
+    spec = synth.BatchSpec(batch=2, max_input_length=48, max_output_length=16, text_neighbors=3, image_neighbors=2,
+                           vocab_size=512, neighbor_vocab_size=512, image_size=32, decoder_only=True)
+    batch = synth.to_device(synth.make_batch(spec, seed=3), torch.device("cuda"))
+    out = model(**batch)
+    out.loss.backward()
+    assert torch.isfinite(out.loss)
+    g = model.lm.prompt_encoder["default"]["embedding"].weight.grad
+    assert g is not None and float(g.abs().max()) > 0
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert all(n.startswith(("lm.prompt_encoder", "text_", "visual_")) for n in trainable), trainable
