@@ -338,8 +338,9 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps):
     _req_cuda(x, gamma, beta, y, mean, rstd)
     rows, hidden = x.shape
     assert x.is_contiguous() and y.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
-    _check(lib().mmgl_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, hidden, eps,
-                                    _stream()), "mmgl_layernorm_fwd")
+    with _Timed("layernorm_fwd", float(rows * hidden * 4)):
+        _check(lib().mmgl_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, hidden, eps,
+                                        _stream()), "mmgl_layernorm_fwd")
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -355,16 +356,18 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, d_res, dx, dgamma=None, dbeta=None, 
     if dgamma is not None or dbeta is not None:
         nbytes = lib().mmgl_layernorm_bwd_workspace_bytes(rows, hidden)
         ws = _workspace(nbytes, x.device)
-    _check(lib().mmgl_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(d_res), _p(dx), _p(dgamma),
-                                    _p(dbeta), int(accumulate), _p(ws), nbytes, rows, hidden, _stream()),
-           "mmgl_layernorm_bwd")
+    with _Timed("layernorm_bwd", float(rows * hidden * (8 if d_res is not None else 6))):
+        _check(lib().mmgl_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(d_res), _p(dx), _p(dgamma),
+                                        _p(dbeta), int(accumulate), _p(ws), nbytes, rows, hidden, _stream()),
+               "mmgl_layernorm_bwd")
 
 
 def rmsnorm_fwd(x, gamma, y, rstd, eps):
     _req_cuda(x, gamma, y, rstd)
     rows, hidden = x.shape
     assert x.is_contiguous() and y.is_contiguous() and gamma.dtype == torch.float32
-    _check(lib().mmgl_rmsnorm_fwd(_p(x), _p(gamma), _p(y), _p(rstd), rows, hidden, eps, _stream()), "mmgl_rmsnorm_fwd")
+    with _Timed("rmsnorm_fwd", float(rows * hidden * 4)):
+        _check(lib().mmgl_rmsnorm_fwd(_p(x), _p(gamma), _p(y), _p(rstd), rows, hidden, eps, _stream()), "mmgl_rmsnorm_fwd")
 
 
 def rmsnorm_bwd(dy, x, gamma, rstd, d_res, dx, dgamma=None, accumulate=False):
@@ -375,8 +378,9 @@ def rmsnorm_bwd(dy, x, gamma, rstd, d_res, dx, dgamma=None, accumulate=False):
     if dgamma is not None:
         nbytes = lib().mmgl_layernorm_bwd_workspace_bytes(rows, hidden)
         ws = _workspace(nbytes, x.device)
-    _check(lib().mmgl_rmsnorm_bwd(_p(dy), _p(x), _p(gamma), _p(rstd), _p(d_res), _p(dx), _p(dgamma), int(accumulate),
-                                  _p(ws), nbytes, rows, hidden, _stream()), "mmgl_rmsnorm_bwd")
+    with _Timed("rmsnorm_bwd", float(rows * hidden * 6)):
+        _check(lib().mmgl_rmsnorm_bwd(_p(dy), _p(x), _p(gamma), _p(rstd), _p(d_res), _p(dx), _p(dgamma), int(accumulate),
+                                      _p(ws), nbytes, rows, hidden, _stream()), "mmgl_rmsnorm_bwd")
 
 
 # ------------------------------------------------------------------------------------------- reductions
@@ -386,8 +390,9 @@ def colsum(x, out, scale=1.0, gate=None, accumulate=False):
     assert out.dtype == torch.float32 and out.numel() == n and x.dtype == torch.bfloat16
     nbytes = lib().mmgl_reduce_workspace_bytes(m, n)
     ws = _workspace(nbytes, x.device)
-    _check(lib().mmgl_colsum(_p(x), _ld(x), m, n, float(scale), _p(gate), _p(out), int(accumulate), _p(ws), nbytes,
-                             _stream()), "mmgl_colsum")
+    with _Timed("colsum", float(m * n * 2)):
+        _check(lib().mmgl_colsum(_p(x), _ld(x), m, n, float(scale), _p(gate), _p(out), int(accumulate), _p(ws), nbytes,
+                                 _stream()), "mmgl_colsum")
     return out
 
 
@@ -396,8 +401,9 @@ def gate_grad(dy, a, gate, out, accumulate=False):
     m, n = dy.shape
     nbytes = lib().mmgl_reduce_workspace_bytes(m, n)
     ws = _workspace(nbytes, dy.device)
-    _check(lib().mmgl_gate_grad(_p(dy), _ld(dy), _p(a), _ld(a), m, n, _p(gate), _p(out), int(accumulate), _p(ws),
-                                nbytes, _stream()), "mmgl_gate_grad")
+    with _Timed("gate_grad", float(m * n * 4)):
+        _check(lib().mmgl_gate_grad(_p(dy), _ld(dy), _p(a), _ld(a), m, n, _p(gate), _p(out), int(accumulate), _p(ws),
+                                    nbytes, _stream()), "mmgl_gate_grad")
     return out
 
 
@@ -405,8 +411,9 @@ def ce_fwd(logits, labels, lse, row_loss, loss, count, ignore_index=-100):
     _req_cuda(logits, labels, lse, row_loss, loss, count)
     rows, vocab = logits.shape
     assert logits.dtype == torch.bfloat16 and labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == rows
-    _check(lib().mmgl_ce_fwd(_p(logits), _ld(logits), _p(labels), rows, vocab, ignore_index, _p(lse), _p(row_loss), _p(loss),
-                             _p(count), _stream()), "mmgl_ce_fwd")
+    with _Timed("ce_fwd", float(rows * vocab * 2)):
+        _check(lib().mmgl_ce_fwd(_p(logits), _ld(logits), _p(labels), rows, vocab, ignore_index, _p(lse), _p(row_loss),
+                                 _p(loss), _p(count), _stream()), "mmgl_ce_fwd")
 
 
 def ce_bwd(logits, labels, lse, dloss, count, dlogits, ignore_index=-100):
@@ -421,8 +428,9 @@ def dropout_apply(x, out, p, seed):
     """out = keep ? x / (1-p) : 0 with the GEMM epilogue's mask for (seed, p); x, out bf16 2-D views."""
     _req_cuda(x, out)
     m, n = x.shape
-    _check(lib().mmgl_dropout_apply(_p(x), _ld(x), _p(out), _ld(out), m, n, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                    _stream()), "mmgl_dropout_apply")
+    with _Timed("dropout_apply", float(m * n * 4)):
+        _check(lib().mmgl_dropout_apply(_p(x), _ld(x), _p(out), _ld(out), m, n, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                        _stream()), "mmgl_dropout_apply")
     return out
 
 
