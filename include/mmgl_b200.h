@@ -137,6 +137,10 @@ typedef struct mmgl_attn_args {
   void* o; int64_t ldo; float* stats;
   int64_t batch; int64_t seq_q; int64_t seq_k; int64_t heads; int64_t head_dim;
   float scale; int32_t causal; float dropout_p; int32_t reserved; uint64_t dropout_seed;
+  /* Forward only (the frozen neighbor encoders, model/modelling_cross_attention.py:992): a packed variable-length batch.
+   * cu_seqlens int32 [batch + 1] (device): sample b is rows [cu[b], cu[b+1]) of q / k / v / o, which hold total_tokens
+   * rows; seq_q = seq_k = the longest sample; no key mask / bias / dropout; stats may be NULL.  NULL = uniform batch. */
+  const int32_t* cu_seqlens; int64_t total_tokens;
 } mmgl_attn_args;
 int mmgl_attn_fwd(const mmgl_attn_args* args, void* stream);
 /* o and stats in args are the forward outputs (read here).  workspace: caller-owned fp32 scratch of

@@ -70,6 +70,7 @@ class AttnArgs(C.Structure):
         ("o", c_vp), ("ldo", c_i64), ("stats", c_vp),
         ("batch", c_i64), ("seq_q", c_i64), ("seq_k", c_i64), ("heads", c_i64), ("head_dim", c_i64),
         ("scale", c_f32), ("causal", c_i32), ("dropout_p", c_f32), ("reserved", c_i32), ("dropout_seed", C.c_uint64),
+        ("cu_seqlens", c_vp), ("total_tokens", c_i64),
     ]
 
 
@@ -307,17 +308,22 @@ def _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads
 
 
 def attn_fwd(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal,
-             dropout_p=0.0, dropout_seed=0):
+             dropout_p=0.0, dropout_seed=0, cu_seqlens=None, total_tokens=0):
     """q, o: [B*seq_q, H] views; k, v: [B*seq_k, H] views; key_mask u8 [B,seq_k] or None; rel_bias fp32
     [heads, seq_q+seq_k-1] or None (bias of (row, key) = rel_bias[h][key - row + seq_q - 1])."""
-    _req_cuda(q, k, v, key_mask, rel_bias, o, stats)
+    _req_cuda(q, k, v, key_mask, rel_bias, o)
     assert rel_bias is None or (rel_bias.dtype == torch.float32 and rel_bias.is_contiguous()
                                 and tuple(rel_bias.shape) == (heads, seq_q + seq_k - 1))
     assert key_mask is None or (key_mask.dtype == torch.uint8 and key_mask.is_contiguous())
     h = heads * head_dim
     a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
                    dropout_seed)
-    with _Timed("sattn_fwd", float(batch * (seq_q + seq_k) * h * 2 * 2)):
+    if cu_seqlens is not None:      # packed variable-length batch (forward only)
+        _req_cuda(cu_seqlens)
+        assert cu_seqlens.dtype == torch.int32 and cu_seqlens.numel() == batch + 1 and cu_seqlens.is_contiguous()
+        a.cu_seqlens, a.total_tokens = _p(cu_seqlens), int(total_tokens)
+    nbytes = float((2 * total_tokens if cu_seqlens is not None else batch * (seq_q + seq_k)) * h * 2 * 2)
+    with _Timed("sattn_fwd", nbytes):
         _check(lib().mmgl_attn_fwd(C.byref(a), _stream()), "mmgl_attn_fwd")
 
 

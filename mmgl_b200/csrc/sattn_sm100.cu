@@ -57,6 +57,7 @@ struct AttnParams {
   const uint8_t* key_mask;   // [B, seq_k] or null
   const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
   int seq_q, seq_k, heads, causal;
+  const int32_t* cu_seqlens; // forward only, or null: sample b = packed rows [cu[b], cu[b+1]) (variable-length batch)
   int coff;                  // causal: key allowed iff key <= row + coff, coff = seq_k - seq_q (bottom-right aligned; prefix K/V)
   float scale;
   uint32_t drop_thresh;      // 0: no dropout; else round(p * 65536)
@@ -272,13 +273,22 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint8_t* sK = sQ + 2 * TB;             // NS stages
   uint8_t* sV = sK + NS * TB;            // NS stages
   uint8_t* sP = sV + NS * TB;            // 2 x [128][128] bf16 (2 slabs each)
-  const int nbk = (p.seq_k + 127) / 128;
+  const int nbk_max = (p.seq_k + 127) / 128;                       // layout: sized for the longest sample
   uint32_t* kbits = reinterpret_cast<uint32_t*>(sP + 2 * 32768);   // 4 * nbk words
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk + ((4 * nbk) & 1));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk_max + ((4 * nbk_max) & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + B::count);
 
-  const int ntq = (p.seq_q + 127) / 128;
   const int h = blockIdx.y, b = blockIdx.z;
+  // this sample's lengths and first rows: uniform batch, or a packed variable-length batch (cu_seqlens)
+  int sq = p.seq_q, sk = p.seq_k, rowq = b * p.seq_q, rowk = b * p.seq_k;
+  if (p.cu_seqlens != nullptr) {
+    const int c0 = p.cu_seqlens[b], c1 = p.cu_seqlens[b + 1];
+    sq = sk = c1 - c0;
+    rowq = rowk = c0;
+  }
+  const int nbk = (sk + 127) / 128;
+  const int ntq = (sq + 127) / 128;
+  if (ntq - 1 - 2 * (int)blockIdx.x < 0) return;   // a shorter sample has no such tile pair (whole CTA, before any barrier)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tri = 0; (void)tri;
   if (threadIdx.x == 0) TR(0, tri, 1);
@@ -289,7 +299,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   auto blocks_of = [&](int qt) { return p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk; };
   const int nblk[2] = {blocks_of(qt0), qt0 - 1 < 0 ? 0 : blocks_of(qt0 - 1)};
   const int nbmax = nblk[0];
-  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
+  const int colq = h * D;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -301,7 +311,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<512>(tmem_ptr);
-  build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
+  build_key_bits(kbits, p.key_mask, b, sk, 4 * nbk);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -412,7 +422,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const float scale = p.scale;
       constexpr bool has_bias = kBias;
       // bias of (row, key) = bias_row[key]  (bias_row points at the entry of key 0; negative offsets are valid memory)
-      const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+      const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (sq + sk - 1) + (sq - 1 - min(row, sq - 1)) : nullptr;
       const float* bias0 = has_bias ? bias_row : nullptr;
       // ---------------- pass 1: row maximum (S double-buffered in TMEM: block j lives at column offset (j & 1) * 256)
       float mx = -FLT_MAX;     // natural units (bias path)
@@ -437,8 +447,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             uint32_t m = kbits[4 * j + c];
             if (diag) m &= low_bits(row + p.coff - key0 + 1);
             const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
-            const float* bk = has_bias ? bias0 + min(key0, p.seq_k - 1) : nullptr;
-            const int lim = max(p.seq_k - 1 - key0, 0);
+            const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
+            const int lim = max(sk - 1 - key0, 0);
             if (u == 0) max_chunk<kBias>(ra, m, full, bk, lim, scale, mx, raw_mx);
             else max_chunk<kBias>(rb, m, full, bk, lim, scale, mx, raw_mx);
           }
@@ -456,8 +466,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       // ---------------- pass 2: P = exp(x - max), O += P V
       float sum = 0.f;
       const uint32_t p_base = smem_u32(sP + t * 32768);
-      const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
-      const int64_t dgroups = (p.seq_k + 7) >> 3;
+      const int64_t drow = ((int64_t)b * p.heads + h) * sq + row;
+      const int64_t dgroups = (sk + 7) >> 3;
       for (int j = 0; j < nb; ++j) {
         const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
         mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
@@ -479,11 +489,11 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int key0 = j * 128 + c * 32;
             uint32_t m = kbits[4 * j + c];
             if (diag) m &= low_bits(row + p.coff - key0 + 1);
-            if (none) m = low_bits(p.seq_k - key0);
+            if (none) m = low_bits(sk - key0);
             const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
             const bool empty = __all_sync(0xffffffffu, m == 0u);
-            const float* bk = has_bias ? bias0 + min(key0, p.seq_k - 1) : nullptr;
-            const int lim = max(p.seq_k - 1 - key0, 0);
+            const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
+            const int lim = max(sk - 1 - key0, 0);
             uint32_t(&rc)[32] = u == 0 ? ra : rb;
             sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
             if (kDrop) {
@@ -511,9 +521,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         uint32_t r[32];
         tmem_ld_32x32(cO + c * 32, r);
         tmem_ld_wait();
-        if (row < p.seq_q) store_row_bf16(o + ((int64_t)rowq + row) * ldo + colq + c * 32, r, inv);
+        if (row < sq) store_row_bf16(o + ((int64_t)rowq + row) * ldo + colq + c * 32, r, inv);
       }
-      if (row < p.seq_q)
+      if (row < sq && stats != nullptr)
         *reinterpret_cast<float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2) = make_float2(mx, inv);
     }
   }
@@ -878,9 +888,11 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 struct Maps { CUtensorMap q, k, v, d_o; };
 
 int build_maps(Maps& mp, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-               int64_t lddo, int64_t batch, int64_t seq_q, int64_t seq_k, int64_t heads, int d) {
+               int64_t lddo, int64_t batch, int64_t seq_q, int64_t seq_k, int64_t heads, int d, int64_t total_tokens = 0) {
   int rc;
-  const uint64_t cols = (uint64_t)(heads * d), rows_q = (uint64_t)(batch * seq_q), rows_k = (uint64_t)(batch * seq_k);
+  const uint64_t cols = (uint64_t)(heads * d);
+  const uint64_t rows_q = (uint64_t)(total_tokens > 0 ? total_tokens : batch * seq_q);
+  const uint64_t rows_k = (uint64_t)(total_tokens > 0 ? total_tokens : batch * seq_k);
   if ((rc = make_tensor_map_2d(&mp.q, q, cols, rows_q, (uint64_t)ldq, 64, 128))) return rc;
   if ((rc = make_tensor_map_2d(&mp.k, k, cols, rows_k, (uint64_t)ldk, 64, 128))) return rc;
   if ((rc = make_tensor_map_2d(&mp.v, v, cols, rows_k, (uint64_t)ldv, 64, 128))) return rc;
@@ -953,7 +965,7 @@ int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
   MMGL_REQUIRE(!a->causal || a->seq_q <= a->seq_k, "%s: causal needs seq_q <= seq_k (keys = prefix + the queries' own positions)", who);
   MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
   MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
-  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias;
+  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias; p.cu_seqlens = a->cu_seqlens;
   p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal;
   p.coff = (int)(a->seq_k - a->seq_q);
   p.scale = a->scale;
@@ -981,11 +993,15 @@ extern "C" int mmgl_attn_fwd(const mmgl_attn_args* a, void* stream_) {
   MMGL_BIND(a->q, "mmgl_attn_fwd");
   AttnParams p;
   if (int rc = fill_params("mmgl_attn_fwd", a, p)) return rc;
-  MMGL_REQUIRE(a->k && a->v && a->o && a->stats && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) &&
+  if (a->cu_seqlens != nullptr)
+    MMGL_REQUIRE(a->seq_q == a->seq_k && a->total_tokens > 0 && a->key_mask == nullptr && a->rel_bias == nullptr && a->dropout_p == 0.f,
+                 "mmgl_attn_fwd: cu_seqlens needs seq_q == seq_k (the longest sample), total_tokens, and no key mask / bias / dropout");
+  MMGL_REQUIRE(a->k && a->v && a->o && (a->stats || a->cu_seqlens) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) &&
                a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0,
                "mmgl_attn_fwd: pointers must be 16B aligned, leading dims %% 8 == 0");
   Maps mp;
-  if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, nullptr, 0, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim)) return rc;
+  if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, nullptr, 0, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim,
+                          a->cu_seqlens ? a->total_tokens : 0)) return rc;
   if (a->head_dim == 64) return launch_fwd<64>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
   return launch_fwd<128>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
 }
@@ -1002,6 +1018,7 @@ extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t l
   AttnParams p;
   if (int rc = fill_params("mmgl_attn_bwd", a, p)) return rc;
   MMGL_REQUIRE(d_o && a->k && a->v && a->o && a->stats && dq && dk && dv, "mmgl_attn_bwd: null pointer");
+  MMGL_REQUIRE(a->cu_seqlens == nullptr, "mmgl_attn_bwd: variable-length batches are forward-only (frozen encoders)");
   MMGL_REQUIRE(workspace != nullptr && workspace_bytes >= mmgl_attn_bwd_workspace_bytes(a->batch, a->seq_q, a->heads),
                "mmgl_attn_bwd: workspace too small (need mmgl_attn_bwd_workspace_bytes)");
   MMGL_REQUIRE(aligned16(d_o) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(dq) &&

@@ -76,3 +76,30 @@ def test_clip_vit_b16_shape_runs():
     rep = Report()
     rep.close("pooler_output", got, ref, 1.5e-2)
     rep.finish()
+
+
+def test_roberta_packing_changes_nothing():
+    """Dropping the padding positions (variable-length attention over the real tokens only) must give the same [CLS]
+    hidden states as running on the padded batch: padded keys are masked and padded queries are never consumed."""
+    from transformers import RobertaConfig, RobertaModel
+    from mmgl_b200 import encoders
+    torch.manual_seed(0)
+    cfg = RobertaConfig(vocab_size=512, hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256,
+                        max_position_embeddings=400, pad_token_id=1)
+    model = RobertaModel(cfg).cuda().eval()
+    gen = torch.Generator().manual_seed(1)
+    n, s = 9, 300
+    lens = torch.tensor([300, 17, 128, 129, 1, 255, 64, 200, 33])
+    am = (torch.arange(s)[None, :] < lens[:, None]).long()
+    ids = torch.where(am.bool(), torch.randint(4, 512, (n, s), generator=gen), torch.tensor(1))
+    a = encoders.roberta_cls_hidden(model, ids.cuda(), am.cuda(), pack_padding=True)
+    b = encoders.roberta_cls_hidden(model, ids.cuda(), am.cuda(), pack_padding=False)
+    ref = model(input_ids=ids.cuda(), attention_mask=am.cuda()).last_hidden_state[:, 0]
+    rep = Report()
+    rep.close("packed vs padded", a, b, 2e-3)
+    rep.close("packed vs HF fp32", a, ref, 1.5e-2)
+    rep.finish()
+    # a mask that is not prefix-form falls back to the padded path
+    am2 = am.clone(); am2[2, 5] = 0
+    c = encoders.roberta_cls_hidden(model, ids.cuda(), am2.cuda())
+    assert torch.isfinite(c.float()).all()
