@@ -57,6 +57,7 @@ struct AttnParams {
   const uint8_t* key_mask;   // [B, seq_k] or null
   const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
   int seq_q, seq_k, heads, causal;
+  int batch;                 // backward kernels: persistent CTAs walk (tile, head, sample) work items
   const int32_t* cu_seqlens; // forward only, or null: sample b = packed rows [cu[b], cu[b+1]) (variable-length batch)
   int coff;                  // causal: key allowed iff key <= row + coff, coff = seq_k - seq_q (bottom-right aligned; prefix K/V)
   float scale;
@@ -639,14 +640,8 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int ntq = (p.seq_q + 127) / 128;
-  const int qt = ntq - 1 - (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int rit = tid & 127, quarter = tid >> 7;          // row in tile, owned chunk
-  const int r0 = qt * 128, row = r0 + rit;
-  const bool row_ok = row < p.seq_q;
-  const int nblk = p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk;
-  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -654,99 +649,115 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
-  sDelta[quarter * 128 + rit] = row_ok ? delta_partial<D>(o, ldo, d_o, lddo, (int64_t)rowq + row, colq + quarter * (D / 4)) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdQ = 256;
-  uint32_t kvuse[2] = {0, 0}, aphase = 0, bphase = 0;
+  uint32_t kvuse[2] = {0, 0}, aphase = 0, bphase = 0, qphase = 0;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 2 * TB);
-    tma_tile<D>(sQ, &map_q, &bars[0], colq, rowq + r0);
-    tma_tile<D>(sdO, &map_do, &bars[0], colq, rowq + r0);
-    mbar_arrive_expect_tx(&bars[1], 2 * TB);
-    tma_tile<D>(sK, &map_k, &bars[1], colq, rowk);
-    tma_tile<D>(sV, &map_v, &bars[1], colq, rowk);
-  }
-  float m = 0.f, inv = 0.f;
-  const float delta = (sDelta[rit] + sDelta[128 + rit]) + (sDelta[256 + rit] + sDelta[384 + rit]);
-  if (row_ok) {
-    const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2);
-    m = st.x; inv = st.y;
-    if (quarter == 0) delta_ws[((int64_t)b * p.heads + h) * p.seq_q + row] = delta;
-  }
-  const bool none = !(m > -FLT_MAX);
-  const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
-  const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
+  // Persistent CTA: work items (query tile, head, sample), late (heavier when causal) tiles first, dealt round-robin so
+  // every CTA gets a mix; TMEM, barriers and the tensor-map fetch are paid once per CTA instead of once per tile.
+  const int hb = p.heads * p.batch;
+  const int n_items = ntq * hb;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int qt = ntq - 1 - item / hb;
+    const int h = (item % hb) % p.heads, b = (item % hb) / p.heads;
+    const int r0 = qt * 128, row = r0 + rit;
+    const bool row_ok = row < p.seq_q;
+    const int nblk = p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk;
+    const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
-  for (int j = 0; j < nblk; ++j) {
-    const int buf = (NB == 2) ? (j & 1) : 0;
-    if (tid == 0) {
-      if (NB == 2 && j + 1 < nblk) {
-        mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
-        tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
-        tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
-      }
-      if (j == 0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
-      tc_fence_after();
-      mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));           // S
-      mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
-      umma_commit(&bars[3]);
+    if (tid == 0) {   // nothing of the previous item is still reading these buffers (its last MMA was waited for)
+      mbar_arrive_expect_tx(&bars[0], 2 * TB);
+      tma_tile<D>(sQ, &map_q, &bars[0], colq, rowq + r0);
+      tma_tile<D>(sdO, &map_do, &bars[0], colq, rowq + r0);
+      mbar_arrive_expect_tx(&bars[1], 2 * TB);
+      tma_tile<D>(sK, &map_k, &bars[1], colq, rowk);
+      tma_tile<D>(sV, &map_v, &bars[1], colq, rowk);
     }
-    const uint32_t mw = row_word(p, kbits[4 * j + quarter], j, qt, rit, quarter, none);
-    __syncwarp();
-    mbar_wait(&bars[3], aphase & 1); aphase++;
-    tc_fence_after();
-    softmax_grad_chunk<false, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, j * 128 + quarter * 32, row_ok, m, inv,
-                                            delta, drow, 0, smem_u32(sdS), rit);
-    fence_proxy_async();
-    tc_fence_before();
+    build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
+    sDelta[quarter * 128 + rit] = row_ok ? delta_partial<D>(o, ldo, d_o, lddo, (int64_t)rowq + row, colq + quarter * (D / 4)) : 0.f;
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mma_pv<D>(tmem_base + cdQ, smem_u32(sdS), smem_u32(sK + buf * TB), j != 0);   // dQ += dS K_j
-      umma_commit(&bars[4]);
-      if (NB == 1 && j + 1 < nblk) {   // single buffer: reload K / V once this block's MMAs have drained
-        mbar_wait(&bars[4], bphase & 1);
-        mbar_arrive_expect_tx(&bars[1], 2 * TB);
-        tma_tile<D>(sK, &map_k, &bars[1], colq, rowk + (j + 1) * 128);
-        tma_tile<D>(sV, &map_v, &bars[1], colq, rowk + (j + 1) * 128);
-      }
-    }
-    __syncwarp();
-    mbar_wait(&bars[4], bphase & 1); bphase++;
-    tc_fence_after();
-  }
-  // dQ tile: quarter q stores columns [q * D/4, (q + 1) * D/4)
-  if (D == 64) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(lane_addr + cdQ + quarter * 16) : "memory");
-    tmem_ld_wait();
+    float m = 0.f, inv = 0.f;
+    const float delta = (sDelta[rit] + sDelta[128 + rit]) + (sDelta[256 + rit] + sDelta[384 + rit]);
     if (row_ok) {
-      __nv_bfloat16* dst = dq + ((int64_t)rowq + row) * lddq + colq + quarter * 16;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint4 v;
-        v.x = pack_bf16(__uint_as_float(r[8 * g]) * p.scale, __uint_as_float(r[8 * g + 1]) * p.scale);
-        v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * p.scale, __uint_as_float(r[8 * g + 3]) * p.scale);
-        v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * p.scale, __uint_as_float(r[8 * g + 5]) * p.scale);
-        v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * p.scale, __uint_as_float(r[8 * g + 7]) * p.scale);
-        *reinterpret_cast<uint4*>(dst + 8 * g) = v;
-      }
+      const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2);
+      m = st.x; inv = st.y;
+      if (quarter == 0) delta_ws[((int64_t)b * p.heads + h) * p.seq_q + row] = delta;
     }
-  } else {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + cdQ + quarter * 32, r);
-    tmem_ld_wait();
-    if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + quarter * 32, r, p.scale);
+    const bool none = !(m > -FLT_MAX);
+    const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
+    const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
+
+    for (int j = 0; j < nblk; ++j) {
+      const int buf = (NB == 2) ? (j & 1) : 0;
+      if (tid == 0) {
+        if (NB == 2 && j + 1 < nblk) {
+          mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
+          tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
+          tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
+        }
+        if (j == 0) { mbar_wait(&bars[0], qphase & 1); }
+        mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
+        tc_fence_after();
+        mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));           // S
+        mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
+        umma_commit(&bars[3]);
+      }
+      const uint32_t mw = row_word(p, kbits[4 * j + quarter], j, qt, rit, quarter, none);
+      __syncwarp();
+      mbar_wait(&bars[3], aphase & 1); aphase++;
+      tc_fence_after();
+      softmax_grad_chunk<false, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, j * 128 + quarter * 32, row_ok, m, inv,
+                                              delta, drow, 0, smem_u32(sdS), rit);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        mma_pv<D>(tmem_base + cdQ, smem_u32(sdS), smem_u32(sK + buf * TB), j != 0);   // dQ += dS K_j
+        umma_commit(&bars[4]);
+        if (NB == 1 && j + 1 < nblk) {   // single buffer: reload K / V once this block's MMAs have drained
+          mbar_wait(&bars[4], bphase & 1);
+          mbar_arrive_expect_tx(&bars[1], 2 * TB);
+          tma_tile<D>(sK, &map_k, &bars[1], colq, rowk + (j + 1) * 128);
+          tma_tile<D>(sV, &map_v, &bars[1], colq, rowk + (j + 1) * 128);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&bars[4], bphase & 1); bphase++;
+      tc_fence_after();
+    }
+    qphase++;
+    // dQ tile: quarter q stores columns [q * D/4, (q + 1) * D/4)
+    if (D == 64) {
+      uint32_t r[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                     "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(lane_addr + cdQ + quarter * 16) : "memory");
+      tmem_ld_wait();
+      if (row_ok) {
+        __nv_bfloat16* dst = dq + ((int64_t)rowq + row) * lddq + colq + quarter * 16;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[8 * g]) * p.scale, __uint_as_float(r[8 * g + 1]) * p.scale);
+          v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * p.scale, __uint_as_float(r[8 * g + 3]) * p.scale);
+          v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * p.scale, __uint_as_float(r[8 * g + 5]) * p.scale);
+          v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * p.scale, __uint_as_float(r[8 * g + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(dst + 8 * g) = v;
+        }
+      }
+    } else {
+      uint32_t r[32];
+      tmem_ld_32x32(lane_addr + cdQ + quarter * 32, r);
+      tmem_ld_wait();
+      if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + quarter * 32, r, p.scale);
+    }
+    tc_fence_before();   // the next item's S / dP / dQ MMAs overwrite TMEM this item's threads have just read
   }
   tc_fence_before();
   __syncthreads();
@@ -775,12 +786,9 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int ntq = (p.seq_q + 127) / 128;
-  const int kb = blockIdx.x;   // key block; early key blocks see the most query tiles and come first
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int nbk = (p.seq_k + 127) / 128;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x, lane = threadIdx.x & 31;
   const int rit = tid & 127, quarter = tid >> 7;
-  const int i0 = p.causal ? max(0, (kb * 128 - p.coff) / 128) : 0;   // first query tile with a row that may see this key block
-  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
 
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -788,21 +796,23 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  if (tid < 128) {
-    const int key = kb * 128 + tid;
-    const bool a = key < p.seq_k && (p.key_mask == nullptr || p.key_mask[(int64_t)b * p.seq_k + key] != 0);
-    const uint32_t bits = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) kbits4[warp] = bits;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdV = 256, cdK = 256 + D;
-  uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0;
-  const uint32_t kword = kbits4[quarter];
+  uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0, kphase = 0;
 
+  // Persistent CTA over work items (key block, head, sample); early key blocks (seen by the most query tiles when
+  // causal) first, dealt round-robin.
+  const int hb = p.heads * p.batch;
+  const int n_items = nbk * hb;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int kb = item / hb;
+  const int h = (item % hb) % p.heads, b = (item % hb) / p.heads;
+  const int i0 = p.causal ? max(0, (kb * 128 - p.coff) / 128) : 0;   // first query tile with a row that may see this key block
+  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], 2 * TB);
     tma_tile<D>(sK, &map_k, &bars[0], colq, rowk + kb * 128);
@@ -811,6 +821,14 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tma_tile<D>(sQ, &map_q, &bars[1], colq, rowq + i0 * 128);
     tma_tile<D>(sdO, &map_do, &bars[1], colq, rowq + i0 * 128);
   }
+  if (tid < 128) {
+    const int key = kb * 128 + tid;
+    const bool a = key < p.seq_k && (p.key_mask == nullptr || p.key_mask[(int64_t)b * p.seq_k + key] != 0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) kbits4[warp] = bits;
+  }
+  __syncthreads();
+  const uint32_t kword = kbits4[quarter];
   for (int i = i0; i < ntq; ++i) {
     const int it = i - i0;
     const int buf = (NB == 2) ? (it & 1) : 0;
@@ -829,7 +847,7 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tma_tile<D>(sQ + (buf ^ 1) * TB, &map_q, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
         tma_tile<D>(sdO + (buf ^ 1) * TB, &map_do, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
       }
-      if (it == 0) mbar_wait(&bars[0], 0);
+      if (it == 0) mbar_wait(&bars[0], kphase & 1);
       mbar_wait(&bars[1 + buf], quse[buf] & 1); quse[buf]++;
       tc_fence_after();
       mma_qk<D>(tmem_base, smem_u32(sQ + buf * TB), smem_u32(sK));          // S  = Q_i K_j^T
@@ -879,6 +897,9 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_wait();
       if (key < p.seq_k) store_row_bf16(dst + c * 32, r, mul);
     }
+  }
+  kphase++;
+  tc_fence_before();   // the next item's MMAs overwrite TMEM this item's threads have just read
   }
   tc_fence_before();
   __syncthreads();
@@ -930,7 +951,8 @@ int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo
     const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 2048 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
     auto kern = sattn_bwd_dq_kernel<D, kBias, kDrop>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.seq_q + 127) / 128), (unsigned)p.heads, (unsigned)batch);
+    const int64_t items = (int64_t)((p.seq_q + 127) / 128) * p.heads * batch;
+    dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
     kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
                                       (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq, delta_ws);
     if (int rc = check_launch("mmgl_attn_bwd(dq)")) return rc;
@@ -939,7 +961,8 @@ int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo
     const size_t smem = (2 + 2 * NB) * (size_t)TB + 65536 + 16 + 5 * 8 + 16;
     auto kern = sattn_bwd_dkv_kernel<D, kBias, kDrop>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.seq_k + 127) / 128), (unsigned)p.heads, (unsigned)batch);
+    const int64_t items = (int64_t)((p.seq_k + 127) / 128) * p.heads * batch;
+    dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
     kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, stats, delta_ws, (__nv_bfloat16*)dk, lddk,
                                       (__nv_bfloat16*)dv, lddv);
     return check_launch("mmgl_attn_bwd(dkv)");
@@ -960,13 +983,14 @@ int launch_bwd(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, 
 int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
   MMGL_REQUIRE(a->batch > 0 && a->seq_q > 0 && a->seq_k > 0 && a->heads > 0, "%s: empty problem", who);
   MMGL_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "%s: head_dim must be 64 or 128 (got %lld)", who, (long long)a->head_dim);
-  MMGL_REQUIRE(a->batch < 65536 && a->heads < 65536, "%s: batch/heads too large for the grid", who);
+  MMGL_REQUIRE(a->batch < 65536 && a->heads < 65536 && a->batch * a->heads * ((a->seq_q + a->seq_k) / 128 + 2) < (1ll << 31),
+               "%s: batch/heads too large for the grid", who);
   MMGL_REQUIRE(a->seq_k <= 8192 && a->seq_q <= (1 << 20), "%s: seq_k must be <= 8192", who);
   MMGL_REQUIRE(!a->causal || a->seq_q <= a->seq_k, "%s: causal needs seq_q <= seq_k (keys = prefix + the queries' own positions)", who);
   MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
   MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
   p.key_mask = a->key_mask; p.rel_bias = a->rel_bias; p.cu_seqlens = a->cu_seqlens;
-  p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal;
+  p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal; p.batch = (int)a->batch;
   p.coff = (int)(a->seq_k - a->seq_q);
   p.scale = a->scale;
   p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
