@@ -167,6 +167,22 @@ __device__ __forceinline__ void mma_pv_desc(uint32_t tmem, uint64_t da0, uint64_
   for (int k = 0; k < 8; ++k)
     umma_f16_ss(tmem, da0 + kslab_off(k), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
 }
+// half-block (64 keys) forms for the double-buffered pass 2 of the forward kernel:
+//   S[128 x 64] = Q[128 x D] * Khalf[64 x D]^T          (db0 = descriptor of the half's first key row)
+//   O[128 x D] (+)= P[128 x 64] * Vhalf[64 x D]          (da0 = P slab, db0 = descriptor of the half's first V row, MN-major)
+template <int D>
+__device__ __forceinline__ void mma_qk_half(uint32_t tmem, uint64_t da0, uint64_t db0) {
+  const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+  for (int k = 0; k < D / 16; ++k) umma_f16_ss(tmem, da0 + kslab_off(k), db0 + kslab_off(k), idesc, k != 0 ? 1u : 0u);
+}
+template <int D>
+__device__ __forceinline__ void mma_pv_half(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_f16_ss(tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
+}
 template <int D>
 __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0) {
 #pragma unroll
@@ -256,9 +272,9 @@ template <int NS> struct FwdBars {
   static constexpr int vfree = 2 + 3 * NS;   // [NS]
   static constexpr int sfull = 2 + 4 * NS;   // [2 buffers][2 tiles]  S_t = Q_t K_j^T complete in TMEM buffer (index 2 * buf + t)
   static constexpr int sfree = 6 + 4 * NS;   // [2 buffers][2 tiles]  pass 1: tile t's 128 threads have read that S buffer
-  static constexpr int pfull = 10 + 4 * NS;  // [2]  pass 2: tile t's P block is in shared memory (128 arrivals)
-  static constexpr int pfree = 12 + 4 * NS;  // [2]  P_t V_j complete: P buffer reusable, O_t updated
-  static constexpr int count = 14 + 4 * NS;
+  static constexpr int pfull = 10 + 4 * NS;  // [2 buffers][2 tiles]  pass 2: tile t's P half-block is in shared memory (128 arrivals)
+  static constexpr int pfree = 14 + 4 * NS;  // [2 buffers][2 tiles]  P V of that half-block complete: P buffer reusable, O_t updated
+  static constexpr int count = 18 + 4 * NS;
 };
 
 template <int D, bool kBias, bool kDrop>
@@ -305,7 +321,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < B::count; ++i) {
-      const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 2);
+      const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 4);
       const bool two = (i >= B::kfree && i < B::kfree + NS) || (i >= B::vfree && i < B::vfree + NS);
       mbar_init(&bars[i], wide ? 128 : (two ? 2 : 1));
     }
@@ -377,36 +393,43 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       for (int tt = 0; tt < 2; ++tt)
         for (int jj = max(nblk[tt] - 2, 0); jj < nblk[tt]; ++jj)
           mbar_wait(&bars[B::sfree + 2 * (jj & 1) + tt], (jj >> 1) & 1);
+      // Pass 2 works on HALF blocks (64 keys) with two S buffers and two P buffers per tile: sub-block jj = half (jj & 1) of
+      // key block jj >> 1 lives in buffer jj & 1.  S(jj + 2) is issued right after P V(jj), so the softmax warps find the next
+      // scores ready when they finish a half block and never wait for the P V + Q K^T pair.
+      const uint32_t cS2[2] = {cS, cS + 64};
+      const uint64_t dp2[2] = {dp, dp + (uint64_t)(16384 >> 4)};
+      const int nsub = 2 * nb;
       {
         const int n = nbmax, s = n % NS;
         if (t == 0) TR(2, tri, 198);
         mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
         tc_fence_after();
-        mma_qk_desc<D>(cS, dq, dk0 + (uint64_t)((s * TB) >> 4));
-        umma_commit(&bars[B::sfull + t]);
+        const uint64_t dk = dk0 + (uint64_t)((s * TB) >> 4);
+        mma_qk_half<D>(cS2[0], dq, dk);
+        umma_commit(&bars[B::sfull + 0 + t]);
+        mma_qk_half<D>(cS2[1], dq, dk + (uint64_t)(8192 >> 4));
+        umma_commit(&bars[B::sfull + 2 + t]);
         release(&bars[B::kfree + s], 0);
         if (t == 0) TR(2, tri, 199);
       }
-      // pass 2: O_t += P_t(j) V_j followed at once by S_t(j + 1), so tile t's warps wait for two MMAs only
-      for (int j = 0; j < nb; ++j) {
-        const int sv = j % NS;
-        mbar_wait(&bars[B::pfull + t], j & 1);
-        if (t == 0) TR(2, tri, 200 + j);
-        mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
+      for (int jj = 0; jj < nsub; ++jj) {
+        const int u = jj & 1, j = jj >> 1, sv = j % NS;
+        mbar_wait(&bars[B::pfull + 2 * u + t], (jj >> 1) & 1);
+        if (t == 0) TR(2, tri, 200 + jj);
+        if (u == 0) mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
         tc_fence_after();
-        if (t == 0) TR(2, tri, 250 + j);
-        mma_pv_desc<D>(cO, dp, dv0 + (uint64_t)((sv * TB) >> 4), j != 0);
-        umma_commit(&bars[B::pfree + t]);
-        release(&bars[B::vfree + sv], j);
-        if (j + 1 < nb) {
+        mma_pv_half<D>(cO, dp2[u], dv0 + (uint64_t)((sv * TB + u * 8192) >> 4), jj != 0);
+        umma_commit(&bars[B::pfree + 2 * u + t]);
+        if (u == 1) release(&bars[B::vfree + sv], j);
+        if (jj + 2 < nsub) {                                  // S of the same half of the NEXT key block, into the buffer just freed
           const int n = nbmax + j + 1, s = n % NS;
-          mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
+          if (u == 0) mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
           tc_fence_after();
-          mma_qk_desc<D>(cS, dq, dk0 + (uint64_t)((s * TB) >> 4));
-          umma_commit(&bars[B::sfull + t]);
-          release(&bars[B::kfree + s], j + 1);
+          mma_qk_half<D>(cS2[u], dq, dk0 + (uint64_t)((s * TB + u * 8192) >> 4));
+          umma_commit(&bars[B::sfull + 2 * u + t]);
+          if (u == 1) release(&bars[B::kfree + s], j + 1);
         }
-        if (t == 0) TR(2, tri, 300 + j);
+        if (t == 0) TR(2, tri, 300 + jj);
       }
     }
     __syncwarp();
@@ -458,62 +481,62 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         mbar_arrive(&bars[B::sfree + 2 * (j & 1) + t]);
         if (threadIdx.x == 0) TR(0, tri, 150 + j);
       }
-      uint32_t sphase = (nb + 1) >> 1;   // pass 2 reuses S buffer 0: its barrier has completed ceil(nb / 2) phases
       if (raw_mx > -FLT_MAX) mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
       // A row with no attended key at all (mx == -FLT_MAX): the reference's clamp makes every existing key's score
       // finfo.min, i.e. uniform attention -> p = 1 on the existing keys of the visited blocks.
       const bool none = !(mx > -FLT_MAX);
       const float c1 = none ? 0.f : scale * kL2E, mxc = none ? 0.f : mx * kL2E, bsc = none ? 0.f : kL2E;
-      // ---------------- pass 2: P = exp(x - max), O += P V
+      // ---------------- pass 2: P = exp(x - max), O += P V, on half blocks (64 keys = chunks 2u, 2u+1 of key block jj >> 1) with
+      // double-buffered S (TMEM) and P (shared memory): while this warpgroup exponentiates half block jj, the tensor core
+      // already holds S(jj + 1) and is free to run P V(jj - 1) and S(jj + 2).
       float sum = 0.f;
       const uint32_t p_base = smem_u32(sP + t * 32768);
       const int64_t drow = ((int64_t)b * p.heads + h) * sq + row;
       const int64_t dgroups = (sk + 7) >> 3;
-      for (int j = 0; j < nb; ++j) {
+      // pass 1 completed ceil(nb / 2) phases on the buffer-0 barrier and floor(nb / 2) on the buffer-1 barrier
+      const uint32_t sbase[2] = {(uint32_t)((nb + 1) >> 1), (uint32_t)(nb >> 1)};
+      const int nsub = 2 * nb;
+      for (int jj = 0; jj < nsub; ++jj) {
+        const int u = jj & 1, j = jj >> 1;
         const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
-        mbar_wait(&bars[B::sfull + t], sphase & 1); sphase++;
+        const uint32_t cSu = cS + u * 64;
+        mbar_wait(&bars[B::sfull + 2 * u + t], (sbase[u] + (uint32_t)(jj >> 1)) & 1);
         tc_fence_after();
-        if (threadIdx.x == 0) TR(0, tri, 200 + j);
-        if (threadIdx.x == 96) TR(1, tri, 200 + j);
+        if (threadIdx.x == 0) TR(0, tri, 200 + jj);
         uint32_t ra[32], rb[32];
-        tmem_ld_32x32(cS, ra);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_32x32(cSu, ra);
+        tmem_ld_32x32(cSu + 32, rb);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = 2 * cc + u;
-            if (threadIdx.x == 0) TR(0, tri, 1000 + 10 * j + c);
-            tmem_ld_wait();
-            if (threadIdx.x == 0) TR(0, tri, 2000 + 10 * j + c);
-            if (u == 0) tmem_ld_32x32(cS + (c + 1) * 32, rb);
-            else if (cc == 0) tmem_ld_32x32(cS + 64, ra);
-            const int key0 = j * 128 + c * 32;
-            uint32_t m = kbits[4 * j + c];
-            if (diag) m &= low_bits(row + p.coff - key0 + 1);
-            if (none) m = low_bits(sk - key0);
-            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
-            const bool empty = __all_sync(0xffffffffu, m == 0u);
-            const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
-            const int lim = max(sk - 1 - key0, 0);
-            uint32_t(&rc)[32] = u == 0 ? ra : rb;
-            sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
-            if (kDrop) {
-              const uint32_t keep = keep_word(p, drow, key0, dgroups);
+        for (int w = 0; w < 2; ++w) {
+          const int c = 2 * u + w;                       // 32-key chunk of the 128-key block
+          const int key0 = j * 128 + c * 32;
+          uint32_t m = kbits[4 * j + c];
+          if (diag) m &= low_bits(row + p.coff - key0 + 1);
+          if (none) m = low_bits(sk - key0);
+          const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
+          const bool empty = __all_sync(0xffffffffu, m == 0u);
+          const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
+          const int lim = max(sk - 1 - key0, 0);
+          if (w == 0) tmem_ld_wait();                    // both chunk loads were issued together
+          uint32_t(&rc)[32] = w == 0 ? ra : rb;
+          sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
+          if (kDrop) {
+            const uint32_t keep = keep_word(p, drow, key0, dgroups);
 #pragma unroll
-              for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
-            }
-            if (c == 0 && j > 0) mbar_wait(&bars[B::pfree + t], (j - 1) & 1);   // P_t(j-1) V done: buffer reusable
-            store_chunk_bf16(p_base, tid, c, rc);
-            if (threadIdx.x == 0) TR(0, tri, 3000 + 10 * j + c);
+            for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
           }
+          if (w == 0 && jj >= 2) mbar_wait(&bars[B::pfree + 2 * u + t], ((jj >> 1) - 1) & 1);   // P V(jj - 2) done: buffer reusable
+          // P buffer u is one 64-column slab; chunk w fills its 16-byte columns 4w .. 4w+3
+          store_chunk_bf16(p_base + u * 16384, tid, w, rc);
         }
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&bars[B::pfull + t]);
-        if (threadIdx.x == 0) TR(0, tri, 250 + j);
-        if (threadIdx.x == 96) TR(1, tri, 250 + j);
+        mbar_arrive(&bars[B::pfull + 2 * u + t]);
+        if (threadIdx.x == 0) TR(0, tri, 250 + jj);
       }
-      mbar_wait(&bars[B::pfree + t], (nb - 1) & 1);   // all of O_t accumulated
+      // all of O_t accumulated: the last P V of each buffer (completion is in issue order, so buffer 1's last implies all)
+      mbar_wait(&bars[B::pfree + 0 + t], ((nsub - 2) >> 1) & 1);
+      mbar_wait(&bars[B::pfree + 2 + t], ((nsub - 1) >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) TR(0, tri, 900);
       const float inv = 1.f / sum;
