@@ -278,7 +278,7 @@ template <int NS> struct FwdBars {
 };
 
 template <int D, bool kBias, bool kDrop>
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__(608, 1)
 sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p,
                  __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats) {
@@ -294,6 +294,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint32_t* kbits = reinterpret_cast<uint32_t*>(sP + 2 * 32768);   // 4 * nbk words
   uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk_max + ((4 * nbk_max) & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + B::count);
+  float* xch = reinterpret_cast<float*>(tmem_ptr + 4);   // [2 tiles][2 column halves][128 rows]: row max, then row sum
 
   const int h = blockIdx.y, b = blockIdx.z;
   // this sample's lengths and first rows: uniform batch, or a packed variable-length batch (cu_seqlens)
@@ -323,11 +324,11 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     for (int i = 0; i < B::count; ++i) {
       const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 4);
       const bool two = (i >= B::kfree && i < B::kfree + NS) || (i >= B::vfree && i < B::vfree + NS);
-      mbar_init(&bars[i], wide ? 128 : (two ? 2 : 1));
+      mbar_init(&bars[i], wide ? 256 : (two ? 2 : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_ptr);
+  if (warp == 16) tmem_alloc<512>(tmem_ptr);
   build_key_bits(kbits, p.key_mask, b, sk, 4 * nbk);
   tc_fence_before();
   __syncthreads();
@@ -335,7 +336,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) TR(0, tri, 2);
 
-  if (warp == 10) {
+  if (warp == 18) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int t = 0; t < 2; ++t)
@@ -358,9 +359,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ MMA issuers: warp 8 -> tile 0, warp 9 -> tile 1
-    const int t = warp - 8;
+  } else if (warp >= 16) {
+    // ------------------------------------------------------------------ MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1
+    const int t = warp - 16;
     const int nb = nblk[t];
     if (lane == 0 && nb > 0) {
       const uint64_t dq = make_smem_desc(smem_u32(sQ + t * TB), 16, 1024);
@@ -434,12 +435,15 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax warps: tile t = warp / 4
-    const int t = warp >> 2;
+    // ------------------------------------------------------------------ softmax warps: TWO threads per score row.
+    // warp w: tile t = (w / 4) & 1, column half hf = w / 8, TMEM lane quarter w & 3; thread (row, hf) owns the 32-key chunks
+    // 2 hf, 2 hf + 1 of every 128-key block in pass 1 and chunk hf of every 64-key half block in pass 2, so four warps per
+    // scheduler hide each other's TMEM / MUFU latency.  Row max and row sum of the two halves meet in shared memory.
+    const int t = (warp >> 2) & 1, hf = warp >> 3;
     const int nb = nblk[t];
     if (nb > 0) {
       const int qt = qts[t];
-      const int tid = threadIdx.x & 127;
+      const int tid = ((warp & 3) << 5) | lane;           // row in tile
       const int row = qt * 128 + tid;
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       const uint32_t cS = lane_addr + t * 128, cO = lane_addr + 256 + t * D;
@@ -448,47 +452,49 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       // bias of (row, key) = bias_row[key]  (bias_row points at the entry of key 0; negative offsets are valid memory)
       const float* bias_row = has_bias ? p.rel_bias + (int64_t)h * (sq + sk - 1) + (sq - 1 - min(row, sq - 1)) : nullptr;
       const float* bias0 = has_bias ? bias_row : nullptr;
+      float* xrow = xch + (t * 2) * 128 + tid;            // [hf * 128] apart
       // ---------------- pass 1: row maximum (S double-buffered in TMEM: block j lives at column offset (j & 1) * 256)
       float mx = -FLT_MAX;     // natural units (bias path)
       float raw_mx = -FLT_MAX; // unscaled (paths without bias)
       for (int j = 0; j < nb; ++j) {
         const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
-        const uint32_t cSj = cS + (j & 1) * 256;
+        const uint32_t cSj = cS + (j & 1) * 256 + hf * 64;
         mbar_wait(&bars[B::sfull + 2 * (j & 1) + t], (j >> 1) & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TR(0, tri, 100 + j);
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(cSj, ra);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_32x32(cSj + 32, rb);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = 2 * cc + u;
-            tmem_ld_wait();
-            if (u == 0) tmem_ld_32x32(cSj + (c + 1) * 32, rb);
-            else if (cc == 0) tmem_ld_32x32(cSj + 64, ra);
-            const int key0 = j * 128 + c * 32;
-            uint32_t m = kbits[4 * j + c];
-            if (diag) m &= low_bits(row + p.coff - key0 + 1);
-            const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
-            const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
-            const int lim = max(sk - 1 - key0, 0);
-            if (u == 0) max_chunk<kBias>(ra, m, full, bk, lim, scale, mx, raw_mx);
-            else max_chunk<kBias>(rb, m, full, bk, lim, scale, mx, raw_mx);
-          }
+        for (int w = 0; w < 2; ++w) {
+          const int c = 2 * hf + w;
+          const int key0 = j * 128 + c * 32;
+          uint32_t m = kbits[4 * j + c];
+          if (diag) m &= low_bits(row + p.coff - key0 + 1);
+          const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
+          const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
+          const int lim = max(sk - 1 - key0, 0);
+          if (w == 0) tmem_ld_wait();
+          if (w == 0) max_chunk<kBias>(ra, m, full, bk, lim, scale, mx, raw_mx);
+          else max_chunk<kBias>(rb, m, full, bk, lim, scale, mx, raw_mx);
         }
         tc_fence_before();
         mbar_arrive(&bars[B::sfree + 2 * (j & 1) + t]);
         if (threadIdx.x == 0) TR(0, tri, 150 + j);
       }
       if (raw_mx > -FLT_MAX) mx = fmaxf(mx, fmaxf(raw_mx * scale, -FLT_MAX));   // scale > 0
+      // the two column halves of a row exchange their maxima (named barrier per tile: 256 threads)
+      xrow[hf * 128] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      mx = fmaxf(mx, xrow[(hf ^ 1) * 128]);
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // both read before the sums overwrite the slots
       // A row with no attended key at all (mx == -FLT_MAX): the reference's clamp makes every existing key's score
       // finfo.min, i.e. uniform attention -> p = 1 on the existing keys of the visited blocks.
       const bool none = !(mx > -FLT_MAX);
       const float c1 = none ? 0.f : scale * kL2E, mxc = none ? 0.f : mx * kL2E, bsc = none ? 0.f : kL2E;
       // ---------------- pass 2: P = exp(x - max), O += P V, on half blocks (64 keys = chunks 2u, 2u+1 of key block jj >> 1) with
-      // double-buffered S (TMEM) and P (shared memory): while this warpgroup exponentiates half block jj, the tensor core
-      // already holds S(jj + 1) and is free to run P V(jj - 1) and S(jj + 2).
+      // double-buffered S (TMEM) and P (shared memory): while this tile's warps exponentiate half block jj, the tensor core
+      // already holds S(jj + 1) and is free to run P V(jj - 1) and S(jj + 2).  This thread owns chunk 2u + hf.
       float sum = 0.f;
       const uint32_t p_base = smem_u32(sP + t * 32768);
       const int64_t drow = ((int64_t)b * p.heads + h) * sq + row;
@@ -499,62 +505,61 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       for (int jj = 0; jj < nsub; ++jj) {
         const int u = jj & 1, j = jj >> 1;
         const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
-        const uint32_t cSu = cS + u * 64;
         mbar_wait(&bars[B::sfull + 2 * u + t], (sbase[u] + (uint32_t)(jj >> 1)) & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TR(0, tri, 200 + jj);
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(cSu, ra);
-        tmem_ld_32x32(cSu + 32, rb);
+        uint32_t rc[32];
+        tmem_ld_32x32(cS + u * 64 + hf * 32, rc);
+        const int c = 2 * u + hf;                        // 32-key chunk of the 128-key block
+        const int key0 = j * 128 + c * 32;
+        uint32_t m = kbits[4 * j + c];
+        if (diag) m &= low_bits(row + p.coff - key0 + 1);
+        if (none) m = low_bits(sk - key0);
+        const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
+        const bool empty = __all_sync(0xffffffffu, m == 0u);
+        const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
+        const int lim = max(sk - 1 - key0, 0);
+        tmem_ld_wait();
+        sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
+        if (kDrop) {
+          const uint32_t keep = keep_word(p, drow, key0, dgroups);
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int c = 2 * u + w;                       // 32-key chunk of the 128-key block
-          const int key0 = j * 128 + c * 32;
-          uint32_t m = kbits[4 * j + c];
-          if (diag) m &= low_bits(row + p.coff - key0 + 1);
-          if (none) m = low_bits(sk - key0);
-          const bool full = __all_sync(0xffffffffu, m == 0xffffffffu);
-          const bool empty = __all_sync(0xffffffffu, m == 0u);
-          const float* bk = has_bias ? bias0 + min(key0, sk - 1) : nullptr;
-          const int lim = max(sk - 1 - key0, 0);
-          if (w == 0) tmem_ld_wait();                    // both chunk loads were issued together
-          uint32_t(&rc)[32] = w == 0 ? ra : rb;
-          sum += exp_chunk<kBias>(rc, m, full, empty, bk, lim, c1, mxc, bsc);
-          if (kDrop) {
-            const uint32_t keep = keep_word(p, drow, key0, dgroups);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
-          }
-          if (w == 0 && jj >= 2) mbar_wait(&bars[B::pfree + 2 * u + t], ((jj >> 1) - 1) & 1);   // P V(jj - 2) done: buffer reusable
-          // P buffer u is one 64-column slab; chunk w fills its 16-byte columns 4w .. 4w+3
-          store_chunk_bf16(p_base + u * 16384, tid, w, rc);
+          for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
         }
+        if (jj >= 2) mbar_wait(&bars[B::pfree + 2 * u + t], ((jj >> 1) - 1) & 1);   // P V(jj - 2) done: buffer reusable
+        // P buffer u is one 64-column slab; this thread's chunk fills its 16-byte columns 4 hf .. 4 hf + 3
+        store_chunk_bf16(p_base + u * 16384, tid, hf, rc);
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars[B::pfull + 2 * u + t]);
         if (threadIdx.x == 0) TR(0, tri, 250 + jj);
       }
+      // the two halves of a row add their sums
+      xrow[hf * 128] = sum;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      sum += xrow[(hf ^ 1) * 128];
       // all of O_t accumulated: the last P V of each buffer (completion is in issue order, so buffer 1's last implies all)
       mbar_wait(&bars[B::pfree + 0 + t], ((nsub - 2) >> 1) & 1);
       mbar_wait(&bars[B::pfree + 2 + t], ((nsub - 1) >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) TR(0, tri, 900);
       const float inv = 1.f / sum;
+      // O read-out: this thread stores the D / 2 columns [hf * D / 2, (hf + 1) * D / 2) of its row
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < D / 64; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(cO + c * 32, r);
+        tmem_ld_32x32(cO + hf * (D / 2) + c * 32, r);
         tmem_ld_wait();
-        if (row < sq) store_row_bf16(o + ((int64_t)rowq + row) * ldo + colq + c * 32, r, inv);
+        if (row < sq) store_row_bf16(o + ((int64_t)rowq + row) * ldo + colq + hf * (D / 2) + c * 32, r, inv);
       }
-      if (row < sq && stats != nullptr)
+      if (row < sq && stats != nullptr && hf == 0)
         *reinterpret_cast<float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2) = make_float2(mx, inv);
     }
   }
   if (threadIdx.x == 0) TR(0, tri, 990);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem_base);
+  if (warp == 16) tmem_dealloc<512>(tmem_base);
   if (threadIdx.x == 0) TR(0, tri, 999);
 }
 
@@ -953,14 +958,14 @@ template <int D>
 int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float* stats, int64_t batch, cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
   constexpr int NS = (D == 64) ? 3 : 1;
-  const size_t smem = (2 + 2 * NS) * (size_t)TB + 65536 + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16;
+  const size_t smem = (2 + 2 * NS) * (size_t)TB + 65536 + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16 + 2 * 2 * 128 * 4;
   const bool bias = p.rel_bias != nullptr, drop = p.drop_thresh != 0;
   auto kern = bias ? (drop ? sattn_fwd_kernel<D, true, true> : sattn_fwd_kernel<D, true, false>)
                    : (drop ? sattn_fwd_kernel<D, false, true> : sattn_fwd_kernel<D, false, false>);
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntq = (p.seq_q + 127) / 128;
   dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
-  kern<<<grid, 352, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
+  kern<<<grid, 608, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
   return check_launch("mmgl_attn_fwd");
 }
 
