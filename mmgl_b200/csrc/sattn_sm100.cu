@@ -274,7 +274,8 @@ template <int NS> struct FwdBars {
   static constexpr int sfree = 6 + 4 * NS;   // [2 buffers][2 tiles]  pass 1: tile t's 128 threads have read that S buffer
   static constexpr int pfull = 10 + 4 * NS;  // [2 buffers][2 tiles]  pass 2: tile t's P half-block is in shared memory (128 arrivals)
   static constexpr int pfree = 14 + 4 * NS;  // [2 buffers][2 tiles]  P V of that half-block complete: P buffer reusable, O_t updated
-  static constexpr int count = 18 + 4 * NS;
+  static constexpr int s2full = 18 + 4 * NS; // [3 buffers][2 tiles]  pass 2: S of a half block complete in TMEM buffer (index 2 * buf + t)
+  static constexpr int count = 24 + 4 * NS;
 };
 
 template <int D, bool kBias, bool kDrop>
@@ -394,42 +395,37 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       for (int tt = 0; tt < 2; ++tt)
         for (int jj = max(nblk[tt] - 2, 0); jj < nblk[tt]; ++jj)
           mbar_wait(&bars[B::sfree + 2 * (jj & 1) + tt], (jj >> 1) & 1);
-      // Pass 2 works on HALF blocks (64 keys) with two S buffers and two P buffers per tile: sub-block jj = half (jj & 1) of
-      // key block jj >> 1 lives in buffer jj & 1.  S(jj + 2) is issued right after P V(jj), so the softmax warps find the next
-      // scores ready when they finish a half block and never wait for the P V + Q K^T pair.
-      const uint32_t cS2[2] = {cS, cS + 64};
+      // Pass 2 works on HALF blocks (64 keys) with NSB S buffers (TMEM) and two P slabs (shared memory) per tile: half block x
+      // = half (x & 1) of key block x >> 1 lives in S buffer x % NSB and P slab x & 1.  S(jj + NSB) is issued right after
+      // P V(jj), so the softmax warps always find the next scores ready and the hand-off latency is off the critical path.
+      constexpr int NSB = (D == 64) ? 3 : 2;                 // S buffers per tile in pass 2 (TMEM: 2 * NSB * 64 + 2 * D <= 512)
+      const uint32_t cS2 = tmem_base + t * (NSB * 64);       // + v * 64
+      const uint32_t cO2 = tmem_base + 2 * NSB * 64 + t * D;
       const uint64_t dp2[2] = {dp, dp + (uint64_t)(16384 >> 4)};
       const int nsub = 2 * nb;
-      {
-        const int n = nbmax, s = n % NS;
-        if (t == 0) TR(2, tri, 198);
-        mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
+      // S of half block x (half x & 1 of key block x >> 1) into S buffer x % NSB; the first half waits for its K stage, the
+      // second releases it
+      auto issue_s = [&](int x) {
+        const int jn = x >> 1, hk = x & 1, n = nbmax + jn, st = n % NS;
+        if (hk == 0) mbar_wait(&bars[B::kfull + st], (n / NS) & 1);
         tc_fence_after();
-        const uint64_t dk = dk0 + (uint64_t)((s * TB) >> 4);
-        mma_qk_half<D>(cS2[0], dq, dk);
-        umma_commit(&bars[B::sfull + 0 + t]);
-        mma_qk_half<D>(cS2[1], dq, dk + (uint64_t)(8192 >> 4));
-        umma_commit(&bars[B::sfull + 2 + t]);
-        release(&bars[B::kfree + s], 0);
-        if (t == 0) TR(2, tri, 199);
-      }
+        mma_qk_half<D>(cS2 + (x % NSB) * 64, dq, dk0 + (uint64_t)((st * TB + hk * 8192) >> 4));
+        umma_commit(&bars[B::s2full + 2 * (x % NSB) + t]);
+        if (hk == 1) release(&bars[B::kfree + st], jn);
+      };
+      if (t == 0) TR(2, tri, 198);
+      for (int x = 0; x < NSB && x < nsub; ++x) issue_s(x);   // the tensor core starts NSB half blocks ahead of the softmax
+      if (t == 0) TR(2, tri, 199);
       for (int jj = 0; jj < nsub; ++jj) {
-        const int u = jj & 1, j = jj >> 1, sv = j % NS;
-        mbar_wait(&bars[B::pfull + 2 * u + t], (jj >> 1) & 1);
+        const int pp = jj & 1, j = jj >> 1, sv = j % NS;
+        mbar_wait(&bars[B::pfull + 2 * pp + t], (jj >> 1) & 1);
         if (t == 0) TR(2, tri, 200 + jj);
-        if (u == 0) mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
+        if (pp == 0) mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
         tc_fence_after();
-        mma_pv_half<D>(cO, dp2[u], dv0 + (uint64_t)((sv * TB + u * 8192) >> 4), jj != 0);
-        umma_commit(&bars[B::pfree + 2 * u + t]);
-        if (u == 1) release(&bars[B::vfree + sv], j);
-        if (jj + 2 < nsub) {                                  // S of the same half of the NEXT key block, into the buffer just freed
-          const int n = nbmax + j + 1, s = n % NS;
-          if (u == 0) mbar_wait(&bars[B::kfull + s], (n / NS) & 1);
-          tc_fence_after();
-          mma_qk_half<D>(cS2[u], dq, dk0 + (uint64_t)((s * TB + u * 8192) >> 4));
-          umma_commit(&bars[B::sfull + 2 * u + t]);
-          if (u == 1) release(&bars[B::kfree + s], j + 1);
-        }
+        mma_pv_half<D>(cO2, dp2[pp], dv0 + (uint64_t)((sv * TB + pp * 8192) >> 4), jj != 0);
+        umma_commit(&bars[B::pfree + 2 * pp + t]);
+        if (pp == 1) release(&bars[B::vfree + sv], j);
+        if (jj + NSB < nsub) issue_s(jj + NSB);               // into the S buffer the softmax warps have just finished reading
         if (t == 0) TR(2, tri, 300 + jj);
       }
     }
@@ -446,7 +442,10 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int tid = ((warp & 3) << 5) | lane;           // row in tile
       const int row = qt * 128 + tid;
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-      const uint32_t cS = lane_addr + t * 128, cO = lane_addr + 256 + t * D;
+      constexpr int NSB = (D == 64) ? 3 : 2;               // S buffers per tile in pass 2
+      const uint32_t cS = lane_addr + t * 128;             // pass 1: + (j & 1) * 256
+      const uint32_t cS2 = lane_addr + t * (NSB * 64);     // pass 2: + v * 64
+      const uint32_t cO = lane_addr + 2 * NSB * 64 + t * D;
       const float scale = p.scale;
       constexpr bool has_bias = kBias;
       // bias of (row, key) = bias_row[key]  (bias_row points at the entry of key 0; negative offsets are valid memory)
@@ -493,23 +492,23 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const bool none = !(mx > -FLT_MAX);
       const float c1 = none ? 0.f : scale * kL2E, mxc = none ? 0.f : mx * kL2E, bsc = none ? 0.f : kL2E;
       // ---------------- pass 2: P = exp(x - max), O += P V, on half blocks (64 keys = chunks 2u, 2u+1 of key block jj >> 1) with
-      // double-buffered S (TMEM) and P (shared memory): while this tile's warps exponentiate half block jj, the tensor core
-      // already holds S(jj + 1) and is free to run P V(jj - 1) and S(jj + 2).  This thread owns chunk 2u + hf.
+      // NSB S buffers in TMEM (3 at head_dim 64) and two P slabs in shared memory: while this tile's warps exponentiate half
+      // block jj, the tensor core already holds S(jj + 1) (and S(jj + 2)) and is free to run P V(jj - 1) and S(jj + NSB), so the
+      // softmax -> MMA -> softmax hand-off latency stays off the critical path.  This thread owns chunk 2u + hf.
       float sum = 0.f;
       const uint32_t p_base = smem_u32(sP + t * 32768);
       const int64_t drow = ((int64_t)b * p.heads + h) * sq + row;
       const int64_t dgroups = (sk + 7) >> 3;
-      // pass 1 completed ceil(nb / 2) phases on the buffer-0 barrier and floor(nb / 2) on the buffer-1 barrier
-      const uint32_t sbase[2] = {(uint32_t)((nb + 1) >> 1), (uint32_t)(nb >> 1)};
       const int nsub = 2 * nb;
       for (int jj = 0; jj < nsub; ++jj) {
         const int u = jj & 1, j = jj >> 1;
         const bool diag = p.causal && j * 128 + 127 > qt * 128 + p.coff;   // the block holds keys beyond some row's limit
-        mbar_wait(&bars[B::sfull + 2 * u + t], (sbase[u] + (uint32_t)(jj >> 1)) & 1);
+        const int v = jj % NSB;                           // S buffer of this half block
+        mbar_wait(&bars[B::s2full + 2 * v + t], (jj / NSB) & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TR(0, tri, 200 + jj);
         uint32_t rc[32];
-        tmem_ld_32x32(cS + u * 64 + hf * 32, rc);
+        tmem_ld_32x32(cS2 + v * 64 + hf * 32, rc);
         const int c = 2 * u + hf;                        // 32-key chunk of the 128-key block
         const int key0 = j * 128 + c * 32;
         uint32_t m = kbits[4 * j + c];
