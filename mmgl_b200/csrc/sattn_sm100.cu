@@ -167,6 +167,15 @@ __device__ __forceinline__ void mma_pv_desc(uint32_t tmem, uint64_t da0, uint64_
   for (int k = 0; k < 8; ++k)
     umma_f16_ss(tmem, da0 + kslab_off(k), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
 }
+// C[128 x D] (+)= A^T * B from descriptor bases: A a [128 rows][128] tile read MN-major (LBO 16384), B a [128 rows][D] tile
+// read MN-major (LBO 16384); 8 k-steps of 16 rows (2048 bytes)
+template <int D>
+__device__ __forceinline__ void mma_tn_desc(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(128, D, 1, 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_f16_ss(tmem, da0 + (uint64_t)((k * 2048) >> 4), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
+}
 // half-block (64 keys) forms for the double-buffered pass 2 of the forward kernel:
 //   S[128 x 64] = Q[128 x D] * Khalf[64 x D]^T          (db0 = descriptor of the half's first key row)
 //   O[128 x D] (+)= P[128 x 64] * Vhalf[64 x D]          (da0 = P slab, db0 = descriptor of the half's first V row, MN-major)
@@ -683,6 +692,11 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdQ = 256;
   uint32_t kvuse[2] = {0, 0}, aphase = 0, bphase = 0, qphase = 0;
+  // descriptor bases built once: the issuing thread only adds constants per MMA (it is also a worker: issue time is on the
+  // critical path of every block)
+  const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_do = make_smem_desc(smem_u32(sdO), 16, 1024);
+  const uint64_t desc_k = make_smem_desc(smem_u32(sK), 16, 1024), desc_v = make_smem_desc(smem_u32(sV), 16, 1024);
+  const uint64_t desc_ds = make_smem_desc(smem_u32(sdS), 16, 1024), desc_kmn = make_smem_desc(smem_u32(sK), 16384, 1024);
 
   // Persistent CTA: work items (query tile, head, sample), late (heavier when causal) tiles first, dealt round-robin so
   // every CTA gets a mix; TMEM, barriers and the tensor-map fetch are paid once per CTA instead of once per tile.
@@ -721,17 +735,18 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     for (int j = 0; j < nblk; ++j) {
       const int buf = (NB == 2) ? (j & 1) : 0;
       if (tid == 0) {
-        if (NB == 2 && j + 1 < nblk) {
+        if (j == 0) { mbar_wait(&bars[0], qphase & 1); }
+        mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
+        tc_fence_after();
+        const uint64_t off = (uint64_t)((buf * TB) >> 4);
+        mma_qk_desc<D>(tmem_base, desc_q, desc_k + off);            // S
+        mma_qk_desc<D>(tmem_base + 128, desc_do, desc_v + off);     // dP = dO V^T
+        umma_commit(&bars[3]);
+        if (NB == 2 && j + 1 < nblk) {   // the next block's tiles, after this block's MMAs are on their way
           mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
           tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
           tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
         }
-        if (j == 0) { mbar_wait(&bars[0], qphase & 1); }
-        mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
-        tc_fence_after();
-        mma_qk<D>(tmem_base, smem_u32(sQ), smem_u32(sK + buf * TB));           // S
-        mma_qk<D>(tmem_base + 128, smem_u32(sdO), smem_u32(sV + buf * TB));    // dP = dO V^T
-        umma_commit(&bars[3]);
       }
       const uint32_t mw = row_word(p, kbits[4 * j + quarter], j, qt, rit, quarter, none);
       __syncwarp();
@@ -744,7 +759,7 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        mma_pv<D>(tmem_base + cdQ, smem_u32(sdS), smem_u32(sK + buf * TB), j != 0);   // dQ += dS K_j
+        mma_pv_desc<D>(tmem_base + cdQ, desc_ds, desc_kmn + (uint64_t)((buf * TB) >> 4), j != 0);   // dQ += dS K_j
         umma_commit(&bars[4]);
         if (NB == 1 && j + 1 < nblk) {   // single buffer: reload K / V once this block's MMAs have drained
           mbar_wait(&bars[4], bphase & 1);
@@ -830,6 +845,10 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t cdV = 256, cdK = 256 + D;
   uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0, kphase = 0;
+  const uint64_t desc_k = make_smem_desc(smem_u32(sK), 16, 1024), desc_v = make_smem_desc(smem_u32(sV), 16, 1024);
+  const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_do = make_smem_desc(smem_u32(sdO), 16, 1024);
+  const uint64_t desc_p_mn = make_smem_desc(smem_u32(sP), 16384, 1024), desc_ds_mn = make_smem_desc(smem_u32(sdS), 16384, 1024);
+  const uint64_t desc_q_mn = make_smem_desc(smem_u32(sQ), 16384, 1024), desc_do_mn = make_smem_desc(smem_u32(sdO), 16384, 1024);
 
   // Persistent CTA over work items (key block, head, sample); early key blocks (seen by the most query tiles when
   // causal) first, dealt round-robin.
@@ -869,17 +888,18 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       delta = __ldg(delta_ws + sidx);
     }
     if (tid == 0) {
-      if (NB == 2 && i + 1 < ntq) {
+      if (it == 0) mbar_wait(&bars[0], kphase & 1);
+      mbar_wait(&bars[1 + buf], quse[buf] & 1); quse[buf]++;
+      tc_fence_after();
+      const uint64_t off = (uint64_t)((buf * TB) >> 4);
+      mma_qk_desc<D>(tmem_base, desc_q + off, desc_k);             // S  = Q_i K_j^T
+      mma_qk_desc<D>(tmem_base + 128, desc_do + off, desc_v);      // dP = dO_i V_j^T
+      umma_commit(&bars[3]);
+      if (NB == 2 && i + 1 < ntq) {   // the next query tile, after this tile's MMAs are on their way
         mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
         tma_tile<D>(sQ + (buf ^ 1) * TB, &map_q, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
         tma_tile<D>(sdO + (buf ^ 1) * TB, &map_do, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
       }
-      if (it == 0) mbar_wait(&bars[0], kphase & 1);
-      mbar_wait(&bars[1 + buf], quse[buf] & 1); quse[buf]++;
-      tc_fence_after();
-      mma_qk<D>(tmem_base, smem_u32(sQ + buf * TB), smem_u32(sK));          // S  = Q_i K_j^T
-      mma_qk<D>(tmem_base + 128, smem_u32(sdO + buf * TB), smem_u32(sV));   // dP = dO_i V_j^T
-      umma_commit(&bars[3]);
     }
     const bool none = !(m > -FLT_MAX);
     const uint32_t mw = row_word(p, kword, kb, i, rit, quarter, none);
@@ -895,8 +915,9 @@ sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_tn<D>(tmem_base + cdV, smem_u32(sP), smem_u32(sdO + buf * TB), it != 0);    // dV_j += P~^T dO_i
-      mma_tn<D>(tmem_base + cdK, smem_u32(sdS), smem_u32(sQ + buf * TB), it != 0);    // dK_j += dS^T Q_i
+      const uint64_t off = (uint64_t)((buf * TB) >> 4);
+      mma_tn_desc<D>(tmem_base + cdV, desc_p_mn, desc_do_mn + off, it != 0);    // dV_j += P~^T dO_i
+      mma_tn_desc<D>(tmem_base + cdK, desc_ds_mn, desc_q_mn + off, it != 0);    // dK_j += dS^T Q_i
       umma_commit(&bars[4]);
       if (NB == 1 && i + 1 < ntq) {
         mbar_wait(&bars[4], bphase & 1);
