@@ -120,10 +120,10 @@ int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
  * row = (b*heads + h)*seq_q + i.
  *
  * 128 x 128 score blocks on tcgen05 with TMEM accumulators, TMA-staged tiles, two-pass fp32 softmax; only blocks at
- * or below the diagonal are visited when causal.  Forward: two query tiles per CTA in ping-pong (8 softmax warps, two
- * MMA-issuing warps, one TMA warp).  Backward = a dQ kernel (per query tile) + a dK/dV kernel (per key block), both
- * recomputing P from stats, four threads per score row; the bias is treated as a constant (its table is frozen
- * under LoRA).
+ * or below the diagonal are visited when causal.  Forward: two query tiles per CTA in ping-pong (16 softmax warps, two
+ * MMA-issuing warps, one TMA warp; pass 2 on 64-key half blocks with multi-buffered S).  Backward = a persistent dQ kernel
+ * (items = query tiles) + a persistent dK/dV kernel (items = key blocks), both recomputing P from stats, four threads per
+ * score row; the bias is treated as a constant (its table is frozen under LoRA).
  *
  * Replaces MPTAttention's self branch model/modelling_cross_attention.py:201-275 with the mask of :455-476, and the
  * attention of the HF T5 / OPT language model that model/modelling_self_attention.py:332 runs (HF

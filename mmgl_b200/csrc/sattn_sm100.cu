@@ -10,14 +10,16 @@
 // (S = Q K_j^T per key block), pass 2 recomputes S, exponentiates against the final maximum and accumulates
 // O += P_j V_j in TMEM.  One extra QK^T per block buys the absence of any accumulator correction.
 //
-//   forward : CTA = TWO 128-query tiles of one (head, sample) in ping-pong: 8 softmax warps (4 per tile, one thread per
-//             score row = one TMEM lane, so the softmax needs no shuffles), one MMA-issuing warp and one TMA warp.  The
-//             K / V blocks stream once through a 3-stage ring for both tiles; while one tile's warps exponentiate, the
-//             tensor core runs the other tile's P V and next Q K^T.  Only blocks at or below the diagonal are visited
-//             when causal (tiles are paired heavy-with-next-heavy, heavy pairs first).
-//   backward: dQ kernel   CTA = (query tile i): loops key blocks j, dQ_i += dS_ij K_j            (accumulates in TMEM)
-//             dK/dV kernel CTA = (key block j): loops query tiles i, dV_j += P_ij^T dO_i, dK_j += dS_ij^T Q_i (TMEM)
-//             both recompute S and dP = dO V^T from Q, K, V, dO and the saved row statistics (m, 1/l).
+//   forward : CTA = TWO 128-query tiles of one (head, sample) in ping-pong: 16 softmax warps (8 per tile, two threads per
+//             score row, each thread = one TMEM lane and half of the columns), two MMA-issuing warps (one per tile) and one
+//             TMA warp.  The K / V blocks stream once through a 3-stage ring for both tiles.  Pass 1 double-buffers S in TMEM;
+//             pass 2 works on 64-key half blocks with three S buffers (two at head_dim 128) and two P slabs per tile, so the
+//             tensor core runs ahead of the exponentials.  Only blocks at or below the diagonal are visited when causal (tiles
+//             are paired heavy-with-next-heavy, heavy pairs first).  A packed variable-length batch (cu_seqlens) is supported.
+//   backward: dQ kernel   item = (query tile i): loops key blocks j, dQ_i += dS_ij K_j            (accumulates in TMEM)
+//             dK/dV kernel item = (key block j): loops query tiles i, dV_j += P_ij^T dO_i, dK_j += dS_ij^T Q_i (TMEM)
+//             both recompute S and dP = dO V^T from Q, K, V, dO and the saved row statistics (m, 1/l); 512 threads = four per
+//             score row; persistent CTAs walk the items, heavy first.
 // Masks are bit masks: one 32-bit word per 32 keys (attend = exists AND not padding), built once per CTA; the causal
 // limit of the diagonal block is a per-thread shift.  Interior blocks (all 128 keys attended, not diagonal, no bias)
 // take a 3-instruction-per-score path.
@@ -91,10 +93,6 @@ __device__ __forceinline__ void build_key_bits(uint32_t* kbits, const uint8_t* k
     if (lane == 0) kbits[w] = bits;
   }
 }
-__device__ __forceinline__ bool block_all_attended(const uint32_t* kbits, int j) {
-  const uint4 w = *reinterpret_cast<const uint4*>(kbits + 4 * j);
-  return (w.x & w.y & w.z & w.w) == 0xffffffffu;
-}
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -118,41 +116,10 @@ __device__ __forceinline__ uint32_t keep_word(const AttnParams& p, int64_t drow,
   return w;
 }
 
-// issue S[128 x 128] = A[128 x D] * B[128 x D]^T (both K-major tiles of DS 64-wide slabs) into TMEM column `col`
-template <int D>
-__device__ __forceinline__ void mma_qk(uint32_t tmem, uint32_t a_base, uint32_t b_base) {
-  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-  for (int k = 0; k < D / 16; ++k) {
-    const uint64_t da = make_smem_desc(a_base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-    const uint64_t db = make_smem_desc(b_base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-    umma_f16_ss(tmem, da, db, idesc, k != 0 ? 1u : 0u);
-  }
-}
-// issue C[128 x D] (+)= A[128 x 128] * B[128 x D]: A K-major (2 slabs of 64), B a [128 rows][D] tile read MN-major
-template <int D>
-__device__ __forceinline__ void mma_pv(uint32_t tmem, uint32_t a_base, uint32_t b_base, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint64_t da = make_smem_desc(a_base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-    const uint64_t db = make_smem_desc(b_base + k * 2048, 16384, 1024);
-    umma_f16_ss(tmem, da, db, idesc, (accumulate || k != 0) ? 1u : 0u);
-  }
-}
-// issue C[128 x D] (+)= A^T * B: A a [128 rows][128] tile read MN-major (transposed), B a [128 rows][D] tile read MN-major
-template <int D>
-__device__ __forceinline__ void mma_tn(uint32_t tmem, uint32_t a_base, uint32_t b_base, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(128, D, 1, 1);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint64_t da = make_smem_desc(a_base + k * 2048, 16384, 1024);
-    const uint64_t db = make_smem_desc(b_base + k * 2048, 16384, 1024);
-    umma_f16_ss(tmem, da, db, idesc, (accumulate || k != 0) ? 1u : 0u);
-  }
-}
-// the same contractions from precomputed descriptor bases (descriptor of addr + delta = descriptor of addr + (delta >> 4)):
-// the issuing thread adds compile-time constants instead of rebuilding two descriptors per instruction
+// MMA issue from precomputed descriptor bases (descriptor of addr + delta = descriptor of addr + (delta >> 4)): the issuing
+// thread adds compile-time constants instead of building two descriptors per instruction.
+//   mma_qk_desc: S[128 x 128] = A[128 x D] * B[128 x D]^T, both K-major tiles of D / 64 slabs of [128][64]
+//   mma_pv_desc: C[128 x D] (+)= A[128 x 128] * B[128 x D], A K-major (2 slabs), B a [128 rows][D] tile read MN-major (LBO 16384)
 __host__ __device__ constexpr uint64_t kslab_off(int k) { return (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4); }
 template <int D>
 __device__ __forceinline__ void mma_qk_desc(uint32_t tmem, uint64_t da0, uint64_t db0) {
@@ -378,7 +345,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const uint64_t dp = make_smem_desc(smem_u32(sP + t * 32768), 16, 1024);
       const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 1024);
       const uint64_t dv0 = make_smem_desc(smem_u32(sV), 16384, 1024);
-      const uint32_t cS = tmem_base + t * 128, cO = tmem_base + 256 + t * D;
+      const uint32_t cS = tmem_base + t * 128;
       // a K / V stage is released by two arrivals, one per tile; the only tile using a block arrives twice
       auto release = [&](uint64_t* bar, int j) {
         umma_commit(bar);
