@@ -171,6 +171,9 @@ def test_self_attention_model_runs_the_lm_on_the_package_kernels(lm):
     out.loss.backward()
     assert torch.isfinite(out.loss)
     assert _capi.launch_count() - n0 > 60, "the LM did not run on the package's kernels"
+    # invariant I7: T5 -> (B, S_out, V); OPT -> (B, S_in + S_out + Nk, V), Nk = (T + I) * n_tokens
+    want = (2, 16, 512) if lm == "t5" else (2, 48 + 16 + (3 + 2) * 2, 512)
+    assert tuple(out.logits.shape) == want, out.logits.shape
     got = {n for n, p in model.named_parameters() if p.grad is not None and float(p.grad.abs().max()) > 0}
     # at init B = 0, so dA is exactly zero; B, the neighbor projection and the lm_head copy must all train
     assert any("lora_B" in n for n in got) and any("lm_head" in n for n in got), got

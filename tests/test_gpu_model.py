@@ -92,6 +92,26 @@ def test_gates_at_zero_equal_plain_opt(golden):
     assert torch.equal(a, b)
 
 
+def test_gradients_at_the_reference_init(golden):
+    """Invariant I4: at the reference's init (gating1 = gating2 = 0) the loss gradient reaches the
+    gates, while every weight inside the gated branches gets an exactly-zero gradient (tanh(0) multiplies the branch)."""
+    g = golden("wrapper_cross_d64")
+    model = _build(g)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "gating" in n:
+                p.zero_()
+    batch = {k: v.cuda() for k, v in g["batch"].items()}
+    model(**batch).loss.backward()
+    params = dict(model.named_parameters())
+    gates = [n for n in params if "gating" in n]
+    assert gates and all(params[n].grad is not None and float(params[n].grad.abs()) > 0 for n in gates)
+    inside = [n for n in params if "neighbor_layers" in n and "gating" not in n and "layer_norm" not in n]
+    assert inside
+    for n in inside:
+        assert params[n].grad is not None and float(params[n].grad.abs().max()) == 0.0, n
+
+
 def test_training_mode_runs_with_dropout(golden):
     g = golden("wrapper_cross_d64")
     model = _build(g, train=True)
