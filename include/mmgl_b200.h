@@ -123,7 +123,7 @@ int mmgl_xattn_bwd(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
  * or below the diagonal are visited when causal.  Forward: two query tiles per CTA in ping-pong (16 softmax warps, two
  * MMA-issuing warps, one TMA warp; pass 2 on 64-key half blocks with multi-buffered S).  Backward = a persistent dQ kernel
  * (items = query tiles) + a persistent dK/dV kernel (items = key blocks), both recomputing P from stats, four threads per
- * score row; the bias is treated as a constant (its table is frozen under LoRA).
+ * score row; the gradient of the bias is optional (its table is frozen under LoRA).
  *
  * Replaces MPTAttention's self branch model/modelling_cross_attention.py:201-275 with the mask of :455-476, and the
  * attention of the HF T5 / OPT language model that model/modelling_self_attention.py:332 runs (HF
@@ -146,8 +146,12 @@ int mmgl_attn_fwd(const mmgl_attn_args* args, void* stream);
 /* o and stats in args are the forward outputs (read here).  workspace: caller-owned fp32 scratch of
  * mmgl_attn_bwd_workspace_bytes() (rowsum(dO . O), written by the dQ kernel and read by the dK/dV kernel). */
 size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t heads);
+/* d_rel_bias: NULL, or fp32 [heads, seq_q + seq_k - 1] that receives += the gradient of rel_bias (sum of dS over every
+ * (sample, row, key) with the same key - row; the caller zeroes it).  Accumulated with fp32 atomics, so its low bits are
+ * not run-to-run deterministic; everything else in the library is. */
 int mmgl_attn_bwd(const mmgl_attn_args* args, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
-                  int64_t lddk, void* dv, int64_t lddv, void* workspace, size_t workspace_bytes, void* stream);
+                  int64_t lddk, void* dv, int64_t lddv, float* d_rel_bias, void* workspace, size_t workspace_bytes,
+                  void* stream);
 
 
 

@@ -88,7 +88,7 @@ SIGNATURES = {
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "mmgl_attn_fwd": (c_i32, [C.POINTER(AttnArgs), c_vp]),
     "mmgl_attn_bwd_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
-    "mmgl_attn_bwd": (c_i32, [C.POINTER(AttnArgs), c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "mmgl_attn_bwd": (c_i32, [C.POINTER(AttnArgs), c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "mmgl_layernorm_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
     "mmgl_layernorm_bwd_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "mmgl_layernorm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz,
@@ -328,15 +328,18 @@ def attn_fwd(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, 
 
 
 def attn_bwd(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv, batch, seq_q, seq_k, heads, head_dim, scale, causal,
-             dropout_p=0.0, dropout_seed=0):
-    _req_cuda(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv)
+             dropout_p=0.0, dropout_seed=0, d_rel_bias=None):
+    """d_rel_bias: None, or a ZEROED fp32 [heads, seq_q+seq_k-1] tensor that receives the gradient of rel_bias."""
+    _req_cuda(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv, d_rel_bias)
+    assert d_rel_bias is None or (rel_bias is not None and d_rel_bias.dtype == torch.float32 and d_rel_bias.is_contiguous()
+                                  and d_rel_bias.shape == rel_bias.shape)
     h = heads * head_dim
     a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
                    dropout_seed)
     ws = torch.empty(batch * heads * seq_q, dtype=torch.float32, device=q.device)
     with _Timed("sattn_bwd", float(batch * (seq_q + seq_k) * h * 2 * 4)):
         _check(lib().mmgl_attn_bwd(C.byref(a), _p(d_o), _ld(d_o), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
-                                   _p(ws), ws.numel() * 4, _stream()), "mmgl_attn_bwd")
+                                   _p(d_rel_bias), _p(ws), ws.numel() * 4, _stream()), "mmgl_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------- layernorm

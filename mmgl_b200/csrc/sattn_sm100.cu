@@ -60,6 +60,7 @@ struct AttnParams {
   const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
   int seq_q, seq_k, heads, causal;
   int batch;                 // backward kernels: persistent CTAs walk (tile, head, sample) work items
+  float* d_rel_bias;         // dQ kernel only, or null: gradient of rel_bias, += over (sample, row) with atomics
   const int32_t* cu_seqlens; // forward only, or null: sample b = packed rows [cu[b], cu[b+1]) (variable-length batch)
   int coff;                  // causal: key allowed iff key <= row + coff, coff = seq_k - seq_q (bottom-right aligned; prefix K/V)
   float scale;
@@ -570,7 +571,8 @@ __device__ __forceinline__ float delta_partial(const __nv_bfloat16* o, int64_t l
 template <bool kWriteP, bool kBias, bool kDrop>
 __device__ __forceinline__ void softmax_grad_chunk(const AttnParams& p, uint32_t lane_addr, int c, uint32_t mw,
                                                    const float* bias_row, int key0, bool row_ok, float m, float inv,
-                                                   float delta, int64_t drow, uint32_t p_base, uint32_t ds_base, int row_in_tile) {
+                                                   float delta, int64_t drow, uint32_t p_base, uint32_t ds_base, int row_in_tile,
+                                                   float* bias_bins = nullptr) {
   const bool flat = !(m > -FLT_MAX) || !row_ok;   // no attended key (uniform row) or a row beyond the sequence (p = 0)
   const float c1 = flat ? 0.f : p.scale * kL2E, mc = flat ? 0.f : m * kL2E, bsc = flat ? 0.f : kL2E;
   const float inv_ok = row_ok ? inv : 0.f;
@@ -604,6 +606,10 @@ __device__ __forceinline__ void softmax_grad_chunk(const AttnParams& p, uint32_t
     }
     pk[e >> 1] = pack_bf16(pv[0], pv[1]);
     dk[e >> 1] = pack_bf16(dv[0], dv[1]);
+    if (kBias && bias_bins != nullptr) {   // d bias(key - row) += dS: one bin per diagonal of the 128 x 128 block
+      atomicAdd(bias_bins + (c * 32 + e - row_in_tile + 127), dv[0]);
+      atomicAdd(bias_bins + (c * 32 + e + 1 - row_in_tile + 127), dv[1]);
+    }
   }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -638,7 +644,8 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* sdS = sV + NB * TB;     // 2 slabs
   const int nbk = (p.seq_k + 127) / 128;
   float* sDelta = reinterpret_cast<float*>(sdS + 32768);   // [4][128] partial row sums
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(sDelta + 512);
+  float* sBins = sDelta + 512;                             // [256] diagonal sums of dS (gradient of the relative-position bias)
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(sBins + 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk);   // q, kv0, kv1, a, b
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
@@ -652,6 +659,8 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  const bool want_dbias = kBias && p.d_rel_bias != nullptr;
+  if (tid < 256) sBins[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -720,10 +729,20 @@ sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(&bars[3], aphase & 1); aphase++;
       tc_fence_after();
       softmax_grad_chunk<false, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, j * 128 + quarter * 32, row_ok, m, inv,
-                                              delta, drow, 0, smem_u32(sdS), rit);
+                                              delta, drow, 0, smem_u32(sdS), rit, want_dbias ? sBins : nullptr);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      if (want_dbias) {   // flush this block's 255 diagonals: bin i holds key - row = j * 128 - r0 + i - 127
+        if (tid < 255) {
+          const float v = sBins[tid];
+          const int idx = j * 128 - r0 + tid - 127 + p.seq_q - 1;
+          if (v != 0.f && idx >= 0 && idx < p.seq_q + p.seq_k - 1)
+            atomicAdd(p.d_rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + idx, v);
+          sBins[tid] = 0.f;
+        }
+        __syncthreads();
+      }
       if (tid == 0) {
         tc_fence_after();
         mma_pv_desc<D>(tmem_base + cdQ, desc_ds, desc_kmn + (uint64_t)((buf * TB) >> 4), j != 0);   // dQ += dS K_j
@@ -963,7 +982,7 @@ int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo
   constexpr int TB = (D / 64) * 16384;
   constexpr int NB = (D == 64) ? 2 : 1;
   {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 2048 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
+    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 2048 + 1024 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
     auto kern = sattn_bwd_dq_kernel<D, kBias, kDrop>;
     MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t items = (int64_t)((p.seq_q + 127) / 128) * p.heads * batch;
@@ -1004,7 +1023,7 @@ int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
   MMGL_REQUIRE(!a->causal || a->seq_q <= a->seq_k, "%s: causal needs seq_q <= seq_k (keys = prefix + the queries' own positions)", who);
   MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
   MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
-  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias; p.cu_seqlens = a->cu_seqlens;
+  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias; p.cu_seqlens = a->cu_seqlens; p.d_rel_bias = nullptr;
   p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal; p.batch = (int)a->batch;
   p.coff = (int)(a->seq_k - a->seq_q);
   p.scale = a->scale;
@@ -1050,7 +1069,8 @@ extern "C" size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, in
 }
 
 extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
-                             int64_t lddk, void* dv, int64_t lddv, void* workspace, size_t workspace_bytes, void* stream_) {
+                             int64_t lddk, void* dv, int64_t lddv, float* d_rel_bias, void* workspace,
+                             size_t workspace_bytes, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   MMGL_REQUIRE(a != nullptr, "mmgl_attn_bwd: null args");
   MMGL_BIND(a->q, "mmgl_attn_bwd");
@@ -1058,6 +1078,8 @@ extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t l
   if (int rc = fill_params("mmgl_attn_bwd", a, p)) return rc;
   MMGL_REQUIRE(d_o && a->k && a->v && a->o && a->stats && dq && dk && dv, "mmgl_attn_bwd: null pointer");
   MMGL_REQUIRE(a->cu_seqlens == nullptr, "mmgl_attn_bwd: variable-length batches are forward-only (frozen encoders)");
+  MMGL_REQUIRE(d_rel_bias == nullptr || a->rel_bias != nullptr, "mmgl_attn_bwd: d_rel_bias without rel_bias");
+  p.d_rel_bias = d_rel_bias;
   MMGL_REQUIRE(workspace != nullptr && workspace_bytes >= mmgl_attn_bwd_workspace_bytes(a->batch, a->seq_q, a->heads),
                "mmgl_attn_bwd: workspace too small (need mmgl_attn_bwd_workspace_bytes)");
   MMGL_REQUIRE(aligned16(d_o) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(dq) &&

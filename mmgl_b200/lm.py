@@ -19,8 +19,7 @@ HF arithmetic restated (HF: models/t5/modeling_t5.py -- T5Stack.forward :637-790
 modules' own fp32 forward / backward on the same weights.
 
 ``supports(lm)`` says whether a model can run here; SelfAttentionModel falls back to the HF forward (library code, as in
-the reference) when it cannot: head_dim not in {64, 128}, gated-GELU T5 variants, a TRAINABLE relative-position table
-(peft "none": the kernels treat the bias as a constant), LayerDrop.  Prefix tuning is implemented for OPT
+the reference) when it cannot: head_dim not in {64, 128}, gated-GELU T5 variants, LayerDrop.  Prefix tuning is implemented for OPT
 (``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions); T5 prefix tuning is not.
 """
 from __future__ import annotations
@@ -85,7 +84,10 @@ def t5_rel_bias(attn, sq, sk):
     dev = attn.relative_attention_bias.weight.device
     rel = torch.arange(-(sq - 1), sk, device=dev)
     bucket = _t5_bucket(rel, not attn.is_decoder, attn.relative_attention_num_buckets, attn.relative_attention_max_distance)
-    return attn.relative_attention_bias.weight.detach().float()[bucket].t().contiguous()
+    w = attn.relative_attention_bias.weight
+    if not w.requires_grad:
+        w = w.detach()
+    return w.float()[bucket].t().contiguous()     # differentiable when the table is trainable (peft "none")
 
 
 def _t5_attention(attn, x, kv, key_mask, rel_bias, causal, p_drop):
@@ -127,8 +129,7 @@ def _t5_supported(lm) -> bool:
         return False
     if getattr(cfg, "dense_act_fn", "relu") != "relu":
         return False
-    tables = [m.relative_attention_bias.weight for m in lm.modules() if hasattr(m, "relative_attention_bias")]
-    return not any(t.requires_grad for t in tables)
+    return True
 
 
 def _shift_right(lm, labels):

@@ -509,7 +509,8 @@ def self_attention(qkv, key_mask, heads, causal=True, scale=None, dropout_p=0.0)
 class AttnFn(torch.autograd.Function):
     """General attention core over separate projections: q [B,Sq,H], k / v [B,Sk,H] (heads interleaved in H),
     key_mask [B,Sk], optional additive relative-position bias rel_bias fp32 [heads, Sq+Sk-1] (bias of (row, key) =
-    rel_bias[h, key - row + Sq - 1]; treated as a constant) and dropout on the probabilities.  This is the attention of
+    rel_bias[h, key - row + Sq - 1]; differentiable: a trainable T5 bias table gets its gradient) and dropout on the
+    probabilities.  This is the attention of
     the HF T5 / OPT language model that the concat path runs (model/modelling_self_attention.py:332): T5 uses
     scale = 1, a bucketed relative-position bias and, in the decoder, cross-attention with Sq != Sk."""
 
@@ -526,6 +527,7 @@ class AttnFn(torch.autograd.Function):
         K.attn_fwd(q2, k2, v2, km, rb, o, stats, b, sq, sk, heads, h // heads, scale, causal, dropout_p, seed)
         ctx.save_for_backward(q2, k2, v2, o, stats, km, rb)
         ctx.cfg = (b, sq, sk, h, heads, bool(causal), float(scale), dropout_p, seed)
+        ctx.bias_dtype = None if rel_bias is None else rel_bias.dtype
         return o.reshape(b, sq, h)
 
     @staticmethod
@@ -533,9 +535,12 @@ class AttnFn(torch.autograd.Function):
         q2, k2, v2, o, stats, km, rb = ctx.saved_tensors
         b, sq, sk, h, heads, causal, scale, dropout_p, seed = ctx.cfg
         dq, dk, dv = torch.empty_like(q2), torch.empty_like(k2), torch.empty_like(v2)
+        d_rb = torch.zeros_like(rb) if (rb is not None and ctx.needs_input_grad[4]) else None
         K.attn_bwd(_as2d(d_o), q2, k2, v2, km, rb, o, stats, dq, dk, dv, b, sq, sk, heads, h // heads, scale, causal,
-                   dropout_p, seed)
-        return dq.reshape(b, sq, h), dk.reshape(b, sk, h), dv.reshape(b, sk, h), None, None, None, None, None, None
+                   dropout_p, seed, d_rel_bias=d_rb)
+        if d_rb is not None and ctx.bias_dtype != F32:
+            d_rb = d_rb.to(ctx.bias_dtype)
+        return dq.reshape(b, sq, h), dk.reshape(b, sk, h), dv.reshape(b, sk, h), None, d_rb, None, None, None, None
 
 
 def attention(q, k, v, key_mask=None, rel_bias=None, heads=1, causal=False, scale=1.0, dropout_p=0.0):

@@ -7,7 +7,7 @@ kernels are: the neighbor projections, the ragged bank packing with the fused po
 accumulates into the same TMEM tile as the base product) and the language model's own layer stack -- attention with the
 T5 relative-position bias or the OPT causal / padding mask, RMSNorm / LayerNorm, FFN, lm_head and the loss
 (mmgl_b200/lm.py, which reads the weights of the HF module in place).  Models that file cannot run (gated-GELU T5,
-head dims other than 64 / 128, a trainable relative-position table under peft "none") fall back to the HF module's own
+head dims other than 64 / 128) fall back to the HF module's own
 forward, as in the reference (third-party code there as well).
 
 peft is not importable in this image and its source is absent, so LoRA / prompt / prefix tuning are restated from

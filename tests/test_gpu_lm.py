@@ -106,6 +106,51 @@ def test_t5_lora_matches_hf():
     _finish(Report(), out, ref_out, pairs, x, xr, product.lm_head.weight, reference.lm_head.weight)
 
 
+def test_t5_full_finetune_matches_hf():
+    """peft_type "none" (model/modelling_self_attention.py:79 is skipped): every T5 weight trains, including the
+    relative-position tables of encoder and decoder -- their gradient comes from the dQ kernel's diagonal sums."""
+    from transformers import T5Config, T5ForConditionalGeneration
+    from mmgl_b200 import lm as L
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(4)
+    cfg = T5Config(vocab_size=384, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_decoder_layers=2, num_heads=2,
+                   decoder_start_token_id=0, dropout_rate=0.0)
+    product = T5ForConditionalGeneration(cfg)
+    with torch.no_grad():
+        for n, p in product.named_parameters():
+            if "relative_attention_bias" in n:
+                p.normal_(0, 1.0)
+            elif "layer_norm" in n:
+                p.uniform_(0.7, 1.3)
+    reference = copy.deepcopy(product).float()
+    product.cuda().eval()
+    reference.cuda().eval()
+    assert L.supports(product)
+    b, s_enc, s_dec = 2, 300, 140                   # 3 x 3 and 2 x 2 score blocks: diagonals span several blocks
+    emb = torch.randn(b, s_enc, cfg.d_model, generator=gen).cuda()
+    am = torch.ones(b, s_enc, dtype=torch.long)
+    am[0, 210:] = 0
+    am[1, 100:140] = 0
+    labels = torch.randint(1, cfg.vocab_size, (b, s_dec), generator=gen)
+    labels[1, 120:] = -100
+    am, labels = am.cuda(), labels.cuda()
+    out = L.forward(product, inputs_embeds=emb.to(BF16), attention_mask=am, labels=labels)
+    out.loss.backward()
+    ref_out = reference(inputs_embeds=emb.to(BF16).float(), attention_mask=am, labels=labels)
+    ref_out.loss.backward()
+    rep = Report()
+    rep.scalar("loss", out.loss, ref_out.loss, 0.0, 2e-2)
+    rep.close("logits", out.logits, ref_out.logits, 2e-2)
+    ref_params = dict(reference.named_parameters())
+    seen = 0
+    for n, p in product.named_parameters():
+        assert p.grad is not None, n
+        rep.close("d " + n, p.grad, ref_params[n].grad, 6e-2)
+        seen += "relative_attention_bias" in n
+    assert seen == 2
+    rep.finish()
+
+
 def test_opt_lora_matches_hf():
     from transformers import OPTConfig, OPTForCausalLM
     from mmgl_b200 import lm as L

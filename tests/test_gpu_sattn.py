@@ -85,7 +85,7 @@ def test_padding_keys_have_zero_influence():
 # ------------------------------------------------------------------------------------------------ general form
 def _rel_vec(gen, heads, sq, sk):
     """a relative-position bias given as its per-distance vector [heads, sq + sk - 1] and as the dense [1,nh,sq,sk]"""
-    vec = torch.randn(heads, sq + sk - 1, generator=gen) * 1.5
+    vec = (torch.randn(heads, sq + sk - 1, generator=gen) * 1.5).requires_grad_(True)
     idx = torch.arange(sk)[None, :] - torch.arange(sq)[:, None] + sq - 1
     return vec, vec[:, idx][None]
 
@@ -113,12 +113,13 @@ def test_general_attention_forward_backward(b, sq, sk, heads, d, causal, bias, p
         key_mask = torch.ones(b, sk, dtype=torch.bool)
         key_mask[0, int(sk * 0.55):int(sk * 0.7)] = False
         key_mask[-1, int(sk * 0.9):] = False
-    vec = dense = None
+    vec = dense = dvec = None
     if bias:
         vec, dense = _rel_vec(gen, heads, sq, sk)
+        dvec = vec.detach().cuda().requires_grad_(True)      # a trainable bias (T5 with peft "none")
     xs = [t.clone().requires_grad_(True) for t in (q, k, v)]
     o = ops.attention(*xs, key_mask=None if key_mask is None else key_mask.cuda(),
-                      rel_bias=None if vec is None else vec.cuda(), heads=heads, causal=causal, scale=scale)
+                      rel_bias=dvec, heads=heads, causal=causal, scale=scale)
     o.backward(d_o)
     rs = [t.float().cpu().requires_grad_(True) for t in (q, k, v)]
     o_ref = O.attention_core(*rs, heads, scale, key_mask, causal, dense)
@@ -127,6 +128,8 @@ def test_general_attention_forward_backward(b, sq, sk, heads, d, causal, bias, p
     rep.close("O", o, o_ref, 4e-3)
     for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
         rep.close(name, x.grad, r.grad, 1e-2)
+    if bias:
+        rep.close("d rel_bias", dvec.grad, vec.grad, 1e-2)
     rep.finish()
 
 
