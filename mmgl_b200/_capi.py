@@ -211,6 +211,9 @@ def _ld(t: torch.Tensor) -> int:
 _ws_cache = {}
 
 
+_DEFAULT_STREAM_K = int(os.environ.get("MMGL_GEMM_STREAM_K", "0"))   # tuning knob: 2 = cut K for the tail wave / skinny outputs
+
+
 def _gemm_workspace(device) -> torch.Tensor:
     """Stream-K scratch (fp32 partial tiles + arrival counters), one buffer per (device, stream): launches on one
     stream are ordered, so consecutive GEMMs can share it; concurrent streams get their own."""
@@ -268,7 +271,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t: bool = Fal
     g.raster = raster
     g.pair = pair
     ws = _gemm_workspace(out.device)
-    g.workspace, g.workspace_bytes, g.stream_k = ws.data_ptr(), ws.numel(), stream_k
+    g.workspace, g.workspace_bytes, g.stream_k = ws.data_ptr(), ws.numel(), stream_k or _DEFAULT_STREAM_K
     g.dropout_p, g.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     with _Timed(f"gemm_tcgen05 m={m} n={n} k={k + int(g.k1)} at={int(a_t)} bt={int(b_t)}" if _prof_detail else "gemm_tcgen05",
                 2.0 * m * n * (k + int(g.k1))):

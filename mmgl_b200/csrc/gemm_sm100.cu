@@ -52,7 +52,9 @@ struct GemmParams {
   // stream-K tail of the CTA-pair kernel: tiles [0, sk_full) run data-parallel (whole K per tile); each of the last
   // sk_tail tiles is cut into sk_split K-slices owned by different CTA pairs; slices > 0 park their fp32 partial tile in
   // sk_ws and bump sk_flags[tile]; slice 0 adds them in and runs the epilogue.  sk_split <= 1: plain data-parallel.
-  int32_t sk_full, sk_split, sk_tail;
+  // sk_park_all (skinny outputs): EVERY slice parks its partial and splitk_reduce_kernel sums them and runs the epilogue,
+  // so the fix-up is parallel over the output instead of serial in the owner's 512 threads.
+  int32_t sk_full, sk_split, sk_tail, sk_park_all;
   float* sk_ws; int32_t* sk_flags;
   void* d; int64_t ldd; int32_t out_fp32; int32_t accumulate;
   float alpha; int32_t relu;
@@ -602,24 +604,29 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
       const int row_in_tile = (int)rank * BM + quarter * 32 + lane;
       const int64_t row = (int64_t)mt * 256 + row_in_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      const int others = (w.tail >= 0) ? p.sk_split - 1 : 0;
-      if (w.slice > 0) {
-        // ---- stream-K contributor: park the raw fp32 partial tile, then signal the owner
-        float* dst = p.sk_ws + ((size_t)(w.tail * others + (w.slice - 1)) * 256 + row_in_tile) * BN;
+      const bool park_all = p.sk_park_all != 0 && w.tail >= 0;
+      const int others = (w.tail >= 0) ? (park_all ? p.sk_split : p.sk_split - 1) : 0;
+      if (w.slice > 0 || park_all) {
+        // ---- stream-K contributor: park the raw fp32 partial tile, then signal the owner (park_all: the reduce kernel
+        // that follows on the stream reads it; rows beyond M are never read)
+        float* dst = p.sk_ws + ((size_t)(w.tail * others + (park_all ? w.slice : w.slice - 1)) * 256 + row_in_tile) * BN;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (park_all && row >= p.m) continue;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             __stcg(reinterpret_cast<float4*>(dst + c * 32) + g,
                    make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                                __uint_as_float(r[4 * g + 3])));
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.sk_flags + w.tail, 1);
+        if (!park_all) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(p.sk_flags + w.tail, 1);
+        }
       } else if (others > 0) {
         // ---- stream-K owner: wait for the 16 epilogue warps of every contributor pair, add their partials
         if (lane == 0) spin_until_at_least(p.sk_flags + w.tail, 16 * others);
@@ -672,6 +679,24 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
   tc_fence_before();
   cluster_sync_all();   // nobody leaves while the peer may still signal its barriers or read its TMEM / smem
   if (warp == 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+}
+
+// Second half of a K-sliced skinny GEMM: sums the sk_split parked partial tiles of every output element in slice order
+// (deterministic) and applies the full epilogue.  One thread per output element; the outputs are small by construction.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const GemmParams p, int bn) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.m * p.n) return;
+  const int64_t row = e / p.n, col = e % p.n;
+  const int mt = (int)(row >> 8), rit = (int)(row & 255);
+  const int nt = (int)(col / bn), cit = (int)(col % bn);
+  const int tile = p.n_fastest ? mt * p.n_blocks + nt : nt * p.m_blocks_pair + mt;
+  const float* src = p.sk_ws + (((size_t)(tile - p.sk_full) * p.sk_split) * 256 + rit) * bn + cit;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < p.sk_split; ++s) acc += __ldcg(src + (size_t)s * 256 * bn);   // loads overlap, adds stay in slice order
+  const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+  epilogue_store1(p, acc, row, col, gate_t);
 }
 
 // --------------------------------------------------------------------------------------- host side
@@ -837,7 +862,8 @@ static int launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& b0, const 
   int clusters = tiles < pairs ? tiles : pairs;
   if (p.sk_split > 1) {
     clusters = p.sk_full > 0 ? pairs : p.sk_tail * p.sk_split;
-    if (cudaMemsetAsync(p.sk_flags, 0, (size_t)p.sk_tail * sizeof(int32_t), stream) != cudaSuccess) {
+    if (!p.sk_park_all &&
+        cudaMemsetAsync(p.sk_flags, 0, (size_t)p.sk_tail * sizeof(int32_t), stream) != cudaSuccess) {
       set_error("mmgl_gemm_bf16(pair): cudaMemsetAsync of the stream-K flags failed");
       return 3;
     }
@@ -857,7 +883,11 @@ static int launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& b0, const 
     set_error("mmgl_gemm_bf16(pair): launch failed: %s", cudaGetErrorString(e));
     return 1;
   }
-  return check_launch("mmgl_gemm_bf16(pair)");
+  const int rc = check_launch("mmgl_gemm_bf16(pair)");
+  if (rc != 0 || !p.sk_park_all || p.sk_split <= 1) return rc;
+  const int64_t elems = p.m * p.n;
+  splitk_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, stream>>>(p, BN);
+  return check_launch("mmgl_gemm_bf16(split-K reduce)");
 }
 
 template <int BN>
@@ -906,9 +936,19 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
 
   // CTA-pair kernel: 256 x {128,256} tiles.  pair = 0: heuristic, 1: never, 2: always (tests, tuning)
   bool use_pair = false;
+  // Skinny output over a long K (the rank-r LoRA weight gradients: 64 x 768 over 4608 tokens): the data-parallel
+  // schedule occupies 6 of 148 SMs; with stream_k == 2 every tile is cut into K-slices and a reduce kernel sums them.
+  // Opt-in: alone and L2-cold 30 -> 19.5 us per GEMM, but inside the cfg3 step (operands warm in L2, two launches instead
+  // of one) the gain was within run-to-run noise on B200, so the default schedule stays data-parallel.
+  const int64_t kblocks_all = (a->k0 + BK - 1) / BK + (a->k1 + BK - 1) / BK;
+  const bool skinny = a->pair == 0 && a->force_block_n == 0 && a->stream_k == 2 && a->workspace != nullptr &&
+                      ((a->m + 127) / 128) * ((a->n + 127) / 128) * 8 <= sms && kblocks_all >= 32;
   if (a->pair == 2) {
     use_pair = true;
     if (bn != 128) bn = 256;
+  } else if (skinny) {
+    use_pair = true;
+    bn = 128;
   } else if (a->pair == 0 && a->force_block_n == 0) {
     use_pair = pick_pair(a->m, a->n, sms, &bn, a->stream_k == 2 && a->workspace != nullptr);
   }
@@ -920,18 +960,24 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   p.m_blocks = (int32_t)((a->m + BM - 1) / BM);
   p.n_blocks = (int32_t)((a->n + bn - 1) / bn);
   p.m_blocks_pair = (int32_t)((a->m + 255) / 256);
-  p.sk_full = 0; p.sk_split = 1; p.sk_tail = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
-  if (use_pair && a->stream_k == 2 && a->workspace != nullptr) {
+  p.sk_full = 0; p.sk_split = 1; p.sk_tail = 0; p.sk_park_all = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
+  if (use_pair && (a->stream_k == 2 || skinny) && a->workspace != nullptr) {
     const int pairs = sms / 2;
     const int tiles = p.m_blocks_pair * p.n_blocks;
     const int full = (tiles / pairs) * pairs, r = tiles - full;
     const int kblocks = p.kblocks0 + p.kblocks1;
     int split = (r > 0) ? pairs / r : 1;
     if (split > kblocks) split = kblocks;
-    if (split > 8) split = 8;
-    const size_t need = kSkFlagBytes + (size_t)r * (split > 1 ? split - 1 : 0) * 256 * bn * sizeof(float);
+    if (skinny) {
+      if (split > kblocks / 4) split = kblocks / 4;     // at least 4 k-blocks per slice
+      if (split > 12) split = 12;
+    } else if (split > 8) {
+      split = 8;
+    }
+    const bool park_all = skinny && full == 0;
+    const size_t need = kSkFlagBytes + (size_t)r * (split > 1 ? split - (park_all ? 0 : 1) : 0) * 256 * bn * sizeof(float);
     if (split >= 2 && (size_t)a->workspace_bytes >= need && aligned16(a->workspace)) {
-      p.sk_full = full; p.sk_split = split; p.sk_tail = r;
+      p.sk_full = full; p.sk_split = split; p.sk_tail = r; p.sk_park_all = park_all ? 1 : 0;
       p.sk_flags = reinterpret_cast<int32_t*>(a->workspace);
       p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + kSkFlagBytes);
     }

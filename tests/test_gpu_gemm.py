@@ -85,6 +85,31 @@ def test_gemm_stream_k_tail(m, n, k, a_t, b_t):
     assert_close("epilogue", out16, torch.relu(ref + bias) + res.float(), TOL_BF16)
 
 
+@pytest.mark.parametrize("m,n,k,a_t,b_t", [
+    (64, 768, 4608, True, True),        # LoRA dA = dt^T x: 6 tiles of 148 SMs without the split
+    (768, 64, 4608, True, True),        # LoRA dB = dy^T t
+    (64, 768, 4608, False, False),
+    (104, 200, 2048 + 40, True, False),  # ragged everything (strides stay 16-byte multiples), K tail in the last slice
+])
+def test_gemm_skinny_output_is_split_along_k(m, n, k, a_t, b_t):
+    """stream_k=2 with the tile heuristic: few output tiles over a long K run as K-slices (every slice parks its partial,
+    a reduce kernel sums them and runs the epilogue); the result must equal the data-parallel schedule, fp32 and bf16
+    outputs, with a scaled epilogue."""
+    gen = torch.Generator().manual_seed(m * 3 + n + k)
+    a_s, b_s, a, b = _operands(gen, m, n, k, a_t, b_t)
+    ref = a @ b.t()
+    for _ in range(2):                  # second launch: the slice flags were reset
+        out = torch.full((m, n), float("nan"), dtype=torch.float32, device="cuda")
+        _K().gemm(a_s, b_s, out, a_t=a_t, b_t=b_t, alpha=0.5, stream_k=2)
+        assert_close("split", out, 0.5 * ref, TOL_F32)
+    plain = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    _K().gemm(a_s, b_s, plain, a_t=a_t, b_t=b_t, alpha=0.5, stream_k=1)
+    assert_close("split vs data-parallel", out, plain, TOL_F32)
+    out16 = torch.empty((m, n), dtype=BF16, device="cuda")
+    _K().gemm(a_s, b_s, out16, a_t=a_t, b_t=b_t, stream_k=2)
+    assert_close("bf16", out16, ref, TOL_BF16)
+
+
 def test_gemm_cta_pair_epilogue_and_second_operand():
     gen = torch.Generator().manual_seed(77)
     m, n, k0, k1 = 700, 512, 256, 64

@@ -145,6 +145,21 @@ def bench_rowops():
                       "GBs": round(rows * 8192 * 2 / med / 1e6, 1)}), flush=True)
 
 
+def bench_skinny_gemm():
+    """Rank-64 LoRA weight gradients of T5-base at batch 8 (4608 encoder tokens): K-sliced (stream_k=2) vs data-parallel (default)."""
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for label, m, n, k in [("lora dA", 64, 768, 4608), ("lora dB", 768, 64, 4608), ("lora dA dec", 64, 768, 1024),
+                           ("opt lora dA", 64, 2048, 5120)]:
+        a = torch.randn(k, m, device="cuda", generator=gen).to(BF16)
+        b = torch.randn(k, n, device="cuda", generator=gen).to(BF16)
+        out = torch.empty(m, n, dtype=torch.float32, device="cuda")
+        r = {"kernel": "skinny_gemm", "label": label, "m": m, "n": n, "k": k}
+        for name, sk in (("k_sliced", 2), ("data_parallel", 1)):
+            med, _ = time_it(lambda: K.gemm(a, b, out, a_t=True, b_t=True, stream_k=sk))
+            r[name + "_us"] = round(med * 1e3, 1)
+        print(json.dumps(r), flush=True)
+
+
 def bench_encoder_gemm():
     """short-K GEMMs of the frozen RoBERTa / CLIP encoders: activation cost in the epilogue, tile choices"""
     for m, n, k, label in [(21504, 3072, 768, "roberta fc1"), (21504, 2304, 768, "roberta qkv"), (21504, 768, 3072, "roberta fc2"),
@@ -189,6 +204,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
     if "gemm" in which:
         bench_gemm()
+    if "skinny" in which:
+        bench_skinny_gemm()
     if "epilogue" in which:
         bench_epilogue()
     if "encoder" in which:
