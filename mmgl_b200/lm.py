@@ -109,17 +109,18 @@ def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0):
     bias = t5_rel_bias(self0, s, s)                      # shared by every layer of the stack (:768-774)
     for block in stack.block:
         sa = block.layer[0]
-        xn = ops.rms_norm(h, sa.layer_norm.weight, eps)
+        xn, h = ops.rms_norm_fork(h, sa.layer_norm.weight, eps)     # (norm, residual): one backward kernel for both
         a = _t5_attention(sa.SelfAttention, xn, xn, key_mask, bias, stack.is_decoder, p)
         h = ops.linear(a, _weight(sa.SelfAttention.o), None, residual=h, dropout_p=p)
         if stack.is_decoder:
             ca = block.layer[1]
-            a = _t5_attention(ca.EncDecAttention, ops.rms_norm(h, ca.layer_norm.weight, eps), enc, enc_mask, None, False, p)
+            xn, h = ops.rms_norm_fork(h, ca.layer_norm.weight, eps)
+            a = _t5_attention(ca.EncDecAttention, xn, enc, enc_mask, None, False, p)
             h = ops.linear(a, _weight(ca.EncDecAttention.o), None, residual=h, dropout_p=p)
         ff = block.layer[-1]
         dense = ff.DenseReluDense
-        h = ops.mlp(ops.rms_norm(h, ff.layer_norm.weight, eps), dense.wi.weight, None, dense.wo.weight, None, residual=h,
-                    dropout_p=p, hidden_dropout_p=p)
+        xn, h = ops.rms_norm_fork(h, ff.layer_norm.weight, eps)
+        h = ops.mlp(xn, dense.wi.weight, None, dense.wo.weight, None, residual=h, dropout_p=p, hidden_dropout_p=p)
     return ops.dropout(ops.rms_norm(h, stack.final_layer_norm.weight, eps), p)
 
 
@@ -206,7 +207,7 @@ def opt_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, lab
     for li, layer in enumerate(dec.layers):
         a = layer.self_attn
         ln1, ln2 = layer.self_attn_layer_norm, layer.final_layer_norm
-        x = ops.layer_norm(h, ln1.weight, ln1.bias, ln1.eps) if layer.do_layer_norm_before else h
+        x, h = ops.layer_norm_fork(h, ln1.weight, ln1.bias, ln1.eps) if layer.do_layer_norm_before else (h, h)
         if n_pre:
             pk = prefix_kv[:, li, 0].to(BF16)[None].expand(b, -1, -1)
             pv = prefix_kv[:, li, 1].to(BF16)[None].expand(b, -1, -1)
@@ -219,7 +220,7 @@ def opt_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, lab
         h = ops.linear(o, a.out_proj.weight, a.out_proj.bias, residual=h, dropout_p=p)
         if not layer.do_layer_norm_before:
             h = ops.layer_norm(h, ln1.weight, ln1.bias, ln1.eps)
-        x = ops.layer_norm(h, ln2.weight, ln2.bias, ln2.eps) if layer.do_layer_norm_before else h
+        x, h = ops.layer_norm_fork(h, ln2.weight, ln2.bias, ln2.eps) if layer.do_layer_norm_before else (h, h)
         h = ops.mlp(x, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias, residual=h, dropout_p=p)
         if not layer.do_layer_norm_before:
             h = ops.layer_norm(h, ln2.weight, ln2.bias, ln2.eps)

@@ -216,10 +216,10 @@ class MPTDecoderLayer(nn.Module):
             return (y,)
         x = hidden_states
         if self.do_layer_norm_before:
-            h = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
-            h1, _, _ = a(h, attention_mask=attention_mask, residual=x, dropout_p=p)
-            f_in = ops.layer_norm(h1, ln2.weight, ln2.bias, ln2.eps)
-            y = ops.mlp(f_in, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=h1, dropout_p=p)
+            h, x_res = ops.layer_norm_fork(x, ln1.weight, ln1.bias, ln1.eps)
+            h1, _, _ = a(h, attention_mask=attention_mask, residual=x_res, dropout_p=p)
+            f_in, h1_res = ops.layer_norm_fork(h1, ln2.weight, ln2.bias, ln2.eps)
+            y = ops.mlp(f_in, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=h1_res, dropout_p=p)
         else:
             u, _, _ = a(x, attention_mask=attention_mask, residual=x, dropout_p=p)
             h1 = ops.layer_norm(u, ln1.weight, ln1.bias, ln1.eps)

@@ -283,6 +283,37 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
 
 
+class LayerNormForkFn(torch.autograd.Function):
+    """The fork at the top of a pre-LN residual block: returns (LayerNorm(x), x).  Feeding the second output to the
+    residual input of the block's last GEMM makes both gradients of x -- through the norm and through the residual --
+    arrive at THIS backward, where one kernel forms dx = d_res + LN'(dy); autograd would otherwise add them in a separate
+    pass over [rows, H] (41 such adds per cfg2 step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x2 = _as2d(x)
+        y, mean, rstd = _ln_fwd(x2, f32(weight), f32(bias), eps)
+        ctx.save_for_backward(x2, weight, bias, mean, rstd)
+        ctx.x_shape = x.shape
+        ctx.set_materialize_grads(False)
+        return y.reshape(x.shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, d_res):
+        x2, weight, bias, mean, rstd = ctx.saved_tensors
+        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dy2 = torch.zeros_like(x2) if dy is None else _as2d(dy)
+        dx, dg, db = _ln_bwd(dy2, x2, f32(weight), mean, rstd, None if d_res is None else _as2d(d_res), want, weight, bias)
+        return dx.reshape(ctx.x_shape), dg, db, None
+
+
+def layer_norm_fork(x, weight, bias, eps=1e-5):
+    """(LayerNorm(x), x): use the second value as the block's residual (see LayerNormForkFn)."""
+    if x.dtype != BF16:
+        return layer_norm(x, weight, bias, eps), x
+    return LayerNormForkFn.apply(x, weight, bias, eps)
+
+
 class RMSNormFn(torch.autograd.Function):
     """T5LayerNorm (HF models/t5/modeling_t5.py:46-70): y = weight * x * rsqrt(mean(x^2) + eps), fp32 statistics."""
 
@@ -309,6 +340,38 @@ class RMSNormFn(torch.autograd.Function):
 
 def rms_norm(x, weight, eps=1e-6):
     return RMSNormFn.apply(x, weight, float(eps))
+
+
+class RMSNormForkFn(torch.autograd.Function):
+    """(RMSNorm(x), x) for the pre-norm residual blocks of T5: see LayerNormForkFn."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        x2 = _as2d(x)
+        y = torch.empty_like(x2)
+        rstd = torch.empty(x2.shape[0], dtype=F32, device=x2.device)
+        K.rmsnorm_fwd(x2, f32(weight), y, rstd, eps)
+        ctx.save_for_backward(x2, weight, rstd)
+        ctx.x_shape = x.shape
+        ctx.set_materialize_grads(False)
+        return y.reshape(x.shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, d_res):
+        x2, weight, rstd = ctx.saved_tensors
+        dx = torch.empty_like(x2)
+        dg = torch.empty(x2.shape[1], dtype=F32, device=x2.device) if ctx.needs_input_grad[1] else None
+        dy2 = torch.zeros_like(x2) if dy is None else _as2d(dy)
+        K.rmsnorm_bwd(dy2, x2, f32(weight), rstd, None if d_res is None else _as2d(d_res), dx, dg)
+        if dg is not None and weight.dtype != F32:
+            dg = dg.to(weight.dtype)
+        return dx.reshape(ctx.x_shape), dg, None
+
+
+def rms_norm_fork(x, weight, eps=1e-6):
+    if x.dtype != BF16:
+        return rms_norm(x, weight, eps), x
+    return RMSNormForkFn.apply(x, weight, float(eps))
 
 
 class DropoutFn(torch.autograd.Function):

@@ -261,6 +261,47 @@ def test_rmsnorm_fwd_bwd(rows, hidden):
     assert_close("dw", w.grad, wr.grad, 1e-2)
 
 
+@pytest.mark.parametrize("kind", ["layer", "rms"])
+def test_norm_fork_fuses_the_residual_gradient(kind):
+    """(norm(x), x) fork of a pre-norm residual block (modelling_cross_attention.py:318-337 pattern: h = x + f(LN(x))):
+    the gradient of x must equal autograd's sum of the norm branch and the residual branch."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    rows, hidden = 150, 768
+    x = (randn(gen, 2, rows // 2, hidden) * 1.5 + 0.3).to(BF16)
+    w = (1 + 0.2 * randn(gen, hidden)).requires_grad_(True)
+    b = (0.1 * randn(gen, hidden)).requires_grad_(True)
+    d1 = randn(gen, 2, rows // 2, hidden).to(BF16)
+    d2 = randn(gen, 2, rows // 2, hidden).to(BF16)
+    xg = x.clone().requires_grad_(True)
+    if kind == "layer":
+        y, r = ops.layer_norm_fork(xg, w, b, 1e-5)
+    else:
+        y, r = ops.rms_norm_fork(xg, w, 1e-6)
+    assert r.data_ptr() == xg.data_ptr()
+    torch.autograd.backward([y, r], [d1, d2])
+    xr = x.float().cpu().requires_grad_(True)
+    wr = w.detach().float().cpu().requires_grad_(True)
+    if kind == "layer":
+        yr = F.layer_norm(xr, (hidden,), wr, b.detach().float().cpu(), 1e-5)
+    else:
+        yr = wr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    torch.autograd.backward([yr, xr * 1.0], [d1.float().cpu(), d2.float().cpu()])
+    assert_close("y", y, yr, 4e-3)
+    assert_close("dx", xg.grad, xr.grad, 1e-2)
+    assert_close("dw", w.grad, wr.grad, 1e-2)
+    # residual branch unused: only the norm gradient
+    xg2 = x.clone().requires_grad_(True)
+    y2, _ = ops.layer_norm_fork(xg2, w, b, 1e-5) if kind == "layer" else ops.rms_norm_fork(xg2, w, 1e-6)
+    y2.backward(d1)
+    xr2 = x.float().cpu().requires_grad_(True)
+    if kind == "layer":
+        F.layer_norm(xr2, (hidden,), wr.detach(), b.detach().float().cpu(), 1e-5).backward(d1.float().cpu())
+    else:
+        (wr.detach() * (xr2 * torch.rsqrt(xr2.pow(2).mean(-1, keepdim=True) + 1e-6))).backward(d1.float().cpu())
+    assert_close("dx (no residual)", xg2.grad, xr2.grad, 1e-2)
+
+
 def test_mlp_with_hidden_dropout_matches_reference_semantics():
     """T5DenseActDense + T5LayerFF: y = r + drop2(wo(drop1(relu(wi(x))))) with both masks from the counter-based RNG
     (restated in oracle.dropout_multiplier); both dropouts and the ReLU live in GEMM epilogues."""
