@@ -261,6 +261,43 @@ def test_rmsnorm_fwd_bwd(rows, hidden):
     assert_close("dw", w.grad, wr.grad, 1e-2)
 
 
+@pytest.mark.parametrize("rows,hidden,kind", [(4741, 2048, "layer"), (4800, 768, "rms"), (4737, 4096, "layer"),
+                                              (9000, 128, "rms")])
+def test_staged_norm_backward_at_large_row_counts(rows, hidden, kind):
+    """Above 4736 rows the norm backward runs as persistent CTAs fed by a cp.async.bulk shared-memory ring (ragged last
+    tile, 2-6 stages by row size; hidden 4096 falls back to the register-resident kernel): dx must equal torch fp32 to
+    the bf16 tolerances of the small-shape tests, with and without a residual gradient; the forward at these sizes too."""
+    from mmgl_b200 import _capi as K
+    gen = torch.Generator().manual_seed(rows + hidden)
+    x = (randn(gen, rows, hidden) * 2 + 0.5).to(BF16)
+    g = 1 + 0.2 * randn(gen, hidden)
+    b = 0.1 * randn(gen, hidden)
+    dy = randn(gen, rows, hidden).to(BF16)
+    res = randn(gen, rows, hidden).to(BF16)
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device="cuda") if kind == "layer" else None
+    rstd = torch.empty(rows, device="cuda")
+    xr = x.float().requires_grad_(True)
+    if kind == "layer":
+        K.layernorm_fwd(x, g, b, y, mean, rstd, 1e-5)
+        yr = F.layer_norm(xr, (hidden,), g, b, 1e-5)
+        assert_close("mean", mean, xr.detach().mean(-1), 1e-3)
+    else:
+        K.rmsnorm_fwd(x, g, y, rstd, 1e-6)
+        yr = g * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert_close("y", y, yr, 4e-3)
+    yr.backward(dy.float())
+    for r in (None, res):
+        dx = torch.full_like(x, float("nan"))
+        if kind == "layer":
+            K.layernorm_bwd(dy, x, g, mean, rstd, r, dx)
+        else:
+            K.rmsnorm_bwd(dy, x, g, rstd, r, dx)
+        want = xr.grad if r is None else xr.grad + r.float()
+        assert_close("dx" + ("" if r is None else " + d_res"), dx, want, 1e-2)
+        assert bool(torch.isfinite(dx.float()).all())
+
+
 @pytest.mark.parametrize("kind", ["layer", "rms"])
 def test_norm_fork_fuses_the_residual_gradient(kind):
     """(norm(x), x) fork of a pre-norm residual block (modelling_cross_attention.py:318-337 pattern: h = x + f(LN(x))):

@@ -145,6 +145,27 @@ def bench_rowops():
                       "GBs": round(rows * 8192 * 2 / med / 1e6, 1)}), flush=True)
 
 
+def bench_norm():
+    """LayerNorm forward / backward(dx) at the step's shapes; run with MMGL_NORM_STAGED=0 for the register-resident backward."""
+    for rows, hidden in [(10240, 2048), (5120, 2048), (4608, 768)]:
+        x = torch.randn(rows, hidden, device="cuda").to(BF16)
+        g = torch.ones(hidden, device="cuda")
+        bta = torch.zeros(hidden, device="cuda")
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, device="cuda")
+        rstd = torch.empty(rows, device="cuda")
+        dx = torch.empty_like(x)
+        res = torch.randn(rows, hidden, device="cuda").to(BF16)
+        r = {"kernel": "norm", "staged": os.environ.get("MMGL_NORM_STAGED", "1"), "rows": rows, "hidden": hidden}
+        med, _ = time_it(lambda: K.layernorm_fwd(x, g, bta, y, mean, rstd, 1e-5))
+        r["fwd_us"], r["fwd_GBs"] = round(med * 1e3, 1), round(2 * rows * hidden * 2 / med / 1e6)
+        med, _ = time_it(lambda: K.layernorm_bwd(y, x, g, mean, rstd, None, dx))
+        r["bwd_us"], r["bwd_GBs"] = round(med * 1e3, 1), round(3 * rows * hidden * 2 / med / 1e6)
+        med, _ = time_it(lambda: K.layernorm_bwd(y, x, g, mean, rstd, res, dx))
+        r["bwd_res_us"], r["bwd_res_GBs"] = round(med * 1e3, 1), round(4 * rows * hidden * 2 / med / 1e6)
+        print(json.dumps(r), flush=True)
+
+
 def bench_skinny_gemm():
     """Rank-64 LoRA weight gradients of T5-base at batch 8 (4608 encoder tokens): K-sliced (stream_k=2) vs data-parallel (default)."""
     gen = torch.Generator(device="cuda").manual_seed(0)
@@ -204,6 +225,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "xattn", "rowops"]
     if "gemm" in which:
         bench_gemm()
+    if "norm" in which:
+        bench_norm()
     if "skinny" in which:
         bench_skinny_gemm()
     if "epilogue" in which:
