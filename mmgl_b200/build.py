@@ -25,6 +25,22 @@ def _digest():
     return h.hexdigest()
 
 
+def _stable_order(out: str) -> str:
+    """ptxas -v reports the kernels of a file in a different order on every run; sort the per-kernel blocks by name so
+    the committed lib/ptxas.log only changes when register / shared-memory use does."""
+    head, blocks = [], []
+    for line in out.splitlines():
+        if "Compile time" in line:
+            continue
+        if "Compiling entry function" in line:
+            blocks.append([line])
+        elif blocks and line.startswith(("ptxas info", "    ")):
+            blocks[-1].append(line)
+        else:
+            head.append(line)
+    return "\n".join(head + [ln for b in sorted(blocks, key=lambda b: b[0]) for ln in b]) + "\n"
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, "build.sha256")
@@ -41,7 +57,7 @@ def build(force=False, verbose=False):
     log = []
     for src, p in procs:
         out, _ = p.communicate()
-        log.append(f"==== {src}\n{out}")
+        log.append(f"==== {src}\n{_stable_order(out)}")
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
