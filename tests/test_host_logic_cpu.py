@@ -71,3 +71,68 @@ def test_lm_output_is_indexable_like_hf_outputs():
     out = LMOutput(loss=loss, logits=logits)
     assert out.loss is loss and out["logits"] is logits and out[0] is loss and out[1] is logits
     assert LMOutput(logits=logits)[0] is logits
+
+
+def test_apply_lora_adapts_q_and_v_of_every_attention_and_keeps_peft_key_names():
+    """Intent of model/modelling_self_attention.py:79-87: rank-r adapters on the q and v projections of every
+    attention of the LM, base weights frozen, B = 0 at init (the adapted model starts as the base model), state-dict
+    keys in peft's layout (`<path>.base_layer.weight`, `<path>.lora_A.default.weight`, `<path>.lora_B.default.weight`)."""
+    from transformers import OPTConfig, OPTForCausalLM, T5Config, T5ForConditionalGeneration
+    from mmgl_b200.self_attention import LoRALinear, _PeftShim, apply_lora
+    t5 = T5ForConditionalGeneration(T5Config(vocab_size=64, d_model=32, d_kv=8, d_ff=64, num_layers=2,
+                                             num_decoder_layers=2, num_heads=4, decoder_start_token_id=0))
+    n = apply_lora(t5, 4, 1.0, 0.0)
+    assert n == 2 * (2 + 2 + 2)                       # encoder self, decoder self, decoder cross: q and v each, 2 layers
+    opt = OPTForCausalLM(OPTConfig(vocab_size=64, hidden_size=32, ffn_dim=64, num_hidden_layers=3, num_attention_heads=4,
+                                   max_position_embeddings=32, word_embed_proj_dim=32))
+    assert apply_lora(opt, 4, 1.0, 0.0) == 2 * 3
+    for model in (t5, opt):
+        adapted = [(k, m) for k, m in model.named_modules() if isinstance(m, LoRALinear)]
+        for name, m in adapted:
+            assert name.rsplit(".", 1)[-1] in ("q", "v", "q_proj", "v_proj")
+            assert not any(p.requires_grad for p in m.base_layer.parameters())
+            assert m.lora_A["default"].weight.shape == (4, m.base_layer.in_features)
+            assert float(m.lora_B["default"].weight.detach().abs().max()) == 0.0
+            assert m.scaling == 0.25
+        keys = _PeftShim(model).state_dict().keys()
+        name = adapted[0][0]
+        for suffix in ("base_layer.weight", "lora_A.default.weight", "lora_B.default.weight"):
+            assert f"base_model.model.{name}.{suffix}" in keys
+
+
+def test_peft_shim_prompt_and_prefix_tables_have_pefts_shapes():
+    """Prompt tuning: Embedding(20, hidden); prefix tuning (OPT): Embedding(20, layers * 2 * hidden), both under
+    `prompt_encoder.default.embedding` (peft's PromptEmbedding / PrefixEncoder without projection); T5 prefix tuning is
+    declared unsupported instead of silently doing something else."""
+    from transformers import OPTConfig, OPTForCausalLM, T5Config, T5ForConditionalGeneration
+    from mmgl_b200.self_attention import _PeftShim
+    opt = OPTForCausalLM(OPTConfig(vocab_size=64, hidden_size=32, ffn_dim=64, num_hidden_layers=3, num_attention_heads=4,
+                                   max_position_embeddings=32, word_embed_proj_dim=32))
+    assert _PeftShim(opt, prompt_tokens=20).state_dict()["prompt_encoder.default.embedding.weight"].shape == (20, 32)
+    assert _PeftShim(opt, prefix_tokens=20).state_dict()["prompt_encoder.default.embedding.weight"].shape == (20, 3 * 2 * 32)
+    t5 = T5ForConditionalGeneration(T5Config(vocab_size=64, d_model=32, d_kv=8, d_ff=64, num_layers=1,
+                                             num_decoder_layers=1, num_heads=4, decoder_start_token_id=0))
+    with pytest.raises(NotImplementedError):
+        _PeftShim(t5, prefix_tokens=20)
+
+
+def test_lm_support_matrix():
+    """lm.supports: HF T5 (ReLU FFN, head dim 64 / 128) and OPT run on the package's kernels; gated-GELU T5 and other
+    head dims go to the HF forward."""
+    from transformers import OPTConfig, OPTForCausalLM, T5Config, T5ForConditionalGeneration
+    from mmgl_b200 import lm as L
+
+    def t5(**kw):
+        base = dict(vocab_size=64, d_model=128, d_kv=64, d_ff=64, num_layers=1, num_decoder_layers=1, num_heads=2,
+                    decoder_start_token_id=0)
+        base.update(kw)
+        return T5ForConditionalGeneration(T5Config(**base))
+
+    assert L.supports(t5())
+    assert L.supports(t5(d_kv=128))
+    assert not L.supports(t5(d_kv=32))
+    assert not L.supports(t5(feed_forward_proj="gated-gelu"))
+    opt = OPTForCausalLM(OPTConfig(vocab_size=64, hidden_size=128, ffn_dim=64, num_hidden_layers=1, num_attention_heads=2,
+                                   max_position_embeddings=32, word_embed_proj_dim=128))
+    assert L.supports(opt)
+    assert not L.supports(torch.nn.Linear(4, 4))
