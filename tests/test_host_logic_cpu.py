@@ -1,5 +1,7 @@
 """Host-side logic of the product path that needs no GPU: index / bucket arithmetic that the CUDA kernels are driven by.
 Integer work: bit-exact.  (The kernels themselves are covered by the `-m gpu` tests.)"""
+import types
+
 import pytest
 import torch
 
@@ -136,3 +138,35 @@ def test_lm_support_matrix():
                                    max_position_embeddings=32, word_embed_proj_dim=128))
     assert L.supports(opt)
     assert not L.supports(torch.nn.Linear(4, 4))
+
+
+def test_cfg2_interleave_positions_and_trainable_parameter_count():
+    """MPTDecoder interleave loop (model/modelling_cross_attention.py:576-627) at the cfg2 dimensions (OPT-1.3B, 4
+    neighbor layers), built on the meta device: one gated cross-attention layer follows each of OPT layers 5 / 11 / 17 /
+    23, only they train (`mark_only_peft_as_trainable`, :731-737), lm_head is tied to the embedding (D12), and
+    the gradient set DDP all-reduces adds up to the 216,736,520 parameters SURVEY 8 (a11) counts."""
+    from transformers import OPTConfig
+    from mmgl_b200 import modules as M
+    opt_cfg = OPTConfig(vocab_size=50272, hidden_size=2048, ffn_dim=8192, num_hidden_layers=24, num_attention_heads=32,
+                        max_position_embeddings=2048, word_embed_proj_dim=2048)
+    args = types.SimpleNamespace(neighbor_layer_wise=None, num_neighbor_layers=4, neighbor_mode="cross_attention",
+                                 peft_type="flamingo", lora_r=64, lora_alpha=1, lora_dropout=0.0)
+    with torch.device("meta"):
+        model = M.MPTForCausalLM(M.MPTConfig(args, opt_cfg))
+    layers = [m for m in model.modules() if isinstance(m, M.MPTDecoderLayer)]
+    cross = [m for m in layers if m.cross_attention]
+    assert len(layers) - len(cross) == 24 and len(cross) == 4
+    assert model.lm_head.weight is model.model.decoder.embed_tokens.weight
+    trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    # 4 gated layers x 50,358,274 (SURVEY 8 a2: "50.36 M params / layer"); the wrapper adds the two neighbor projections
+    # Linear(768 -> 4 x 2048), their two Embedding(129, 8192) position tables and the TextPooler dense = 15,303,424
+    per_layer = sum(p.numel() for p in cross[0].parameters())
+    assert per_layer == 50_358_274 and trainable == 4 * per_layer
+    wrapper = 2 * (768 * 8192 + 8192) + 2 * 129 * 8192 + (768 * 768 + 768)
+    assert trainable + wrapper == 216_736_520
+    assert all(p.requires_grad for m in cross for p in m.parameters())
+    assert not any(p.requires_grad for m in layers if not m.cross_attention for p in m.parameters())
+    # D1: the CLI defines only num_neighbor_layers; one gated layer follows every 24 / 4 = 6th OPT layer (indices 5..23)
+    dec = model.model.decoder
+    assert dec.neighbor_layer_wise == 6 and len(dec.layers) == 24 and len(dec.neighbor_layers) == 4
+    assert [i for i in range(24) if (i + 1) % dec.neighbor_layer_wise == 0] == [5, 11, 17, 23]
