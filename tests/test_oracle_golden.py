@@ -162,3 +162,73 @@ def test_t5_relative_position_bias_matches_hf():
             assert torch.equal(vec[:, idx][None], dense.detach()), (is_decoder, sq, sk)
             ref = O.t5_position_bias(attn.relative_attention_bias.weight.detach(), sq, sk, not is_decoder)
             assert torch.equal(ref, dense.detach())
+
+
+def _additive_mask(key_mask, sq, causal):
+    """[B,1,Sq,Sk] additive fp32 mask the way HF builds it: finfo.min where a key is padding or (causal) in the future."""
+    b, sk = key_mask.shape
+    allowed = key_mask[:, None, None, :].bool().expand(b, 1, sq, sk)
+    if causal:
+        allowed = allowed & torch.tril(torch.ones(sq, sk, dtype=torch.bool))[None, None]
+    return torch.zeros(b, 1, sq, sk).masked_fill(~allowed, torch.finfo(torch.float32).min)
+
+
+@pytest.mark.parametrize("decoder", [False, True])
+def test_attention_core_matches_hf_t5_attention(decoder):
+    """oracle.attention_core (the checker of the self-attention kernels) against the HF module it restates, run here in
+    fp32: T5Attention.forward (HF models/t5/modeling_t5.py:253-345) -- unscaled scores + bucketed position bias + mask,
+    encoder (bidirectional) and decoder (causal) self-attention with key padding, forward and input gradient."""
+    from transformers import T5Config
+    from transformers.models.t5.modeling_t5 import T5Attention
+    torch.manual_seed(1 + decoder)
+    cfg = T5Config(d_model=64, d_kv=16, num_heads=4, is_decoder=decoder, dropout_rate=0.0)
+    attn = T5Attention(cfg, has_relative_attention_bias=True, layer_idx=0).eval()
+    with torch.no_grad():
+        attn.relative_attention_bias.weight.normal_()
+    b, s = 2, 50
+    x = torch.randn(b, s, 64, requires_grad=True)
+    key_mask = torch.ones(b, s, dtype=torch.long)
+    key_mask[0, 41:] = 0
+    key_mask[1, 20:27] = 0
+    d_o = torch.randn(b, s, 64)
+    ref = attn(x, mask=_additive_mask(key_mask, s, decoder))[0]
+    ref.backward(d_o)
+    want_dx = x.grad.clone()
+    x.grad = None
+    bias = O.t5_position_bias(attn.relative_attention_bias.weight.detach(), s, s, not decoder)
+    q, k, v = (lin(x) for lin in (attn.q, attn.k, attn.v))
+    got = attn.o(O.attention_core(q, k, v, 4, 1.0, key_mask.bool(), decoder, bias))
+    got.backward(d_o)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(x.grad, want_dx, rtol=1e-4, atol=1e-5)
+
+
+def test_attention_core_matches_hf_opt_attention():
+    """... and OPTAttention.forward (HF models/opt/modeling_opt.py:74-182; the self branch of MPTAttention,
+    model/modelling_cross_attention.py:201-275, is its copy): q scaled by d^-1/2, causal + key-padding additive mask."""
+    from transformers import OPTConfig
+    from transformers.models.opt.modeling_opt import OPTAttention
+    torch.manual_seed(3)
+    cfg = OPTConfig(hidden_size=64, num_attention_heads=4, ffn_dim=128, num_hidden_layers=1, dropout=0.0,
+                    attention_dropout=0.0)
+    cfg._attn_implementation = "eager"
+    attn = OPTAttention(cfg, layer_idx=0).eval()
+    b, s = 2, 45
+    x = torch.randn(b, s, 64, requires_grad=True)
+    key_mask = torch.ones(b, s, dtype=torch.long)
+    key_mask[0, :6] = 0                                  # left padding: the first rows attend nothing but padding
+    key_mask[1, 30:] = 0
+    d_o = torch.randn(b, s, 64)
+    ref = attn(x, attention_mask=_additive_mask(key_mask, s, True))[0]
+    # rows whose every allowed key is padding are uniform over ALL keys in both (finfo.min ties); they carry no loss in
+    # the model, compare the rest
+    rows = torch.ones(b, s, dtype=torch.bool)
+    rows[0, :6] = False
+    (ref * rows[..., None]).backward(d_o)
+    want_dx = x.grad.clone()
+    x.grad = None
+    q, k, v = attn.q_proj(x), attn.k_proj(x), attn.v_proj(x)
+    got = attn.out_proj(O.attention_core(q, k, v, 4, 16 ** -0.5, key_mask.bool(), True))
+    (got * rows[..., None]).backward(d_o)
+    torch.testing.assert_close(got[rows], ref[rows], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(x.grad, want_dx, rtol=1e-4, atol=1e-5)
