@@ -49,7 +49,13 @@ int64_t mmgl_launch_count(void);
  *                  a_mn_major = 1 -> A is [K rows][M cols] (M contiguous; transposed use, e.g. wgrad).
  *                  b_mn_major likewise for B ([N][K] = nn.Linear weight layout when 0; [K][N] when 1).
  * Requirements: bf16 operands, 16-byte aligned base pointers, leading dimensions multiples of 8
- * elements.  M, N, K arbitrary (TMA zero-fills operand tails, output tails are predicated).
+ * elements (a TMA constraint: the row pitch of a tensor map is a multiple of 16 bytes).  M, N, K themselves are
+ * arbitrary (TMA zero-fills operand tails, output tails are predicated) -- but an operand stored CONTIGUOUSLY has
+ * leading dimension = its contiguous extent, so in practice: K % 8 == 0 for K-major operands, M % 8 == 0 (N % 8 == 0)
+ * for an MN-major A (B).  A caller with such a shape pads the leading dimension (e.g. a [rows][12] matrix stored with
+ * pitch 16); the call returns code 2 with a message otherwise.  Inside this package the only such contraction, the
+ * Laplacian-PE projection with K = 12 / 28 (model/modelling_self_attention.py:313), does not go through the GEMM: it
+ * is fused into mmgl_bank_pack_fwd.
  *
  * Replaces: nn.Linear / torch.bmm call sites  model/modelling_cross_attention.py:194,198-199,273,352,355
  * (and their autograd backward), :997,:1020 (neighbor projections), model/graph.py:24,29,

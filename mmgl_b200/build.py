@@ -11,7 +11,12 @@ LIB = os.path.join(LIB_DIR, "libmmgl_b200.so")
 SOURCES = ["capi.cu", "gemm_sm100.cu", "xattn.cu", "xattn_sm100.cu", "sattn_sm100.cu", "rowops.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"] + os.environ.get("MMGL_EXTRA_FLAGS", "").split()
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("MMGL_EXTRA_FLAGS", "").split()
+# --use_fast_math only where the epilogue / softmax issue rate matters and every transcendental on the path is an explicit
+# intrinsic anyway (ex2 / rcp in the attention and GELU code; the tanh of the scalar gate is common.cuh:tanh_precise).
+# rowops.cu (LayerNorm / RMSNorm statistics, cross-entropy log-sum-exp, gate-gradient reductions) is HBM-bound and is
+# compiled with IEEE division / sqrt / logf and denormals kept.
+FAST_MATH = {"gemm_sm100.cu", "xattn_sm100.cu", "sattn_sm100.cu"}
 
 
 def _digest():
@@ -21,7 +26,7 @@ def _digest():
             with open(os.path.join(root, name), "rb") as f:
                 h.update(name.encode())
                 h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(FLAGS + sorted(FAST_MATH)).encode())
     return h.hexdigest()
 
 
@@ -52,7 +57,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *(["--use_fast_math"] if src in FAST_MATH else []), "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -1,9 +1,9 @@
 """Architecture hyper-parameters of the public checkpoints BASELINE.json names, as HF config objects.
 
-There is no network and no HF cache in the build/bench images, so models are random-initialised from these
-configs (values are the published ``config.json`` of each checkpoint).  ``args.model_name_or_path`` etc. may be
-one of these names, or a local directory written by ``save_pretrained`` (then weights are loaded from it, as the
-reference does at model/modelling_cross_attention.py:953-954).
+There is no network and no HF cache in the build/bench images, so with ``MMGL_ALLOW_RANDOM_INIT=1`` (bench.py, tests)
+models are random-initialised from these configs (values are the published ``config.json`` of each checkpoint).
+Without that opt-in ``args.model_name_or_path`` etc. go through ``from_pretrained`` as in the reference
+(model/modelling_cross_attention.py:953-954) and a missing checkpoint is an error (modules._load_or_init).
 """
 from __future__ import annotations
 
@@ -26,8 +26,7 @@ def lm_config(name: str):
         return _opt(1024, 24, 16, 4096, proj=512, pre_ln=False)
     if key == "opt-1.3b":
         return _opt(2048, 24, 32, 8192)
-    if key == "opt-2.7b":
-        return _opt(2560, 32, 32, 10240)
+    # opt-2.7b (head_dim 80) is not listed: the attention kernels cover head_dim 64 / 128 only
     if key == "opt-6.7b":
         return _opt(4096, 32, 32, 16384)
     if key in ("t5-base", "t5-small", "t5-large"):

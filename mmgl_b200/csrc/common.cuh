@@ -69,6 +69,25 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// tanh of the scalar Flamingo gate (model/modelling_cross_attention.py:335, :359).  --use_fast_math turns tanhf into
+// tanh.approx (2^-11 relative error); the gates are trained from 0.0 and their gradient carries 1 - tanh^2, so this stays
+// at fp32 accuracy whatever the translation unit's flags: odd Taylor polynomial below 0.1 (error < 3e-11), otherwise
+// (e^2x - 1) / (e^2x + 1) with an IEEE reciprocal (__expf: 2 ulp of a value >= 1.22).
+__device__ __forceinline__ float tanh_precise(float x) {
+  const float ax = fabsf(x);
+  float t;
+  if (ax < 0.1f) {
+    const float x2 = ax * ax;
+    t = ax * (1.f + x2 * (-0.333333333f + x2 * (0.133333333f + x2 * -0.0539682540f)));
+  } else if (ax > 15.f) {
+    t = 1.f;
+  } else {
+    const float e = __expf(2.f * ax);
+    t = __fmul_rn(e - 1.f, __frcp_rn(e + 1.f));
+  }
+  return copysignf(t, x);
+}
+
 // ---- counter-based dropout mask ---------------------------------------------------------------
 // 16 random bits per element from splitmix64 of (seed, row, col / 8); element (row, col) is KEPT iff its 16-bit lane
 // >= thresh, thresh = round(p * 65536).  Stateless, so backward regenerates the forward mask from the seed alone

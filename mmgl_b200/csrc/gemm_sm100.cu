@@ -418,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     constexpr int kChunksPerHalf = BN / 64;
-    const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+    const float gate_t = (p.gate != nullptr) ? tanh_precise(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks) * BM;
@@ -591,7 +591,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     // ===================== epilogue warps (2..9) of both CTAs: own 128 accumulator rows, two column halves =====================
     const int quarter = warp & 3;
     const int c_begin = ((warp - 2) >> 2) * (BN / 64), c_end = c_begin + BN / 64;
-    const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+    const float gate_t = (p.gate != nullptr) ? tanh_precise(__ldg(p.gate)) : 1.f;
     int as = 0; uint32_t aphase = 0;
     PairWork w;
     for (int it = 0; pair_next_work(p, cluster, num_clusters, num_tiles, kblocks, it, w); ++it) {
@@ -695,7 +695,7 @@ splitk_reduce_kernel(const GemmParams p, int bn) {
   float acc = 0.f;
 #pragma unroll 4
   for (int s = 0; s < p.sk_split; ++s) acc += __ldcg(src + (size_t)s * 256 * bn);   // loads overlap, adds stay in slice order
-  const float gate_t = (p.gate != nullptr) ? tanhf(__ldg(p.gate)) : 1.f;
+  const float gate_t = (p.gate != nullptr) ? tanh_precise(__ldg(p.gate)) : 1.f;
   epilogue_store1(p, acc, row, col, gate_t);
 }
 

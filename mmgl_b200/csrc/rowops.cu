@@ -334,7 +334,7 @@ col_final_kernel(const float* __restrict__ partial, int chunks, int64_t n, float
     float t = 0.f;
 #pragma unroll
     for (int y = 0; y < 8; ++y) t += red[y][tx];
-    if (gate != nullptr) t *= tanhf(__ldg(gate));
+    if (gate != nullptr) t *= tanh_precise(__ldg(gate));
     t *= scale;
     out[col] = accumulate ? out[col] + t : t;
   }
@@ -377,7 +377,7 @@ gate_final_kernel(const float* __restrict__ partial, int blocks, const float* __
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int i = 0; i < 8; ++i) v += red[i];
-    const float t = tanhf(__ldg(gate));
+    const float t = tanh_precise(__ldg(gate));
     v *= (1.f - t * t);
     out[0] = accumulate ? out[0] + v : v;
   }

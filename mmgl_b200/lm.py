@@ -18,8 +18,8 @@ HF arithmetic restated (HF: models/t5/modeling_t5.py -- T5Stack.forward :637-790
 :320-400, OPTDecoderLayer :202-254).  Parity: tests/test_gpu_lm.py compares loss, logits and gradients with the HF
 modules' own fp32 forward / backward on the same weights.
 
-``supports(lm)`` says whether a model can run here; SelfAttentionModel falls back to the HF forward (library code, as in
-the reference) when it cannot: head_dim not in {64, 128}, gated-GELU T5 variants, LayerDrop.  Prefix tuning is implemented for OPT
+``supports(lm)`` says whether a model can run here; SelfAttentionModel raises when it cannot (head_dim not in {64, 128},
+gated-GELU T5 variants, LayerDrop): there is no HF / eager fallback.  Prefix tuning is implemented for OPT
 (``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions); T5 prefix tuning is not.
 """
 from __future__ import annotations

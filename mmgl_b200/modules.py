@@ -11,9 +11,10 @@ What runs where
     frozen decoder layers: this package's CUDA kernels (``ops``), forward and backward.
   * the causal self-attention core of the frozen OPT layers (``ops.self_attention``), the frozen RoBERTa / CLIP
     encoders (``encoders``: HF weights read in place), the lm_head projection and the shifted cross-entropy: this
-    package's kernels as well.  Library fallbacks remain only for shapes the kernels do not cover (head dims other than
-    64 / 128, arbitrary 4-D masks handed in by other callers).
-There is no CPU path: modules raise on CPU tensors.
+    package's kernels as well.
+There is no CPU path and no library fallback: modules raise on CPU tensors, and shapes the kernels do not cover (head
+dims other than 64 / 128, neighbor banks longer than ``ops.xattn_max_keys(head_dim)`` rows, arbitrary 4-D attention
+masks handed in by other callers) are rejected in the constructors / at the call with a message that says so.
 
 Reference defects that are deliberately NOT inherited: D1 (``neighbor_layer_wise`` vs
 ``num_neighbor_layers``), D2 (``neighbor_mode == "embedding"`` with flamingo means cross-attention), D4 (bank is
@@ -27,7 +28,6 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import configs, encoders, ops
 
@@ -99,17 +99,6 @@ class KeyPaddingCausalMask:
         self.key_mask = key_mask
 
 
-def _allowed_from_additive(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """the reference's additive [B,1,S,S] float mask (0 = attend) -> boolean 'allowed' mask; bool passes through"""
-    if isinstance(mask, KeyPaddingCausalMask):
-        key_ok = mask.key_mask.to(torch.bool)
-        s = key_ok.shape[1]
-        return torch.ones(s, s, dtype=torch.bool, device=key_ok.device).tril_()[None, None] & key_ok[:, None, None, :]
-    if mask is None or mask.dtype == torch.bool:
-        return mask
-    return mask == 0
-
-
 # ------------------------------------------------------------------------------------------------- attention
 class MPTAttention(nn.Module):
     """model/modelling_cross_attention.py:148-275.  Cross branch: q/k/v projections (bias and the d^-1/2 scale in
@@ -123,6 +112,9 @@ class MPTAttention(nn.Module):
         self.head_dim = self.embed_dim // self.num_heads
         if self.head_dim * self.num_heads != self.embed_dim:
             raise ValueError(f"embed_dim {self.embed_dim} not divisible by num_heads {self.num_heads}")
+        if self.head_dim not in (64, 128):
+            raise ValueError(f"mmgl_b200's attention kernels cover head_dim 64 and 128; hidden_size {self.embed_dim} / "
+                             f"{self.num_heads} heads gives {self.head_dim} (no library fallback is provided)")
         self.scaling = self.head_dim ** -0.5
         bias = config.enable_bias
         self.k_proj = nn.Linear(self.embed_dim, self.embed_dim, bias=bias)
@@ -136,12 +128,14 @@ class MPTAttention(nn.Module):
     def _key_mask(attention_mask, b, s):
         """The self-attention kernel takes the mask in its compact form: a [B,S] key-padding mask + a causal flag.
         MPTDecoder passes exactly that (``KeyPaddingCausalMask``); None means causal without padding; anything else
-        (an arbitrary 4-D mask handed in by other callers) returns False -> library fallback."""
+        (an arbitrary 4-D mask handed in by other callers) is rejected: there is no library fallback."""
         if attention_mask is None:
             return None, s > 1
         if isinstance(attention_mask, KeyPaddingCausalMask):
             return attention_mask.key_mask, True
-        return False, False
+        raise NotImplementedError(
+            "mmgl_b200 self-attention takes the decoder mask in compact form (modules.KeyPaddingCausalMask([B,S] key mask), "
+            "or None for causal without padding); arbitrary [B,1,S,S] masks are not supported and there is no fallback")
 
     def forward(self, hidden_states, attention_mask=None, neighbor_embeds=None, neighbor_attention_mask=None,
                 layer_head_mask=None, past_key_value=None, output_attentions=False, residual=None, dropout_p=0.0):
@@ -165,14 +159,7 @@ class MPTAttention(nn.Module):
             else:
                 qkv = torch.cat([ops.linear(hidden_states, p.weight, p.bias) for p in projs], dim=-1)
             key_mask, causal = self._key_mask(attention_mask, b, s)
-            if key_mask is not False and self.head_dim in (64, 128):
-                o = ops.self_attention(qkv, key_mask, self.num_heads, causal=causal, scale=self.scaling)
-            else:  # arbitrary [B,1,S,S] masks / other head dims: library fallback on the same semantics
-                q, k, v = qkv.view(b, s, 3, self.num_heads, self.head_dim).unbind(2)
-                allowed = _allowed_from_additive(attention_mask)
-                o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-                                                   attn_mask=allowed, is_causal=allowed is None and s > 1)
-                o = o.transpose(1, 2).reshape(b, s, self.embed_dim)
+            o = ops.self_attention(qkv, key_mask, self.num_heads, causal=causal, scale=self.scaling)
         out = ops.linear(o, self.out_proj.weight, self.out_proj.bias, residual=residual, dropout_p=dropout_p)
         return out, None, None
 
@@ -378,15 +365,33 @@ class TextPooler(nn.Module):
 
 # ------------------------------------------------------------------------------------------------- loaders
 def _load_or_init(kind: str, name, auto_cls_name: str):
-    """A local ``save_pretrained`` directory is loaded (reference behaviour); a bare checkpoint name is random-
-    initialised from the built-in config (no network / no weights in this environment)."""
+    """``from_pretrained(name)`` exactly as the reference does (model/modelling_cross_attention.py:920, :934, :953-954;
+    model/modelling_self_attention.py:68, :72, :111, :125): a local ``save_pretrained`` directory or a checkpoint name
+    found in the local HF cache.  When the weights cannot be found (no network, empty cache) the call RAISES unless the
+    caller opted in to random initialisation from the built-in architecture config -- ``MMGL_ALLOW_RANDOM_INIT=1`` in
+    the environment, which bench.py and the synthetic-data tests set -- and then it says so loudly.  Passing a HF config
+    object instead of a name is the explicit form of the same opt-in (tests)."""
     import transformers
     cls = getattr(transformers, auto_cls_name)
     if isinstance(name, transformers.PretrainedConfig):   # extension: explicit config object -> random init
         return cls(name)
     if isinstance(name, str) and os.path.isdir(name):
         return cls.from_pretrained(name)
+    err = None
+    try:
+        return cls.from_pretrained(name, local_files_only=os.environ.get("HF_HUB_OFFLINE", "0") == "1"
+                                   or os.environ.get("TRANSFORMERS_OFFLINE", "0") == "1")
+    except Exception as e:  # noqa: BLE001 -- hub / cache / network errors come in many types
+        err = e
+    if os.environ.get("MMGL_ALLOW_RANDOM_INIT", "0") != "1":
+        raise RuntimeError(
+            f"mmgl_b200: pretrained weights for {name!r} were not found ({type(err).__name__}: {err}).  The reference "
+            f"always trains from from_pretrained() weights; set MMGL_ALLOW_RANDOM_INIT=1 to build a RANDOM-initialised "
+            f"{auto_cls_name} of the same architecture instead (synthetic benchmarks / tests only).") from err
+    import warnings
     cfg = {"lm": configs.lm_config, "text": configs.text_config, "visual": configs.visual_config}[kind](name)
+    warnings.warn(f"mmgl_b200: {name!r} is RANDOM-INITIALISED from its architecture config (MMGL_ALLOW_RANDOM_INIT=1); "
+                  f"no pretrained weights were loaded", RuntimeWarning, stacklevel=2)
     return cls(cfg)
 
 
@@ -441,9 +446,10 @@ class _NeighborEncoderMixin:
         neighbor's bank rows are masked, get softmax weight exactly 0 and gradient exactly 0 (SURVEY invariant I2),
         so its encoder pass is skipped and its projection rows are left zero -- loss and gradients are identical.
         Exception kept for parity: a sample with NO valid neighbor attends uniformly over its masked rows in the
-        reference, so all of its neighbors stay 'needed'.  One host sync per call (index list)."""
-        if pos_ids is None or not self.skip_padding_neighbors:
-            return None
+        reference, so all of its neighbors stay 'needed'.  Not applied with position_type == "gnn" (the GCN mixes rows
+        before the mask acts).  One host sync per call (index list)."""
+        if pos_ids is None or not self.skip_padding_neighbors or getattr(self, "position_type", "none") == "gnn":
+            return None   # the GCN aggregates bank rows BEFORE masking: an edge into a padding slot would see W*enc+b
         valid = pos_ids > 0
         need = valid | ~valid.any(dim=1, keepdim=True)
         if bool(need.all()):
@@ -544,6 +550,15 @@ class CrossAttentionModel(nn.Module, _NeighborEncoderMixin):
             self.lm.eval()
             for p in self.lm.parameters():
                 p.requires_grad = False
+        # the cross-attention core keeps a head's whole bank on chip: reject configurations it cannot hold here, not at
+        # the first forward
+        n_nbrs = (getattr(args, "max_text_neighbors", None) or 0) + (getattr(args, "max_image_neighbors", None) or 0)
+        cfg = self.lm.config
+        limit = ops.xattn_max_keys(cfg.hidden_size // cfg.num_attention_heads)
+        if self.neighbor_mode == "cross_attention" and n_nbrs * self.n_text_tokens > limit:
+            raise ValueError(f"neighbor bank of {n_nbrs} neighbors x {self.n_text_tokens} tokens = "
+                             f"{n_nbrs * self.n_text_tokens} rows exceeds the cross-attention kernel's limit of {limit} "
+                             f"rows at head_dim {cfg.hidden_size // cfg.num_attention_heads}")
 
     def initialize_lm(self, args):
         """OPT weights copied into the self-attention layers, cross layers fresh (:951-976)."""

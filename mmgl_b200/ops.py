@@ -27,15 +27,42 @@ F32 = torch.float32
 _shadow = {}   # (id(param), dtype) -> (weakref(param), version, device, converted tensor)
 
 
+_epoch = [0]   # bumped by invalidate_weight_cache(): part of every cache entry's validity stamp
+
+
+def invalidate_weight_cache(trainable_only: bool = False) -> None:
+    """Drop every cached bf16 / fp32 shadow and fused-row concatenation (``trainable_only``: only those of parameters
+    with ``requires_grad`` -- the frozen layers' fused Wq|Wk|Wv rows then survive an optimizer step).
+
+    Shadows are keyed on the parameter object, its ``_version`` counter, its storage pointer and device.  In-place
+    updates made through autograd-visible ops (every torch optimizer, ``copy_``, ``load_state_dict``) bump ``_version``
+    and refresh the shadow on the next use by themselves; writes THROUGH ``param.data`` (``p.data.add_(...)``: some EMA
+    helpers, HF Adafactor, manual weight surgery) do not, so code that updates weights that way must call this after the
+    update (``train.optimizer_step`` does, for any optimizer)."""
+    if not trainable_only:
+        _epoch[0] += 1
+        _shadow.clear()
+        return
+    for key, ent in list(_shadow.items()):
+        refs = ent[0] if isinstance(ent[0], tuple) else (ent[0],)
+        if any(r() is None or r().requires_grad for r in refs):
+            _shadow.pop(key, None)
+
+
+def _stamp(p: torch.Tensor):
+    return (p._version, p.data_ptr(), p.device, _epoch[0])
+
+
 def _converted(p: torch.Tensor, dtype) -> torch.Tensor:
-    """`p` converted to `dtype`, cached per parameter object and `_version` (identity-keyed: tensors do not
-    hash/compare by value, and the entry dies with the parameter)."""
+    """`p` converted to `dtype`, cached per parameter object, `_version` and storage pointer (identity-keyed: tensors
+    do not hash/compare by value, and the entry dies with the parameter).  See invalidate_weight_cache()."""
     key = (id(p), dtype)
     ent = _shadow.get(key)
-    if ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.device:
-        return ent[3]
+    st = _stamp(p)
+    if ent is not None and ent[0]() is p and ent[1] == st:
+        return ent[2]
     conv = p.detach().to(dtype).contiguous()
-    _shadow[key] = (weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)), p._version, p.device, conv)
+    _shadow[key] = (weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)), st, conv)
     return conv
 
 
@@ -93,12 +120,12 @@ def fused_rows(params, dtype):
     them changes.  Used for FROZEN projections only: one N = 3H GEMM instead of three N = H GEMMs."""
     key = (tuple(id(p) for p in params), dtype, "rows")
     ent = _shadow.get(key)
-    vers = tuple(p._version for p in params)
-    if ent is not None and all(r() is p for r, p in zip(ent[0], params)) and ent[1] == vers and ent[2] == params[0].device:
-        return ent[3]
+    vers = tuple(_stamp(p) for p in params)
+    if ent is not None and all(r() is p for r, p in zip(ent[0], params)) and ent[1] == vers:
+        return ent[2]
     conv = torch.cat([p.detach().to(dtype) for p in params], dim=0).contiguous()
     refs = tuple(weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)) for p in params)
-    _shadow[key] = (refs, vers, params[0].device, conv)
+    _shadow[key] = (refs, vers, conv)
     return conv
 
 
@@ -523,6 +550,12 @@ class XAttnCoreFn(torch.autograd.Function):
 
 def xattn_core(q, k, v, mask, heads):
     return XAttnCoreFn.apply(q, k, v, mask, heads)
+
+
+def xattn_max_keys(head_dim: int) -> int:
+    """Longest neighbor bank (rows = neighbors x tokens per neighbor) the cross-attention core holds on chip per head:
+    the limits mmgl_xattn_fwd / _bwd enforce (include/mmgl_b200.h).  0 = head_dim not supported."""
+    return {64: 256, 128: 128}.get(int(head_dim), 0)
 
 
 def _key_mask_u8(key_mask):

@@ -7,8 +7,7 @@ kernels are: the neighbor projections, the ragged bank packing with the fused po
 accumulates into the same TMEM tile as the base product) and the language model's own layer stack -- attention with the
 T5 relative-position bias or the OPT causal / padding mask, RMSNorm / LayerNorm, FFN, lm_head and the loss
 (mmgl_b200/lm.py, which reads the weights of the HF module in place).  Models that file cannot run (gated-GELU T5,
-head dims other than 64 / 128) fall back to the HF module's own
-forward, as in the reference (third-party code there as well).
+head dims other than 64 / 128) are rejected with an error: there is no HF / eager fallback.
 
 peft is not importable in this image and its source is absent, so LoRA / prompt / prefix tuning are restated from
 their published definitions (parity unpinned, see oracle/mmgl_oracle.py:lora_linear); module and state-dict names follow
@@ -70,7 +69,6 @@ class _PeftShim(nn.Module):
     def __init__(self, model, prompt_tokens: int = 0, prefix_tokens: int = 0):
         super().__init__()
         self.base_model = _PeftHolder(model)
-        self.use_kernel_lm = True
         self.num_virtual_tokens = prompt_tokens
         self.num_prefix_tokens = prefix_tokens
         if prompt_tokens:
@@ -110,22 +108,24 @@ class _PeftShim(nn.Module):
             if labels is not None and not lm.config.is_encoder_decoder:
                 pad = torch.full((b, self.num_virtual_tokens), -100, dtype=labels.dtype, device=labels.device)
                 labels = torch.cat((pad, labels), 1)
-        return run_language_model(lm, self.use_kernel_lm, input_ids=input_ids, attention_mask=attention_mask,
+        return run_language_model(lm, input_ids=input_ids, attention_mask=attention_mask,
                                   inputs_embeds=inputs_embeds, labels=labels, **kw)
 
 
-def run_language_model(lm, use_kernels=True, **kw):
-    """The LM call of the concat path (model/modelling_self_attention.py:246, :261, :280, :332).  HF T5 / OPT models
-    that ``lm_kernels.supports`` run their layer stack on this package's kernels (mmgl_b200/lm.py); anything else (and
-    the peft shim, which forwards to its base model through this function) goes through the module's own forward --
-    HF library code under bf16 autocast, as in the reference."""
+def run_language_model(lm, **kw):
+    """The LM call of the concat path (model/modelling_self_attention.py:246, :261, :280, :332): the layer stack of the
+    HF T5 / OPT model runs on this package's kernels (mmgl_b200/lm.py).  The peft shim forwards to its base model through
+    this function.  A model the kernels cannot run, or a call without labels (the training forward computes the loss
+    in-kernel), raises: there is no HF / eager fallback."""
     if isinstance(lm, _PeftShim):
-        lm.use_kernel_lm = use_kernels
         return lm(**kw)
-    if use_kernels and kw.get("labels") is not None and lm_kernels.supports(lm):
-        return lm_kernels.forward(lm, **kw)
-    with torch.autocast("cuda", dtype=BF16):
-        return lm(**kw)
+    if not lm_kernels.supports(lm):
+        raise NotImplementedError(
+            f"mmgl_b200 cannot run {type(lm).__name__} with this configuration on its kernels (supported: HF T5 with a ReLU "
+            f"FFN and OPT, head_dim 64 or 128, no LayerDrop / attention dropout for OPT); there is no library fallback")
+    if kw.get("labels") is None:
+        raise NotImplementedError("mmgl_b200 runs the training forward (loss computed in-kernel): labels are required")
+    return lm_kernels.forward(lm, **kw)
 
 
 def apply_lora(model: nn.Module, r: int, alpha: float, dropout: float) -> int:
@@ -206,10 +206,8 @@ class SelfAttentionModel(nn.Module, _NeighborEncoderMixin):
         self._freeze_modes()
         return self
 
-    use_kernel_lm = True
-
     def _run_lm(self, **kw):
-        return run_language_model(self.lm, self.use_kernel_lm, **kw)
+        return run_language_model(self.lm, **kw)
 
     def forward(self, input_ids, attention_mask, labels, images=None, image_positions=None, neighbor_input_ids=None,
                 neighbor_attention_mask=None, neighbor_pos_ids=None, text_locations=None, neighbor_images=None,

@@ -19,7 +19,7 @@ import types
 import torch
 
 REF = "/root/reference"
-OUT = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("MMGL_GOLDEN_OUT", os.path.dirname(os.path.abspath(__file__)))
 
 
 def load_ref(name, path):
@@ -203,6 +203,7 @@ def main():
 
     # ---- case 2: MPTForCausalLM tiny (interleave loop + loss) --------------------------------
     g = torch.Generator().manual_seed(21)
+    torch.manual_seed(20)   # the weights come from the global RNG: seed it here, not from whatever case 1 left behind
     cfg = xa.MPTConfig(mpt_args(), tiny_opt_config(True))
     lm = xa.MPTForCausalLM(cfg)
     for n, prm in lm.named_parameters():

@@ -185,9 +185,10 @@ def test_opt_lora_matches_hf():
 
 
 @pytest.mark.parametrize("lm", ["t5", "opt"])
-def test_self_attention_model_runs_the_lm_on_the_package_kernels(lm):
+def test_self_attention_model_runs_the_lm_on_the_package_kernels(lm, monkeypatch):
     """End to end through the wrapper: with LoRA the LM's layer stack runs in libmmgl_b200.so (attention kernel launches
-    are counted), dropout on, loss finite, and the kernel path agrees with the HF-forward fallback at dropout 0."""
+    are counted), dropout on, loss finite, and the kernel path agrees with the HF module's own forward (run by the test
+    itself: the product has no such fallback) at dropout 0."""
     from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig, T5Config
     from mmgl_b200 import _capi, synth
     from mmgl_b200.self_attention import SelfAttentionModel
@@ -228,9 +229,16 @@ def test_self_attention_model_runs_the_lm_on_the_package_kernels(lm):
     # under the causal mask no loss position can see it and the neighbor projection gets no gradient -- reproduced)
     # kernel path vs the HF forward of the same wrapper, dropout off
     model.eval()
+    from mmgl_b200 import self_attention as SA
+
+    def hf_forward(lm_, **kw):   # test-side oracle: the HF module's own forward (the product has no such path)
+        if isinstance(lm_, SA._PeftShim):
+            return lm_(**kw)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return lm_(**kw)
     with torch.no_grad():
         a = model(**batch)
-        model.use_kernel_lm = False
+        monkeypatch.setattr(SA, "run_language_model", hf_forward)
         bref = model(**batch)
     rep = Report()
     rep.scalar("loss (kernels vs HF forward)", a.loss, bref.loss, 0.0, 3e-2)

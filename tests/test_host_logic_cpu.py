@@ -170,3 +170,77 @@ def test_cfg2_interleave_positions_and_trainable_parameter_count():
     dec = model.model.decoder
     assert dec.neighbor_layer_wise == 6 and len(dec.layers) == 24 and len(dec.neighbor_layers) == 4
     assert [i for i in range(24) if (i + 1) % dec.neighbor_layer_wise == 0] == [5, 11, 17, 23]
+
+
+def test_pretrained_names_are_not_silently_random_initialised(monkeypatch):
+    """a hub name whose weights are absent must RAISE (the reference always calls from_pretrained,
+    model/modelling_cross_attention.py:953-954); random init only behind MMGL_ALLOW_RANDOM_INIT=1, with a warning."""
+    from mmgl_b200 import modules
+    monkeypatch.delenv("MMGL_ALLOW_RANDOM_INIT", raising=False)
+    with pytest.raises(RuntimeError, match="MMGL_ALLOW_RANDOM_INIT"):
+        modules._load_or_init("lm", "facebook/opt-125m", "OPTForCausalLM")
+    monkeypatch.setenv("MMGL_ALLOW_RANDOM_INIT", "1")
+    with pytest.warns(RuntimeWarning, match="RANDOM-INITIALISED"):
+        m = modules._load_or_init("text", "roberta-base", "RobertaModel")
+    assert m.config.hidden_size == 768
+
+
+def test_pretrained_directory_is_loaded(tmp_path):
+    """a local save_pretrained directory loads its weights (reference behaviour), no opt-in needed"""
+    from transformers import OPTConfig, OPTForCausalLM
+    from mmgl_b200 import modules
+    cfg = OPTConfig(vocab_size=64, hidden_size=64, num_hidden_layers=1, ffn_dim=64, num_attention_heads=1,
+                    max_position_embeddings=32, word_embed_proj_dim=64)
+    src = OPTForCausalLM(cfg)
+    src.save_pretrained(tmp_path)
+    got = modules._load_or_init("lm", str(tmp_path), "OPTForCausalLM")
+    assert torch.equal(got.model.decoder.layers[0].fc1.weight, src.model.decoder.layers[0].fc1.weight)
+
+
+def test_unsupported_head_dim_is_rejected_at_construction():
+    """head_dim 80 (opt-2.7b) can never run on the kernels -> constructor error, not a first-forward error."""
+    from mmgl_b200 import modules, ops
+    cfg = types.SimpleNamespace(hidden_size=160, num_attention_heads=2, enable_bias=True, peft_type="flamingo")
+    with pytest.raises(ValueError, match="head_dim 64 and 128"):
+        modules.MPTAttention(cfg, cross_attention=True)
+    assert ops.xattn_max_keys(64) == 256 and ops.xattn_max_keys(128) == 128 and ops.xattn_max_keys(80) == 0
+    with pytest.raises(KeyError):
+        from mmgl_b200 import configs
+        configs.lm_config("facebook/opt-2.7b")
+
+
+def test_weight_shadow_cache_sees_data_writes_after_invalidate():
+    """p.data.add_() does not bump p._version; ops.invalidate_weight_cache() is the documented remedy (called
+    by train.optimizer_step), while version-bumping updates refresh by themselves and a re-pointed .data is noticed."""
+    from mmgl_b200 import ops
+    p = torch.nn.Parameter(torch.ones(4, 4))
+    a = ops.w16(p)
+    assert ops.w16(p) is a                               # cached
+    with torch.no_grad():
+        p.add_(1.0)                                      # bumps _version
+    b = ops.w16(p)
+    assert float(b[0, 0]) == 2.0
+    p.data.add_(1.0)                                     # silent: same version, same storage
+    assert ops.w16(p) is b
+    ops.invalidate_weight_cache(trainable_only=True)
+    assert float(ops.w16(p)[0, 0]) == 3.0
+    p.data = torch.full((4, 4), 7.0)                     # new storage -> stamp changes
+    assert float(ops.w16(p)[0, 0]) == 7.0
+    frozen = torch.nn.Parameter(torch.ones(2, 2), requires_grad=False)
+    f = ops.fused_rows([frozen, frozen], torch.bfloat16)
+    ops.invalidate_weight_cache(trainable_only=True)
+    assert ops.fused_rows([frozen, frozen], torch.bfloat16) is f   # frozen entries survive an optimizer step
+    ops.invalidate_weight_cache()
+    assert ops.fused_rows([frozen, frozen], torch.bfloat16) is not f
+
+
+def test_gnn_disables_the_padding_neighbor_skip():
+    """with position_type == 'gnn' the GCN mixes bank rows before the mask acts, so padding neighbors keep their
+    W*enc+b rows (reference semantics) instead of zeros."""
+    from mmgl_b200.modules import _NeighborEncoderMixin
+    m = _NeighborEncoderMixin()
+    pos = torch.tensor([[1, 2, 0], [1, 0, 0]])
+    m.position_type = "none"
+    assert m._needed(pos).tolist() == [0, 1, 3]
+    m.position_type = "gnn"
+    assert m._needed(pos) is None
