@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- sections/sec of MMGL's neighbor-fusion training step on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference|eager]
+                    [--workload cfg2|cfg3|cfg4|tiny] [--no-packing]
     (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 A "step" is one optimisation step of CrossAttentionModel on one synthetic WikiWeb2M-shaped micro-batch per GPU:
@@ -14,7 +15,9 @@ through the public nn.Module call with pinned HOST batches (H2D inside the timed
 ``roofline`` = achieved TFLOP/s of the dominant kernel (the tcgen05 GEMM) from per-launch CUDA events in an
 instrumented replica of the timed region; ``cpu_baseline`` = the oracle port of the same step on the host cores.
 
-``--impl reference`` times the reference algorithm's CPU port (oracle/cpu_step.py) on the host cores instead.
+``--impl reference`` times the REAL reference modules (oracle/_ref: /root/reference/model/*.py byte-compiled by
+oracle/build_ref.py) on the host cores; ``--impl eager`` runs the same modules in PyTorch eager on the B200 (the honest
+GPU baseline); the default line carries both as ``cpu_baseline`` and ``gpu_eager_baseline``.
 """
 from __future__ import annotations
 
@@ -39,13 +42,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="sections per GPU per step (reference default: 4; measured on one B200: 4 -> 129, 8 -> 178, 16 -> 206, 32 -> 215 sections/s)")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
+    ap.add_argument("--eager-dtype", default="bf16", choices=["bf16", "tf32", "fp32"], help="--impl eager: arithmetic of the reference modules on the GPU")
+    ap.add_argument("--no-packing", action="store_true",
+                    help="control: run the frozen text encoder on all T x 512 padded tokens and on padding neighbors, as the reference does")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--batches", type=int, default=8, help="distinct seeded synthetic batches cycled through")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
     return ap.parse_args()
 
 
@@ -141,32 +149,152 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(a, w):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from mmgl_b200 import configs, synth
+# ------------------------------------------------------------------------------------------------ reference arms
+def token_stats(batches, w):
+    """real vs padded neighbor-text tokens per step (mean over the cycled batches): the GPU arm packs the real tokens and
+    skips padding neighbors (f2), the reference runs all T x S_in padded positions of every slot"""
+    real = sum(int((b["neighbor_attention_mask"] * (b["neighbor_pos_ids"] > 0)[:, :, None]).sum()) for b in batches) / len(batches)
+    padded = float(batches[0]["neighbor_attention_mask"].numel())
+    nbrs = sum(int((b["neighbor_pos_ids"] > 0).sum()) + int((b["neighbor_images_pos_ids"] > 0).sum()) for b in batches) / len(batches)
+    return {"real_neighbor_tokens_per_step": real, "padded_neighbor_tokens_per_step": padded,
+            "valid_neighbors_per_step": nbrs, "neighbor_slots_per_step": float(batches[0]["neighbor_pos_ids"].shape[0] * (w["t"] + w["i"]))}
+
+
+def _time_reference_steps(model, batches, steps, warmup, dtype, cuda):
+    from oracle import ref_loader as R
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01)
+    losses = []
+    for i in range(warmup):
+        losses.append(R.train_step(model, batches[i % len(batches)], opt, dtype))
+    if cuda:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        losses.append(R.train_step(model, batches[(warmup + i) % len(batches)], opt, dtype))
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / max(1, steps)
+    else:
+        sec = (time.perf_counter() - t0) / max(1, steps)
+    del opt
+    return sec, [float(l) for l in losses]
+
+
+def reference_kind():
+    from oracle import ref_loader as R
+    return "reference" if R.available() else "port"
+
+
+def cpu_reference_run(a, w, steps, warmup, bsz):
+    """sections/s of the reference's own CrossAttentionModel train step on this box's host cores (all of them), fp32,
+    dropout on, AdamW -- oracle/_ref when present (kind "reference"), else the oracle port (kind "port").
+    Returns (seconds per step, losses, kind, threads, reference model or None)."""
+    from mmgl_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    batches = [synth.make_batch(spec_for(w, bsz), seed=1234 + s) for s in range(2)]
+    if reference_kind() == "reference" and w.get("kind") != "self":
+        from oracle import ref_loader as R
+        model = R.build_cross_attention_model(w)
+        sec, losses = _time_reference_steps(model, batches, steps, warmup, torch.float32, cuda=False)
+        return sec, losses, "reference", threads, model
+    from mmgl_b200 import configs
     from oracle import cpu_step
     args = make_args(w)
     lm_cfg = configs.lm_config(w["lm"])
     args.neighbor_layer_wise = lm_cfg.num_hidden_layers // args.num_neighbor_layers
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     p, cfg, tm, vm = cpu_step.build_cpu_reference(lm_cfg, configs.text_config(w["text"]), configs.visual_config(w["visual"]), args)
+    sec, losses = cpu_step.time_steps(p, cfg, batches, tm, vm, steps, warmup, threads)
+    return sec, losses, "port", threads, None
+
+
+def _sample_text(bsz, kind):
+    what = ("the reference's own CrossAttentionModel (oracle/_ref: /root/reference/model/*.py byte-compiled), model(**batch) -> "
+            "loss.backward() -> AdamW.step(), train mode (dropout on)") if kind == "reference" else \
+           "oracle port of the train step (oracle/cpu_step.py), dropout off"
+    return f"{bsz} section(s) per step, fp32 on all host cores: {what}"
+
+
+def run_reference(a, w):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("MMGL_ALLOW_RANDOM_INIT", "1")
     bsz = a.cpu_sample_batch
-    batches = [synth.make_batch(spec_for(w, bsz), seed=1234 + s) for s in range(2)]
-    sec, losses = cpu_step.time_steps(p, cfg, batches, tm, vm, a.steps, a.warmup, threads)
+    sec, losses, kind, threads, _ = cpu_reference_run(a, w, a.steps, a.warmup, bsz)
     val = bsz / sec
-    sample = f"{bsz} section(s) per step: full fp32 train step (frozen encoders + LM fwd/bwd + AdamW), dropout off"
     print(json.dumps({
         "impl": "reference", "metric": "sections_per_sec", "value": val, "unit": "sections/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, w), "per_step_sections": bsz},
-        "cpu_baseline": {"value": val, "unit": "sections/s", "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights of the named architectures)",
+        "config": {"workload": workload_name(a, w), "per_step_sections": bsz, "dropout": 0.1 if kind == "reference" else 0.0},
+        "cpu_baseline": {"value": val, "unit": "sections/s", "cores": threads, "kind": kind, "sample": _sample_text(bsz, kind),
+                         "cpu_model": _cpu_model()},
         "e2e": {"value": val, "unit": "sections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss_first_last": [losses[0], losses[-1]]}), flush=True)
+
+
+def eager_on_gpu(model, w, batch, dev, steps, warmup, dtypes, n_batches=4):
+    """The reference's own modules in PyTorch eager on the B200 (SURVEY 8d 'honest GPU baseline'): same step, same
+    batch size, same synthetic batches, train mode.  ``fp32`` is what the stock reference can run (--fp16 means
+    model.float(), run_generation.py:304-305; its bf16 path raises, defect D4); ``tf32`` adds
+    torch.backends.cuda.matmul.allow_tf32; ``bf16`` is model.bfloat16() with the D4 bank-dtype fix applied from outside."""
+    from mmgl_b200 import synth
+    out = {}
+    host = [synth.make_batch(spec_for(w, batch), seed=1234 + s) for s in range(n_batches)]
+    resident = [synth.to_device(b, dev) for b in host]
+    model.to(dev)
+    for name in dtypes:
+        tf32 = name == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        dt = torch.bfloat16 if name == "bf16" else torch.float32
+        if dt == torch.bfloat16:
+            model.bfloat16()
+        try:
+            sec, losses = _time_reference_steps(model, resident, steps, warmup, dt, cuda=True)
+            out[name] = {"value": batch / sec, "unit": "sections/s", "ms_per_step": sec * 1e3, "per_gpu_batch": batch,
+                         "steps": steps, "warmup": warmup, "loss_first_last": [losses[0], losses[-1]]}
+        except torch.cuda.OutOfMemoryError as e:  # noqa: PERF203
+            out[name] = {"error": f"out of memory at batch {batch}: {str(e)[:120]}"}
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return out
+
+
+EAGER_NOTE = ("the reference's own modules (oracle/_ref) in PyTorch eager on this B200: HF RoBERTa / CLIP forward on all padded "
+              "tokens, OPT layers with materialised [B,nh,S,S] attention, cuBLAS GEMMs, ATen softmax / LayerNorm, torch AdamW; "
+              "lm_head frozen (D12); bf16 = model.bfloat16() with the D4 bank-dtype fix applied from outside")
+
+
+def run_eager(a, w):
+    """--impl eager: the reference's modules on the GPU (single process; under torchrun rank 0 alone runs it)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("MMGL_ALLOW_RANDOM_INIT", "1")
+    from oracle import ref_loader as R
+    if not R.available() or not torch.cuda.is_available():
+        print(json.dumps({"impl": "eager", "unavailable": "oracle/_ref not built or no CUDA device"}), flush=True)
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    model = R.build_cross_attention_model(w)
+    res = eager_on_gpu(model, w, a.batch, dev, a.steps, max(3, a.warmup), [a.eager_dtype], n_batches=min(a.batches, 4))[a.eager_dtype]
+    if "error" in res:
+        print(json.dumps({"impl": "eager", "unavailable": res["error"]}), flush=True)
+        return
+    print(json.dumps({
+        "impl": "eager", "metric": "sections_per_sec", "value": res["value"], "unit": "sections/s", "n_gpus": 1,
+        "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.eager_dtype, "data": "synthetic (random-init weights)",
+        "config": {"workload": workload_name(a, w), "per_gpu_batch": a.batch, "dropout": 0.1, "note": EAGER_NOTE},
+        "loss_first_last": res["loss_first_last"]}), flush=True)
 
 
 def workload_name(a, w):
@@ -195,6 +323,10 @@ def run_ours(a, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _capi.lib()  # fail loudly if the extension is missing
+    os.environ.setdefault("MMGL_ALLOW_RANDOM_INIT", "1")   # no checkpoints offline: random-init weights of the named architectures
+    if a.no_packing:
+        from mmgl_b200 import encoders
+        encoders.PACK_PADDING = False
 
     torch.manual_seed(1234)
     args = make_args(w)
@@ -209,6 +341,8 @@ def run_ours(a, w):
         for n, p in model.named_parameters():
             if "gating" in n:
                 p.fill_(0.5)  # live gates: at the reference's init (0.0) the whole cross branch is multiplied by zero
+    if a.no_packing:
+        model.skip_padding_neighbors = False
     modules.prepare_for_training(model, dev)
     model.train()
     net = model
@@ -225,12 +359,14 @@ def run_ours(a, w):
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
 
     spec = spec_for(w, a.batch)
-    host = [synth.make_batch(spec, seed=1234 + rank * 100 + s, pin=True) for s in range(2)]
+    nb = max(2, a.batches)
+    host = [synth.make_batch(spec, seed=1234 + rank * 100 + s, pin=True) for s in range(nb)]
     resident = [synth.to_device(b, dev) for b in host]
     h2d = synth.batch_nbytes(host[0])
+    tokens = token_stats(host, w)
 
     def step_resident(i):
-        out = net(**resident[i % 2])
+        out = net(**resident[i % nb])
         out.loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -247,7 +383,7 @@ def run_ours(a, w):
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            batch = synth.to_device(host[i % 2], dev)
+            batch = synth.to_device(host[i % nb], dev)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return batch, ev
@@ -387,7 +523,10 @@ def run_ours(a, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a, w), "per_gpu_batch": a.batch, "global_batch": sections,
                    "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "AdamW(fused) on fp32 master weights",
-                   "l2": "per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; two alternating batches"},
+                   "l2": f"per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; {nb} seeded batches cycled",
+                   "packing": "off (control): padded tokens and padding neighbors are encoded like the reference does" if a.no_packing
+                   else "text encoder runs on real tokens of valid neighbors only (f2)",
+                   "weights": "random-init (MMGL_ALLOW_RANDOM_INIT=1: no checkpoints offline)", **tokens},
         "e2e": {"value": sections / (ms_e2e * 1e-3), "unit": "sections/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "pipeline": "batch i+1 H2D prefetched on a copy stream during step i; loss of step i read from pinned "
@@ -400,7 +539,15 @@ def run_ours(a, w):
         "trainable_params": sum(p.numel() for p in params),
     }
     if world == 1 and not a.no_cpu_baseline and not self_path:
-        line["cpu_baseline"] = cpu_baseline(a, w)
+        del opt, net, resident
+        model.to("cpu")
+        torch.cuda.empty_cache()
+        line.update(baselines(a, w, dev))
+        eager = line.get("gpu_eager_baseline", {})
+        best = max((v["value"] for v in eager.values() if isinstance(v, dict) and "value" in v), default=None)
+        if best:
+            line["vs_gpu_eager"] = {"e2e_over_best_eager": line["e2e"]["value"] / best,
+                                    "note": "this arm's e2e sections/s over the FASTEST eager variant of the reference on the same GPU, same batch size"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -466,23 +613,21 @@ def block_roofline(model, batch, seq, pk, dev):
     return {"bound": "tensor", "peak_source": pk["source"] + " (burst: block timed alone)", "sizes": out}
 
 
-def cpu_baseline(a, w):
-    """The oracle port of the same step on this box's host cores, on a bounded sample (rank 0, N=1 only)."""
-    from mmgl_b200 import configs, synth
-    from oracle import cpu_step
-    args = make_args(w)
-    lm_cfg = configs.lm_config(w["lm"])
-    args.neighbor_layer_wise = lm_cfg.num_hidden_layers // args.num_neighbor_layers
-    threads = os.cpu_count() or 1
+def baselines(a, w, dev):
+    """cpu_baseline (+ gpu_eager_baseline) of the default line: the reference model is built ONCE on the host, timed there
+    on a bounded sample, then moved to the GPU and timed in eager mode at the bench's own batch size."""
     t0 = time.time()
-    p, cfg, tm, vm = cpu_step.build_cpu_reference(lm_cfg, configs.text_config(w["text"]), configs.visual_config(w["visual"]), args)
     bsz = a.cpu_sample_batch
-    batches = [synth.make_batch(spec_for(w, bsz), seed=99)]
-    sec, _ = cpu_step.time_steps(p, cfg, batches, tm, vm, steps=2, warmup=1, threads=threads)
-    return {"value": bsz / sec, "unit": "sections/s", "cores": threads, "kind": "port",
-            "sample": f"{bsz} section(s) per step x 2 timed steps (+1 warm-up): full fp32 train step on host cores "
-                      f"(frozen encoders + LM fwd/bwd + AdamW), dropout off; setup {time.time() - t0 - 3 * sec:.0f}s untimed",
-            "cpu_model": _cpu_model()}
+    sec, _, kind, threads, ref_model = cpu_reference_run(a, w, steps=2, warmup=1, bsz=bsz)
+    out = {"cpu_baseline": {"value": bsz / sec, "unit": "sections/s", "cores": threads, "kind": kind,
+                            "sample": _sample_text(bsz, kind) + f"; 2 timed steps (+1 warm-up); setup {time.time() - t0 - 3 * sec:.0f}s untimed",
+                            "cpu_model": _cpu_model()}}
+    if ref_model is not None and not a.no_eager_baseline:
+        res = eager_on_gpu(ref_model, w, a.batch, dev, steps=5, warmup=3, dtypes=["fp32", "tf32", "bf16"])
+        out["gpu_eager_baseline"] = {"what": EAGER_NOTE, **res}
+    del ref_model
+    torch.cuda.empty_cache()
+    return out
 
 
 def _physical_gpu_index(local):
@@ -508,5 +653,7 @@ if __name__ == "__main__":
     w = WORKLOADS[a.workload]
     if a.impl == "reference":
         run_reference(a, w)
+    elif a.impl == "eager":
+        run_eager(a, w)
     else:
         run_ours(a, w)

@@ -78,6 +78,9 @@ def _pack_plan(attention_mask):
 
 _ACT = {"relu": 1, "gelu": 2, "quick_gelu": 3}
 
+# bench.py --no-packing control: run the text encoder on the padded [N, S] batch like the reference does
+PACK_PADDING = True
+
 
 def _supported(cfg) -> bool:
     d = cfg.hidden_size // cfg.num_attention_heads
@@ -85,12 +88,16 @@ def _supported(cfg) -> bool:
 
 
 @torch.no_grad()
-def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=True):
+def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=None):
     """``model(input_ids, attention_mask).last_hidden_state[:, 0]`` of a HF RobertaModel, [N, hidden] bf16.
     (HF: models/roberta/modeling_roberta.py -- embeddings :70-150, layer :400-470; post-LN blocks.)"""
     cfg = model.config
     if not _supported(cfg):
-        return model(input_ids=input_ids, attention_mask=attention_mask).last_hidden_state[:, 0]
+        raise NotImplementedError(f"mmgl_b200 runs the frozen text encoder on its own kernels: head_dim must be 64 / 128 and "
+                                  f"hidden_act one of {sorted(_ACT)} (got {cfg.hidden_size // cfg.num_attention_heads}, "
+                                  f"{cfg.hidden_act!r}); there is no library fallback")
+    if pack_padding is None:
+        pack_padding = PACK_PADDING
     n, s = input_ids.shape
     emb = model.embeddings
     pad = emb.padding_idx
@@ -141,7 +148,8 @@ def clip_pooler_output(model, pixel_values):
     p = cfg.patch_size
     n, c, hh, ww = pixel_values.shape
     if not _supported(cfg) or hh % p or ww % p or (c * p * p) % 8:
-        return model(pixel_values.to(next(model.parameters()).dtype)).pooler_output
+        raise NotImplementedError("mmgl_b200 runs the frozen vision tower on its own kernels: head_dim 64 / 128, image size a "
+                                  "multiple of the patch size, 3 * patch^2 a multiple of 8; there is no library fallback")
     gh, gw = hh // p, ww // p
     s = gh * gw + 1
     h, heads = cfg.hidden_size, cfg.num_attention_heads

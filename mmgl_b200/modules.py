@@ -403,7 +403,9 @@ class _NeighborEncoderMixin:
         self.text_model = None
         if with_text:
             if "clip" in str(args.text_model):
-                self.text_model = _load_or_init("text", args.text_model, "CLIPTextModel")
+                raise NotImplementedError(
+                    "CLIP TEXT towers as the neighbor text encoder (model/modelling_cross_attention.py:919) are not built on "
+                    "the package's kernels yet (RoBERTa is); there is no library fallback")
             else:
                 self.text_model = _load_or_init("text", args.text_model, "RobertaModel")
                 self.text_pooler = TextPooler(self.text_model.config)
@@ -429,9 +431,6 @@ class _NeighborEncoderMixin:
         (model/modelling_cross_attention.py:988-996)."""
         l = input_ids.shape[-1]
         ids2, am2 = input_ids.reshape(-1, l), attention_mask.reshape(-1, l)
-        if "clip" in str(self.args.text_model):
-            with torch.no_grad():
-                return self.text_model(input_ids=ids2, attention_mask=am2).pooler_output
         # frozen RoBERTa on this package's kernels; only the [CLS] row is consumed (TextPooler: hidden[:, 0])
         return self.text_pooler.pool_cls(encoders.roberta_cls_hidden(self.text_model, ids2, am2))
 

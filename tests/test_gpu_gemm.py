@@ -136,6 +136,28 @@ def test_gemm_production_shapes_heuristic_tile(m, n, k):
     assert_close("bf16 out", out, a @ b.t(), TOL_BF16)
 
 
+@pytest.mark.parametrize("m,n,k,a_t,b_t,fp32", [
+    (10240, 2048, 2048, False, False, False),   # q / out projection at per-GPU batch 16 (M = 16 x 640): pair-kernel tiles
+    (10240, 8192, 2048, False, False, False),   # fc1
+    (10240, 2048, 8192, False, False, False),   # fc2
+    (10240, 2048, 8192, False, True, False),    # dgrad of fc1
+    (8192, 2048, 10240, True, True, True),      # wgrad of fc1: K = tokens = 10240, fp32 master-gradient output
+    (2048, 8192, 10240, True, True, True),      # wgrad of fc2
+    (2048, 2048, 10240, True, True, True),      # wgrad of q / out projection
+    (1024, 2048, 2048, False, False, False),    # K / V projection of the bank (16 x 64 rows)
+])
+def test_gemm_at_benchmarked_shapes(m, n, k, a_t, b_t, fp32):
+    """the GEMM shapes of the timed cfg2 step at batch 16 (the earlier production-shape test stopped
+    at M = 2560), forward, dgrad and wgrad layouts, against an fp32 torch matmul on the same bf16 operands (on the GPU:
+    cuBLAS fp32 without TF32 is the reference arithmetic here)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(m + n + k)
+    a_s, b_s, a, b = _operands(gen, m, n, k, a_t, b_t)
+    out = torch.empty((m, n), dtype=torch.float32 if fp32 else BF16, device="cuda")
+    _K().gemm(a_s, b_s, out, a_t=a_t, b_t=b_t)
+    assert_close("out", out, a @ b.t(), TOL_F32 if fp32 else TOL_BF16)
+
+
 def test_gemm_wgrad_shape_fp32():
     """dW[N_out,K_in] = dy^T x: both operands MN-major, long K (= tokens), fp32 master-weight output."""
     gen = torch.Generator().manual_seed(6)

@@ -161,6 +161,45 @@ def test_gated_cross_layer_vs_oracle(pre_ln, b, s, nk, heads, h, f, smooth):
     rep.finish()
 
 
+@pytest.mark.parametrize("b,s,nk,heads,h,f", [
+    (2, 640, 64, 32, 2048, 8192),      # cfg2: OPT-1.3B width, seq 512+128, 16 neighbors x 4 tokens (the benchmarked shape)
+    (2, 640, 128, 32, 2048, 8192),     # cfg4: 32 neighbors
+    (1, 1152, 128, 32, 4096, 11008),   # cfg5: Llama-2-7B width, head_dim 128, seq 1024+128
+])
+def test_gated_cross_layer_at_benchmarked_sizes(b, s, nk, heads, h, f):
+    """the gated block against the oracle at the dims bench.py times (pair-kernel GEMM tiles, 5 / 9
+    query tiles per head, Nk = 64 / 128), natural ReLU (no smoothing), ragged masks, init_std-scaled weights."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(97 + nk + h)
+    p = _round_big(_layer_params(gen, h, f, scale=0.02))
+    x = randn(gen, b, s, h).to(BF16)
+    bank = randn(gen, b, nk, h).to(BF16)
+    mask = torch.rand(b, nk, generator=gen) > 0.3
+    mask[0, :] = True
+    dy = randn(gen, b, s, h).to(BF16)
+    gp = {k: _leaf(v) for k, v in p.items()}
+    xg, bg = _leaf(x), _leaf(bank)
+    y = ops.gated_cross_layer(
+        xg, bg, mask.cuda(), gp["self_attn_layer_norm.weight"], gp["self_attn_layer_norm.bias"],
+        gp["self_attn.q_proj.weight"], gp["self_attn.q_proj.bias"], gp["self_attn.k_proj.weight"],
+        gp["self_attn.k_proj.bias"], gp["self_attn.v_proj.weight"], gp["self_attn.v_proj.bias"],
+        gp["self_attn.out_proj.weight"], gp["self_attn.out_proj.bias"], gp["gating1"],
+        gp["final_layer_norm.weight"], gp["final_layer_norm.bias"], gp["fc1.weight"], gp["fc1.bias"],
+        gp["fc2.weight"], gp["fc2.bias"], gp["gating2"], heads, 1e-5, True)
+    y.backward(dy)
+    cp = {k: _cpu32(v) for k, v in p.items()}
+    xc, bc = _cpu32(x), _cpu32(bank)
+    yr = O.mpt_decoder_layer(xc, cp, heads, cross_attention=True, bank=bc,
+                             bank_add_mask=O.expand_mask(mask, torch.float32, s), do_layer_norm_before=True)
+    yr.backward(dy.float().cpu())
+    rep = Report()
+    rep.close("y", y, yr, TOL_Y)
+    rep.close("dx", xg.grad, xc.grad, TOL_G_RELU)
+    rep.close("dbank", bg.grad, bc.grad, TOL_G_RELU)
+    _compare_param_grads(rep, gp, {k: v.grad for k, v in cp.items()}, TOL_G_RELU, False)
+    rep.finish()
+
+
 @pytest.mark.parametrize("pre_ln", [True, False])
 def test_gated_cross_layer_with_dropout(pre_ln):
     """Training mode (dropout p = 0.1 after out_proj and after fc2, model/modelling_cross_attention.py:332, :356):

@@ -166,3 +166,67 @@ def test_skipping_padding_neighbors_changes_nothing(golden):
             continue
         rep.close("d " + n, res[True][2][n], res[False][2][n], 2e-3)
     rep.finish()
+
+
+@pytest.mark.parametrize("position_type", ["laplacian", "gnn"])
+def test_cross_attention_model_with_graph_position_encodings_vs_oracle(golden, position_type):
+    """BASELINE configs[3] (cfg4: flamingo + graph positional encodings) is an EXTENSION of the reference (its
+    CrossAttentionModel.forward has no lpe / graph kwargs): the bank gets the same ``lpe_embeddings`` / ``GCN`` add the
+    self-attention wrapper applies (model/modelling_self_attention.py:311-320) before the gated cross-attention layers.
+    Oracle: oracle.cross_attention_model_from_pooled with the lpe / graph terms (lpe_add / gnn_add are pinned against the
+    reference's SelfAttentionModel by the wrapper_self_*_{laplacian,gnn} fixtures), on the wrapper_cross_d64 weights."""
+    from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig
+    from mmgl_b200 import modules as M
+    from oracle import mmgl_oracle as O
+    g = golden("wrapper_cross_d64")
+    t, i = g["batch"]["neighbor_pos_ids"].shape[1], g["batch"]["neighbor_images_pos_ids"].shape[1]
+    n, b = t + i, g["batch"]["input_ids"].shape[0]
+    args = types.SimpleNamespace(
+        context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=2, n_visual_tokens=2,
+        model_name_or_path=OPTConfig(**g["lm_config"]), text_model=RobertaConfig(**g["text_config"]),
+        visual_model=CLIPVisionConfig(**g["visual_config"]), max_output_length=16, freeze_lm=False,
+        neighbor_layer_wise=2, lora_r=64, lora_alpha=1, lora_dropout=0.0, position_type=position_type,
+        max_text_neighbors=t, max_image_neighbors=i)
+    model = M.CrossAttentionModel(args, tokenizer=None)
+    missing, unexpected = model.load_state_dict(g["state"], strict=False)
+    assert not unexpected
+    gen = torch.Generator().manual_seed(123)
+    extra = {}
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if name.startswith(("lpe_embeddings.", "gnn.")):
+                prm.copy_((torch.randn(prm.shape, generator=gen) * 0.05).to(BF16).float())
+                extra[name] = prm.detach().clone()
+    assert extra, "the graph-PE parameters were not created"
+    M.prepare_for_training(model, "cuda")
+    model.eval()
+    model.skip_padding_neighbors = False
+    tp, vp = g["text_pooled"].cuda(), g["visual_pooled"].cuda()
+    model.encode_images = lambda px: vp.reshape(-1, vp.shape[-1]).to(BF16)
+    model.encode_text = lambda ids, am: tp.reshape(-1, tp.shape[-1]).to(BF16)
+    batch = dict(g["batch"])
+    if position_type == "laplacian":
+        lpe = torch.randn((b, n + 1, n - 4), generator=gen)
+        batch["lpe"] = lpe / lpe.norm(dim=1, keepdim=True).clamp_min(1e-6)
+    else:
+        a = (torch.rand((b, n + 1, n + 1), generator=gen) < 0.5).float()
+        a = ((a + a.transpose(1, 2)) > 0).float() + torch.eye(n + 1)
+        batch["graph"] = a / a.sum(-1, keepdim=True)
+    out = model(**{k: v.cuda() for k, v in batch.items()})
+    out.loss.backward()
+
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in {**g["state"], **extra}.items()}
+    cfg = dict(g["cfg"], flamingo=True)
+    loss, logits = O.cross_attention_model_from_pooled(p, cfg, batch, g["text_pooled"], g["visual_pooled"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) > 1e-4, "the graph PE term must change the loss (path is live)"
+    rep = Report()
+    rep.close("logits", out.logits, logits, 2e-2)
+    rep.scalar("loss", out.loss, loss, 0.0, 2e-2)
+    params = dict(model.named_parameters())
+    for k in list(extra) + ["text_embeddings.weight", "visual_embeddings.weight",
+                            "lm.model.decoder.neighbor_layers.0.self_attn.v_proj.weight",
+                            "lm.model.decoder.neighbor_layers.1.fc2.weight"]:
+        assert params[k].grad is not None, f"{k} received no gradient"
+        rep.close("d " + k, params[k].grad, p[k].grad, 8e-2)
+    rep.finish()

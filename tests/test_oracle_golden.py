@@ -232,3 +232,27 @@ def test_attention_core_matches_hf_opt_attention():
     (got * rows[..., None]).backward(d_o)
     torch.testing.assert_close(got[rows], ref[rows], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(x.grad, want_dx, rtol=1e-4, atol=1e-5)
+
+
+def test_compiled_reference_in_oracle_ref_is_the_reference(golden):
+    """oracle/_ref (the reference's model files byte-compiled by oracle/build_ref.py; bench.py's `--impl reference` /
+    `--impl eager` arms run it) reproduces a golden vector made from /root/reference BIT-exactly: it IS the reference."""
+    from oracle import ref_loader as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    import types
+    from transformers import OPTConfig
+    xa = R.cross_attention_module()
+    g = golden("xattn_layer_preln")
+    cfg = OPTConfig(vocab_size=512, hidden_size=64, num_hidden_layers=4, ffn_dim=128, num_attention_heads=4,
+                    max_position_embeddings=200, word_embed_proj_dim=64, do_layer_norm_before=True)
+    args = types.SimpleNamespace(neighbor_layer_wise=2, neighbor_mode="cross_attention", peft_type="flamingo", lora_r=64,
+                                 lora_alpha=1, lora_dropout=0.0)
+    layer = xa.MPTDecoderLayer(xa.MPTConfig(args, cfg), cross_attention=True)
+    layer.load_state_dict(g["state"])
+    layer.eval()
+    x = g["x"].clone().requires_grad_(True)
+    y = layer(x, neighbor_embeds=g["bank"], neighbor_attention_mask=xa._expand_mask(g["mask"], x.dtype, tgt_len=x.shape[1]))[0]
+    assert torch.equal(y, g["y"])
+    (y * g["w"]).sum().backward()
+    assert torch.equal(x.grad, g["dx"])

@@ -1,4 +1,6 @@
 """Shared helpers for the parity tests (test infrastructure, not product code)."""
+import os
+
 import torch
 
 BF16 = torch.bfloat16
@@ -19,6 +21,10 @@ def assert_close(name: str, got: torch.Tensor, want: torch.Tensor, tol: float):
     assert tuple(got.shape) == tuple(want.shape), f"{name}: shape {tuple(got.shape)} != {tuple(want.shape)}"
     assert torch.isfinite(got.float()).all(), f"{name}: non-finite values"
     err = rel_l2(got, want)
+    path = os.environ.get("MMGL_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '?')}\n  {name:36s} rel-L2 {err:.3e} (tol {tol:.1e})\n")
     assert err <= tol, f"{name}: rel-L2 {err:.3e} > {tol:.1e} (max|d| {max_abs(got, want):.3e})"
 
 
@@ -59,4 +65,8 @@ class Report:
 
     def finish(self):
         print("\n".join(self.rows))
+        path = os.environ.get("MMGL_PARITY_REPORT")      # one GPU run -> the measured error of every comparison
+        if path:
+            with open(path, "a") as f:
+                f.write(os.environ.get("PYTEST_CURRENT_TEST", "?") + "\n  " + "\n  ".join(self.rows) + "\n")
         assert not self.bad, "out of tolerance: " + ", ".join(self.bad)
