@@ -152,8 +152,12 @@ typedef struct mmgl_attn_args {
   const int32_t* cu_seqlens; int64_t total_tokens;
 } mmgl_attn_args;
 int mmgl_attn_fwd(const mmgl_attn_args* args, void* stream);
-/* o and stats in args are the forward outputs (read here).  workspace: caller-owned fp32 scratch of
- * mmgl_attn_bwd_workspace_bytes() (rowsum(dO . O), written by the dQ kernel and read by the dK/dV kernel). */
+/* o and stats in args are the forward outputs (read here).  One kernel computes dQ, dK and dV from a single
+ * recomputation of the scores (csrc/sattn_bwd_sm100.cu): a persistent CTA owns a (sample, head), accumulates dK / dV of a
+ * key block in TMEM and sums the dQ contributions of successive key blocks in `workspace`, a caller-owned fp32 scratch of
+ * mmgl_attn_bwd_workspace_bytes() (16-byte aligned; one [ceil(seq_q / 128) * 128, 128] tile set per resident CTA; its
+ * contents on entry and exit are irrelevant).  The accumulation order is fixed, so dQ / dK / dV are run-to-run
+ * deterministic.  seq_q is limited by the shared memory that holds one rowsum(dO . O) per query row (about 8000). */
 size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t heads);
 /* d_rel_bias: NULL, or fp32 [heads, seq_q + seq_k - 1] that receives += the gradient of rel_bias (sum of dS over every
  * (sample, row, key) with the same key - row; the caller zeroes it).  Accumulated with fp32 atomics, so its low bits are

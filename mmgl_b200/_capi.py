@@ -339,10 +339,11 @@ def attn_bwd(d_o, q, k, v, key_mask, rel_bias, o, stats, dq, dk, dv, batch, seq_
     h = heads * head_dim
     a = _attn_args(q, k, v, key_mask, rel_bias, o, stats, batch, seq_q, seq_k, heads, head_dim, scale, causal, dropout_p,
                    dropout_seed)
-    ws = torch.empty(batch * heads * seq_q, dtype=torch.float32, device=q.device)
+    # fp32 scratch of the per-CTA dQ accumulation (L2-resident; never read by the caller)
+    ws = _workspace(lib().mmgl_attn_bwd_workspace_bytes(batch, seq_q, heads), q.device)
     with _Timed("sattn_bwd", float(batch * (seq_q + seq_k) * h * 2 * 4)):
         _check(lib().mmgl_attn_bwd(C.byref(a), _p(d_o), _ld(d_o), _p(dq), _ld(dq), _p(dk), _ld(dk), _p(dv), _ld(dv),
-                                   _p(d_rel_bias), _p(ws), ws.numel() * 4, _stream()), "mmgl_attn_bwd")
+                                   _p(d_rel_bias), _p(ws), ws.numel(), _stream()), "mmgl_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------- layernorm

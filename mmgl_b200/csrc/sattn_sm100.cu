@@ -23,149 +23,10 @@
 // Masks are bit masks: one 32-bit word per 32 keys (attend = exists AND not padding), built once per CTA; the causal
 // limit of the diagonal block is a per-thread shift.  Interior blocks (all 128 keys attended, not diagonal, no bias)
 // take a 3-instruction-per-score path.
-#include <cfloat>
-#include <cuda.h>
-#include <cuda_bf16.h>
-
-#include "../../include/mmgl_b200.h"
-#include "common.cuh"
-#include "ptx.cuh"
+#include "sattn_common.cuh"
 
 namespace mmgl {
-
-int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1);
-
 namespace {
-
-constexpr float kL2E = 1.4426950408889634f;
-
-// Development trace (compiled in only with -DMMGL_TRACE): CTA (0,0,0) stamps (tag, clock) pairs per role into a global
-// buffer read back by mmgl_debug_trace(); tools/attn_trace.py prints the timeline.
-#ifdef MMGL_TRACE
-__device__ unsigned long long g_trace[4 * 1024];
-#define TR(role, idx_var, tag)                                                          \
-  do {                                                                                  \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx_var) < 511) {     \
-      g_trace[(role) * 1024 + 2 * (idx_var)] = (unsigned long long)(tag);               \
-      g_trace[(role) * 1024 + 2 * (idx_var) + 1] = clock64();                           \
-      ++(idx_var);                                                                      \
-    }                                                                                   \
-  } while (0)
-#else
-#define TR(role, idx_var, tag) do { } while (0)
-#endif
-
-struct AttnParams {
-  const uint8_t* key_mask;   // [B, seq_k] or null
-  const float* rel_bias;     // [heads, seq_q + seq_k - 1] or null: bias(h, row, key) = rel_bias[h][key - row + seq_q - 1]
-  int seq_q, seq_k, heads, causal;
-  int batch;                 // backward kernels: persistent CTAs walk (tile, head, sample) work items
-  float* d_rel_bias;         // dQ kernel only, or null: gradient of rel_bias, += over (sample, row) with atomics
-  const int32_t* cu_seqlens; // forward only, or null: sample b = packed rows [cu[b], cu[b+1]) (variable-length batch)
-  int coff;                  // causal: key allowed iff key <= row + coff, coff = seq_k - seq_q (bottom-right aligned; prefix K/V)
-  float scale;
-  uint32_t drop_thresh;      // 0: no dropout; else round(p * 65536)
-  float drop_scale;          // 1 / (1 - p)
-  uint64_t drop_seed;
-};
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t swz(uint32_t slab_base, int row, int chunk) {
-  return slab_base + row * 128 + (((chunk ^ (row & 7)) & 7) << 4);
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// the low n bits set (n may be <= 0 or >= 32)
-__device__ __forceinline__ uint32_t low_bits(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
-
-// attend bits of the whole key range of sample b: word w covers keys [32w, 32w + 32); bit = key exists and is not padding.
-// All threads of the CTA must call (full warps).
-__device__ __forceinline__ void build_key_bits(uint32_t* kbits, const uint8_t* key_mask, int b, int seq_k, int nwords) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int w = warp; w < nwords; w += nwarps) {
-    const int key = w * 32 + lane;
-    const bool a = key < seq_k && (key_mask == nullptr || key_mask[(int64_t)b * seq_k + key] != 0);
-    const uint32_t bits = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) kbits[w] = bits;
-  }
-}
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 v;
-    v.x = pack_bf16(__uint_as_float(r[8 * g]) * mul, __uint_as_float(r[8 * g + 1]) * mul);
-    v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * mul, __uint_as_float(r[8 * g + 3]) * mul);
-    v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * mul, __uint_as_float(r[8 * g + 5]) * mul);
-    v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * mul, __uint_as_float(r[8 * g + 7]) * mul);
-    *reinterpret_cast<uint4*>(dst + 8 * g) = v;
-  }
-}
-// keep bits (bit e = element e kept) of 32 consecutive keys starting at key0 (multiple of 32) of dropout row `drow`
-__device__ __forceinline__ uint32_t keep_word(const AttnParams& p, int64_t drow, int key0, int64_t groups_per_row) {
-  uint32_t w = 0;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const DropBits bits = dropout_bits(p.drop_seed, drow, (key0 >> 3) + g, groups_per_row);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) w |= dropout_keep(bits, e, p.drop_thresh) ? (1u << (8 * g + e)) : 0u;
-  }
-  return w;
-}
-
-// MMA issue from precomputed descriptor bases (descriptor of addr + delta = descriptor of addr + (delta >> 4)): the issuing
-// thread adds compile-time constants instead of building two descriptors per instruction.
-//   mma_qk_desc: S[128 x 128] = A[128 x D] * B[128 x D]^T, both K-major tiles of D / 64 slabs of [128][64]
-//   mma_pv_desc: C[128 x D] (+)= A[128 x 128] * B[128 x D], A K-major (2 slabs), B a [128 rows][D] tile read MN-major (LBO 16384)
-__host__ __device__ constexpr uint64_t kslab_off(int k) { return (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4); }
-template <int D>
-__device__ __forceinline__ void mma_qk_desc(uint32_t tmem, uint64_t da0, uint64_t db0) {
-  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-  for (int k = 0; k < D / 16; ++k) umma_f16_ss(tmem, da0 + kslab_off(k), db0 + kslab_off(k), idesc, k != 0 ? 1u : 0u);
-}
-template <int D>
-__device__ __forceinline__ void mma_pv_desc(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    umma_f16_ss(tmem, da0 + kslab_off(k), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
-}
-// C[128 x D] (+)= A^T * B from descriptor bases: A a [128 rows][128] tile read MN-major (LBO 16384), B a [128 rows][D] tile
-// read MN-major (LBO 16384); 8 k-steps of 16 rows (2048 bytes)
-template <int D>
-__device__ __forceinline__ void mma_tn_desc(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(128, D, 1, 1);
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    umma_f16_ss(tmem, da0 + (uint64_t)((k * 2048) >> 4), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
-}
-// half-block (64 keys) forms for the double-buffered pass 2 of the forward kernel:
-//   S[128 x 64] = Q[128 x D] * Khalf[64 x D]^T          (db0 = descriptor of the half's first key row)
-//   O[128 x D] (+)= P[128 x 64] * Vhalf[64 x D]          (da0 = P slab, db0 = descriptor of the half's first V row, MN-major)
-template <int D>
-__device__ __forceinline__ void mma_qk_half(uint32_t tmem, uint64_t da0, uint64_t db0) {
-  const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
-#pragma unroll
-  for (int k = 0; k < D / 16; ++k) umma_f16_ss(tmem, da0 + kslab_off(k), db0 + kslab_off(k), idesc, k != 0 ? 1u : 0u);
-}
-template <int D>
-__device__ __forceinline__ void mma_pv_half(uint32_t tmem, uint64_t da0, uint64_t db0, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_f16_ss(tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
-}
-template <int D>
-__device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0) {
-#pragma unroll
-  for (int j = 0; j < D / 64; ++j) tma_load_2d(dst + j * 16384, map, bar, col0 + 64 * j, row0);
-}
-
 
 // ---- per-chunk softmax pieces (one thread = one score row, rc = 32 consecutive keys of it) ------------------------------
 // pass 1: running maxima.  raw_mx: unscaled, over attended keys (no-bias paths); mx: natural units (bias path).
@@ -539,427 +400,6 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (threadIdx.x == 0) TR(0, tri, 999);
 }
 
-// ------------------------------------------------------------------------------------------------ backward
-// Both backward kernels run 512 threads per CTA: FOUR threads per score row (thread = (row, quarter); quarter = the
-// 32-key chunk of every 128-key block it owns), so one block costs each thread a single 32-element chunk and 16 warps
-// hide each other's TMEM / MUFU latency.  Warp w = 4 * quarter + row / 32 reads TMEM lanes 32 * (w & 3) as required.
-//
-// delta[row] = rowsum(dO . O): computed once by the dQ kernel (which sees every query row exactly once), parked in a
-// caller-provided fp32 workspace [B, nh, seq_q] and read back by the dK/dV kernel (launched after it on the same stream).
-template <int D>
-__device__ __forceinline__ float delta_partial(const __nv_bfloat16* o, int64_t ldo, const __nv_bfloat16* d_o, int64_t lddo,
-                                               int64_t grow, int col0) {
-  // this thread's quarter of the row: D / 4 columns starting at col0
-  const uint4* po = reinterpret_cast<const uint4*>(o + grow * ldo + col0);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + grow * lddo + col0);
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < D / 32; ++i) {
-    const uint4 vo = __ldg(po + i), vd = __ldg(pd + i);
-    const uint32_t wo[4] = {vo.x, vo.y, vo.z, vo.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc += bf16lo(wo[e]) * bf16lo(wd[e]) + bf16hi(wo[e]) * bf16hi(wd[e]);
-  }
-  return acc;
-}
-
-// P~ and dS of this thread's 32-key chunk c of one 128-key block: reads S (col 32c) and dP (col 128 + 32c) from TMEM,
-// writes bf16 into the swizzled [128][128] tiles.
-//   P~  = keep/(1-p) . P      (tile for dV += P~^T dO; equals P without dropout)
-//   dS  = P . (keep/(1-p) . dP - delta)
-// mw: attend bits of the chunk for this row (key bits AND causal limit; the existing keys when the row attends nothing).
-template <bool kWriteP, bool kBias, bool kDrop>
-__device__ __forceinline__ void softmax_grad_chunk(const AttnParams& p, uint32_t lane_addr, int c, uint32_t mw,
-                                                   const float* bias_row, int key0, bool row_ok, float m, float inv,
-                                                   float delta, int64_t drow, uint32_t p_base, uint32_t ds_base, int row_in_tile,
-                                                   float* bias_bins = nullptr) {
-  const bool flat = !(m > -FLT_MAX) || !row_ok;   // no attended key (uniform row) or a row beyond the sequence (p = 0)
-  const float c1 = flat ? 0.f : p.scale * kL2E, mc = flat ? 0.f : m * kL2E, bsc = flat ? 0.f : kL2E;
-  const float inv_ok = row_ok ? inv : 0.f;
-  uint32_t rs[32], rp[32];
-  tmem_ld_32x32(lane_addr + c * 32, rs);
-  tmem_ld_32x32(lane_addr + 128 + c * 32, rp);
-  uint32_t keep = 0xffffffffu;
-  if (kDrop) keep = keep_word(p, drow, key0, (p.seq_k + 7) >> 3);
-  const float ks = kDrop ? p.drop_scale : 1.f;
-  const int lim = max(p.seq_k - 1 - key0, 0);
-  const float* bk = kBias ? bias_row + min(key0, p.seq_k - 1) : nullptr;
-  tmem_ld_wait();
-  uint32_t pk[16], dk[16];
-#pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    float pv[2], dv[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float off = -mc;
-      if (kBias) off = fmaf(__ldg(bk + min(e + u, lim)), bsc, -mc);
-      float pr = ex2(fmaf(__uint_as_float(rs[e + u]), c1, off)) * inv_ok;
-      pr = (mw >> (e + u)) & 1u ? pr : 0.f;
-      if (kDrop) {
-        const float kmul = (keep >> (e + u)) & 1u ? ks : 0.f;
-        pv[u] = pr * kmul;
-        dv[u] = pr * fmaf(__uint_as_float(rp[e + u]), kmul, -delta);
-      } else {
-        pv[u] = pr;
-        dv[u] = pr * (__uint_as_float(rp[e + u]) - delta);
-      }
-    }
-    pk[e >> 1] = pack_bf16(pv[0], pv[1]);
-    dk[e >> 1] = pack_bf16(dv[0], dv[1]);
-    if (kBias && bias_bins != nullptr) {   // d bias(key - row) += dS: one bin per diagonal of the 128 x 128 block
-      atomicAdd(bias_bins + (c * 32 + e - row_in_tile + 127), dv[0]);
-      atomicAdd(bias_bins + (c * 32 + e + 1 - row_in_tile + 127), dv[1]);
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (kWriteP) sts128(swz(p_base + (c >> 1) * 16384, row_in_tile, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-    sts128(swz(ds_base + (c >> 1) * 16384, row_in_tile, (c & 1) * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-  }
-}
-
-// attend word of chunk c of key block j for query row (tile qt, row_in_tile)
-__device__ __forceinline__ uint32_t row_word(const AttnParams& p, uint32_t kword, int j, int qt, int row_in_tile, int c, bool none) {
-  uint32_t m = kword;
-  if (p.causal) m &= low_bits(qt * 128 + row_in_tile + p.coff - (j * 128 + c * 32) + 1);
-  if (none) m = low_bits(p.seq_k - (j * 128 + c * 32));   // uniform over the existing keys of the visited blocks
-  return m;
-}
-
-// ------------------------------------------------------------------------------------------------ backward: dQ
-template <int D, bool kBias, bool kDrop>
-__global__ void __launch_bounds__(512, 1)
-sattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
-                    const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                    const __grid_constant__ AttnParams p, const __nv_bfloat16* __restrict__ o, int64_t ldo,
-                    const __nv_bfloat16* __restrict__ d_o, int64_t lddo, const float* __restrict__ stats,
-                    __nv_bfloat16* __restrict__ dq, int64_t lddq, float* __restrict__ delta_ws) {
-  constexpr int TB = (D / 64) * 16384;
-  constexpr int NB = (D == 64) ? 2 : 1;   // K / V buffers
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sdO = sQ + TB;
-  uint8_t* sK = sdO + TB;
-  uint8_t* sV = sK + NB * TB;
-  uint8_t* sdS = sV + NB * TB;     // 2 slabs
-  const int nbk = (p.seq_k + 127) / 128;
-  float* sDelta = reinterpret_cast<float*>(sdS + 32768);   // [4][128] partial row sums
-  float* sBins = sDelta + 512;                             // [256] diagonal sums of dS (gradient of the relative-position bias)
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(sBins + 256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk);   // q, kv0, kv1, a, b
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int ntq = (p.seq_q + 127) / 128;
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
-  const int rit = tid & 127, quarter = tid >> 7;          // row in tile, owned chunk
-
-  if (tid == 0) {
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  const bool want_dbias = kBias && p.d_rel_bias != nullptr;
-  if (tid < 256) sBins[tid] = 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t cdQ = 256;
-  uint32_t kvuse[2] = {0, 0}, aphase = 0, bphase = 0, qphase = 0;
-  // descriptor bases built once: the issuing thread only adds constants per MMA (it is also a worker: issue time is on the
-  // critical path of every block)
-  const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_do = make_smem_desc(smem_u32(sdO), 16, 1024);
-  const uint64_t desc_k = make_smem_desc(smem_u32(sK), 16, 1024), desc_v = make_smem_desc(smem_u32(sV), 16, 1024);
-  const uint64_t desc_ds = make_smem_desc(smem_u32(sdS), 16, 1024), desc_kmn = make_smem_desc(smem_u32(sK), 16384, 1024);
-
-  // Persistent CTA: work items (query tile, head, sample), late (heavier when causal) tiles first, dealt round-robin so
-  // every CTA gets a mix; TMEM, barriers and the tensor-map fetch are paid once per CTA instead of once per tile.
-  const int hb = p.heads * p.batch;
-  const int n_items = ntq * hb;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int qt = ntq - 1 - item / hb;
-    const int h = (item % hb) % p.heads, b = (item % hb) / p.heads;
-    const int r0 = qt * 128, row = r0 + rit;
-    const bool row_ok = row < p.seq_q;
-    const int nblk = p.causal ? min(nbk, (qt * 128 + 127 + p.coff) / 128 + 1) : nbk;
-    const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
-
-    if (tid == 0) {   // nothing of the previous item is still reading these buffers (its last MMA was waited for)
-      mbar_arrive_expect_tx(&bars[0], 2 * TB);
-      tma_tile<D>(sQ, &map_q, &bars[0], colq, rowq + r0);
-      tma_tile<D>(sdO, &map_do, &bars[0], colq, rowq + r0);
-      mbar_arrive_expect_tx(&bars[1], 2 * TB);
-      tma_tile<D>(sK, &map_k, &bars[1], colq, rowk);
-      tma_tile<D>(sV, &map_v, &bars[1], colq, rowk);
-    }
-    build_key_bits(kbits, p.key_mask, b, p.seq_k, 4 * nbk);
-    sDelta[quarter * 128 + rit] = row_ok ? delta_partial<D>(o, ldo, d_o, lddo, (int64_t)rowq + row, colq + quarter * (D / 4)) : 0.f;
-    __syncthreads();
-    float m = 0.f, inv = 0.f;
-    const float delta = (sDelta[rit] + sDelta[128 + rit]) + (sDelta[256 + rit] + sDelta[384 + rit]);
-    if (row_ok) {
-      const float2 st = *reinterpret_cast<const float2*>(stats + (((int64_t)b * p.heads + h) * p.seq_q + row) * 2);
-      m = st.x; inv = st.y;
-      if (quarter == 0) delta_ws[((int64_t)b * p.heads + h) * p.seq_q + row] = delta;
-    }
-    const bool none = !(m > -FLT_MAX);
-    const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
-    const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
-
-    for (int j = 0; j < nblk; ++j) {
-      const int buf = (NB == 2) ? (j & 1) : 0;
-      if (tid == 0) {
-        if (j == 0) { mbar_wait(&bars[0], qphase & 1); }
-        mbar_wait(&bars[1 + buf], kvuse[buf] & 1); kvuse[buf]++;
-        tc_fence_after();
-        const uint64_t off = (uint64_t)((buf * TB) >> 4);
-        mma_qk_desc<D>(tmem_base, desc_q, desc_k + off);            // S
-        mma_qk_desc<D>(tmem_base + 128, desc_do, desc_v + off);     // dP = dO V^T
-        umma_commit(&bars[3]);
-        if (NB == 2 && j + 1 < nblk) {   // the next block's tiles, after this block's MMAs are on their way
-          mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
-          tma_tile<D>(sK + (buf ^ 1) * TB, &map_k, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
-          tma_tile<D>(sV + (buf ^ 1) * TB, &map_v, &bars[1 + (buf ^ 1)], colq, rowk + (j + 1) * 128);
-        }
-      }
-      const uint32_t mw = row_word(p, kbits[4 * j + quarter], j, qt, rit, quarter, none);
-      __syncwarp();
-      mbar_wait(&bars[3], aphase & 1); aphase++;
-      tc_fence_after();
-      softmax_grad_chunk<false, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, j * 128 + quarter * 32, row_ok, m, inv,
-                                              delta, drow, 0, smem_u32(sdS), rit, want_dbias ? sBins : nullptr);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (want_dbias) {   // flush this block's 255 diagonals: bin i holds key - row = j * 128 - r0 + i - 127
-        if (tid < 255) {
-          const float v = sBins[tid];
-          const int idx = j * 128 - r0 + tid - 127 + p.seq_q - 1;
-          if (v != 0.f && idx >= 0 && idx < p.seq_q + p.seq_k - 1)
-            atomicAdd(p.d_rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + idx, v);
-          sBins[tid] = 0.f;
-        }
-        __syncthreads();
-      }
-      if (tid == 0) {
-        tc_fence_after();
-        mma_pv_desc<D>(tmem_base + cdQ, desc_ds, desc_kmn + (uint64_t)((buf * TB) >> 4), j != 0);   // dQ += dS K_j
-        umma_commit(&bars[4]);
-        if (NB == 1 && j + 1 < nblk) {   // single buffer: reload K / V once this block's MMAs have drained
-          mbar_wait(&bars[4], bphase & 1);
-          mbar_arrive_expect_tx(&bars[1], 2 * TB);
-          tma_tile<D>(sK, &map_k, &bars[1], colq, rowk + (j + 1) * 128);
-          tma_tile<D>(sV, &map_v, &bars[1], colq, rowk + (j + 1) * 128);
-        }
-      }
-      __syncwarp();
-      mbar_wait(&bars[4], bphase & 1); bphase++;
-      tc_fence_after();
-    }
-    qphase++;
-    // dQ tile: quarter q stores columns [q * D/4, (q + 1) * D/4)
-    if (D == 64) {
-      uint32_t r[16];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                     "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                   : "r"(lane_addr + cdQ + quarter * 16) : "memory");
-      tmem_ld_wait();
-      if (row_ok) {
-        __nv_bfloat16* dst = dq + ((int64_t)rowq + row) * lddq + colq + quarter * 16;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[8 * g]) * p.scale, __uint_as_float(r[8 * g + 1]) * p.scale);
-          v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * p.scale, __uint_as_float(r[8 * g + 3]) * p.scale);
-          v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * p.scale, __uint_as_float(r[8 * g + 5]) * p.scale);
-          v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * p.scale, __uint_as_float(r[8 * g + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(dst + 8 * g) = v;
-        }
-      }
-    } else {
-      uint32_t r[32];
-      tmem_ld_32x32(lane_addr + cdQ + quarter * 32, r);
-      tmem_ld_wait();
-      if (row_ok) store_row_bf16(dq + ((int64_t)rowq + row) * lddq + colq + quarter * 32, r, p.scale);
-    }
-    tc_fence_before();   // the next item's S / dP / dQ MMAs overwrite TMEM this item's threads have just read
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-// ------------------------------------------------------------------------------------------------ backward: dK, dV
-template <int D, bool kBias, bool kDrop>
-__global__ void __launch_bounds__(512, 1)
-sattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
-                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                     const __grid_constant__ AttnParams p, const float* __restrict__ stats,
-                     const float* __restrict__ delta_ws, __nv_bfloat16* __restrict__ dk, int64_t lddk,
-                     __nv_bfloat16* __restrict__ dv, int64_t lddv) {
-  constexpr int TB = (D / 64) * 16384;
-  constexpr int NB = (D == 64) ? 2 : 1;   // Q / dO buffers
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + TB;
-  uint8_t* sQ = sV + TB;
-  uint8_t* sdO = sQ + NB * TB;
-  uint8_t* sP = sdO + NB * TB;     // 2 slabs
-  uint8_t* sdS = sP + 32768;       // 2 slabs
-  uint32_t* kbits4 = reinterpret_cast<uint32_t*>(sdS + 32768);   // the 4 words of this key block
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbits4 + 4);     // kv, q0, q1, a, b
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int ntq = (p.seq_q + 127) / 128;
-  const int nbk = (p.seq_k + 127) / 128;
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x, lane = threadIdx.x & 31;
-  const int rit = tid & 127, quarter = tid >> 7;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t cdV = 256, cdK = 256 + D;
-  uint32_t quse[2] = {0, 0}, aphase = 0, bphase = 0, kphase = 0;
-  const uint64_t desc_k = make_smem_desc(smem_u32(sK), 16, 1024), desc_v = make_smem_desc(smem_u32(sV), 16, 1024);
-  const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_do = make_smem_desc(smem_u32(sdO), 16, 1024);
-  const uint64_t desc_p_mn = make_smem_desc(smem_u32(sP), 16384, 1024), desc_ds_mn = make_smem_desc(smem_u32(sdS), 16384, 1024);
-  const uint64_t desc_q_mn = make_smem_desc(smem_u32(sQ), 16384, 1024), desc_do_mn = make_smem_desc(smem_u32(sdO), 16384, 1024);
-
-  // Persistent CTA over work items (key block, head, sample); early key blocks (seen by the most query tiles when
-  // causal) first, dealt round-robin.
-  const int hb = p.heads * p.batch;
-  const int n_items = nbk * hb;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const int kb = item / hb;
-  const int h = (item % hb) % p.heads, b = (item % hb) / p.heads;
-  const int i0 = p.causal ? max(0, (kb * 128 - p.coff) / 128) : 0;   // first query tile with a row that may see this key block
-  const int colq = h * D, rowq = b * p.seq_q, rowk = b * p.seq_k;
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 2 * TB);
-    tma_tile<D>(sK, &map_k, &bars[0], colq, rowk + kb * 128);
-    tma_tile<D>(sV, &map_v, &bars[0], colq, rowk + kb * 128);
-    mbar_arrive_expect_tx(&bars[1], 2 * TB);
-    tma_tile<D>(sQ, &map_q, &bars[1], colq, rowq + i0 * 128);
-    tma_tile<D>(sdO, &map_do, &bars[1], colq, rowq + i0 * 128);
-  }
-  if (tid < 128) {
-    const int key = kb * 128 + tid;
-    const bool a = key < p.seq_k && (p.key_mask == nullptr || p.key_mask[(int64_t)b * p.seq_k + key] != 0);
-    const uint32_t bits = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) kbits4[warp] = bits;
-  }
-  __syncthreads();
-  const uint32_t kword = kbits4[quarter];
-  for (int i = i0; i < ntq; ++i) {
-    const int it = i - i0;
-    const int buf = (NB == 2) ? (it & 1) : 0;
-    const int row = i * 128 + rit;
-    const bool row_ok = row < p.seq_q;
-    float m = 0.f, inv = 0.f, delta = 0.f;
-    if (row_ok) {
-      const int64_t sidx = ((int64_t)b * p.heads + h) * p.seq_q + row;
-      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + sidx * 2));
-      m = st.x; inv = st.y;
-      delta = __ldg(delta_ws + sidx);
-    }
-    if (tid == 0) {
-      if (it == 0) mbar_wait(&bars[0], kphase & 1);
-      mbar_wait(&bars[1 + buf], quse[buf] & 1); quse[buf]++;
-      tc_fence_after();
-      const uint64_t off = (uint64_t)((buf * TB) >> 4);
-      mma_qk_desc<D>(tmem_base, desc_q + off, desc_k);             // S  = Q_i K_j^T
-      mma_qk_desc<D>(tmem_base + 128, desc_do + off, desc_v);      // dP = dO_i V_j^T
-      umma_commit(&bars[3]);
-      if (NB == 2 && i + 1 < ntq) {   // the next query tile, after this tile's MMAs are on their way
-        mbar_arrive_expect_tx(&bars[1 + (buf ^ 1)], 2 * TB);
-        tma_tile<D>(sQ + (buf ^ 1) * TB, &map_q, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
-        tma_tile<D>(sdO + (buf ^ 1) * TB, &map_do, &bars[1 + (buf ^ 1)], colq, rowq + (i + 1) * 128);
-      }
-    }
-    const bool none = !(m > -FLT_MAX);
-    const uint32_t mw = row_word(p, kword, kb, i, rit, quarter, none);
-    const float* bias_row = kBias ? p.rel_bias + (int64_t)h * (p.seq_q + p.seq_k - 1) + (p.seq_q - 1 - min(row, p.seq_q - 1)) : nullptr;
-    const int64_t drow = ((int64_t)b * p.heads + h) * p.seq_q + row;
-    __syncwarp();
-    mbar_wait(&bars[3], aphase & 1); aphase++;
-    tc_fence_after();
-    softmax_grad_chunk<true, kBias, kDrop>(p, lane_addr, quarter, mw, bias_row, kb * 128 + quarter * 32, row_ok, m, inv,
-                                           delta, drow, smem_u32(sP), smem_u32(sdS), rit);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t off = (uint64_t)((buf * TB) >> 4);
-      mma_tn_desc<D>(tmem_base + cdV, desc_p_mn, desc_do_mn + off, it != 0);    // dV_j += P~^T dO_i
-      mma_tn_desc<D>(tmem_base + cdK, desc_ds_mn, desc_q_mn + off, it != 0);    // dK_j += dS^T Q_i
-      umma_commit(&bars[4]);
-      if (NB == 1 && i + 1 < ntq) {
-        mbar_wait(&bars[4], bphase & 1);
-        mbar_arrive_expect_tx(&bars[1], 2 * TB);
-        tma_tile<D>(sQ, &map_q, &bars[1], colq, rowq + (i + 1) * 128);
-        tma_tile<D>(sdO, &map_do, &bars[1], colq, rowq + (i + 1) * 128);
-      }
-    }
-    __syncwarp();
-    mbar_wait(&bars[4], bphase & 1); bphase++;
-    tc_fence_after();
-  }
-  // quarters 0,1 store dV, quarters 2,3 store dK; each stores half of the D columns of its key row
-  {
-    const int key = kb * 128 + rit;
-    const bool is_k = quarter >= 2;
-    const int half = quarter & 1;
-    const uint32_t src = lane_addr + (is_k ? cdK : cdV) + half * (D / 2);
-    __nv_bfloat16* dst = (is_k ? dk + ((int64_t)rowk + key) * lddk : dv + ((int64_t)rowk + key) * lddv) + colq + half * (D / 2);
-    const float mul = is_k ? p.scale : 1.f;
-#pragma unroll
-    for (int c = 0; c < D / 64; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(src + c * 32, r);
-      tmem_ld_wait();
-      if (key < p.seq_k) store_row_bf16(dst + c * 32, r, mul);
-    }
-  }
-  kphase++;
-  tc_fence_before();   // the next item's MMAs overwrite TMEM this item's threads have just read
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-struct Maps { CUtensorMap q, k, v, d_o; };
-
-int build_maps(Maps& mp, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-               int64_t lddo, int64_t batch, int64_t seq_q, int64_t seq_k, int64_t heads, int d, int64_t total_tokens = 0) {
-  int rc;
-  const uint64_t cols = (uint64_t)(heads * d);
-  const uint64_t rows_q = (uint64_t)(total_tokens > 0 ? total_tokens : batch * seq_q);
-  const uint64_t rows_k = (uint64_t)(total_tokens > 0 ? total_tokens : batch * seq_k);
-  if ((rc = make_tensor_map_2d(&mp.q, q, cols, rows_q, (uint64_t)ldq, 64, 128))) return rc;
-  if ((rc = make_tensor_map_2d(&mp.k, k, cols, rows_k, (uint64_t)ldk, 64, 128))) return rc;
-  if ((rc = make_tensor_map_2d(&mp.v, v, cols, rows_k, (uint64_t)ldv, 64, 128))) return rc;
-  if (d_o != nullptr && (rc = make_tensor_map_2d(&mp.d_o, d_o, cols, rows_q, (uint64_t)lddo, 64, 128))) return rc;
-  return 0;
-}
-
-size_t kbits_bytes(int64_t seq_k) {
-  const size_t words = 4 * (size_t)((seq_k + 127) / 128);
-  return (words + (words & 1)) * 4;
-}
-
 template <int D>
 int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float* stats, int64_t batch, cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
@@ -973,64 +413,6 @@ int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float*
   dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
   kern<<<grid, 608, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
   return check_launch("mmgl_attn_fwd");
-}
-
-template <int D, bool kBias, bool kDrop>
-int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
-                 const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* delta_ws,
-                 int64_t batch, cudaStream_t stream) {
-  constexpr int TB = (D / 64) * 16384;
-  constexpr int NB = (D == 64) ? 2 : 1;
-  {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 32768 + 2048 + 1024 + kbits_bytes(p.seq_k) + 5 * 8 + 16;
-    auto kern = sattn_bwd_dq_kernel<D, kBias, kDrop>;
-    MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t items = (int64_t)((p.seq_q + 127) / 128) * p.heads * batch;
-    dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-    kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
-                                      (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq, delta_ws);
-    if (int rc = check_launch("mmgl_attn_bwd(dq)")) return rc;
-  }
-  {
-    const size_t smem = (2 + 2 * NB) * (size_t)TB + 65536 + 16 + 5 * 8 + 16;
-    auto kern = sattn_bwd_dkv_kernel<D, kBias, kDrop>;
-    MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t items = (int64_t)((p.seq_k + 127) / 128) * p.heads * batch;
-    dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-    kern<<<grid, 512, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, stats, delta_ws, (__nv_bfloat16*)dk, lddk,
-                                      (__nv_bfloat16*)dv, lddv);
-    return check_launch("mmgl_attn_bwd(dkv)");
-  }
-}
-
-template <int D>
-int launch_bwd(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
-               const float* stats, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* delta_ws,
-               int64_t batch, cudaStream_t stream) {
-  const bool bias = p.rel_bias != nullptr, drop = p.drop_thresh != 0;
-#define MMGL_BWD(B_, R_) launch_bwd_v<D, B_, R_>(mp, p, o, ldo, d_o, lddo, stats, dq, lddq, dk, lddk, dv, lddv, delta_ws, batch, stream)
-  if (bias) return drop ? MMGL_BWD(true, true) : MMGL_BWD(true, false);
-  return drop ? MMGL_BWD(false, true) : MMGL_BWD(false, false);
-#undef MMGL_BWD
-}
-
-int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) {
-  MMGL_REQUIRE(a->batch > 0 && a->seq_q > 0 && a->seq_k > 0 && a->heads > 0, "%s: empty problem", who);
-  MMGL_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "%s: head_dim must be 64 or 128 (got %lld)", who, (long long)a->head_dim);
-  MMGL_REQUIRE(a->batch < 65536 && a->heads < 65536 && a->batch * a->heads * ((a->seq_q + a->seq_k) / 128 + 2) < (1ll << 31),
-               "%s: batch/heads too large for the grid", who);
-  MMGL_REQUIRE(a->seq_k <= 8192 && a->seq_q <= (1 << 20), "%s: seq_k must be <= 8192", who);
-  MMGL_REQUIRE(!a->causal || a->seq_q <= a->seq_k, "%s: causal needs seq_q <= seq_k (keys = prefix + the queries' own positions)", who);
-  MMGL_REQUIRE(a->scale > 0.f, "%s: scale must be positive", who);
-  MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0,1)", who);
-  p.key_mask = a->key_mask; p.rel_bias = a->rel_bias; p.cu_seqlens = a->cu_seqlens; p.d_rel_bias = nullptr;
-  p.seq_q = (int)a->seq_q; p.seq_k = (int)a->seq_k; p.heads = (int)a->heads; p.causal = a->causal; p.batch = (int)a->batch;
-  p.coff = (int)(a->seq_k - a->seq_q);
-  p.scale = a->scale;
-  p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
-  p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
-  p.drop_seed = a->dropout_seed;
-  return 0;
 }
 
 }  // namespace
@@ -1064,32 +446,3 @@ extern "C" int mmgl_attn_fwd(const mmgl_attn_args* a, void* stream_) {
   return launch_fwd<128>(mp, p, a->o, a->ldo, a->stats, a->batch, s);
 }
 
-extern "C" size_t mmgl_attn_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t heads) {
-  return (size_t)(batch * seq_q * heads) * sizeof(float);
-}
-
-extern "C" int mmgl_attn_bwd(const mmgl_attn_args* a, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
-                             int64_t lddk, void* dv, int64_t lddv, float* d_rel_bias, void* workspace,
-                             size_t workspace_bytes, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  MMGL_REQUIRE(a != nullptr, "mmgl_attn_bwd: null args");
-  MMGL_BIND(a->q, "mmgl_attn_bwd");
-  AttnParams p;
-  if (int rc = fill_params("mmgl_attn_bwd", a, p)) return rc;
-  MMGL_REQUIRE(d_o && a->k && a->v && a->o && a->stats && dq && dk && dv, "mmgl_attn_bwd: null pointer");
-  MMGL_REQUIRE(a->cu_seqlens == nullptr, "mmgl_attn_bwd: variable-length batches are forward-only (frozen encoders)");
-  MMGL_REQUIRE(d_rel_bias == nullptr || a->rel_bias != nullptr, "mmgl_attn_bwd: d_rel_bias without rel_bias");
-  p.d_rel_bias = d_rel_bias;
-  MMGL_REQUIRE(workspace != nullptr && workspace_bytes >= mmgl_attn_bwd_workspace_bytes(a->batch, a->seq_q, a->heads),
-               "mmgl_attn_bwd: workspace too small (need mmgl_attn_bwd_workspace_bytes)");
-  MMGL_REQUIRE(aligned16(d_o) && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(dq) &&
-               aligned16(dk) && aligned16(dv), "mmgl_attn_bwd: pointers must be 16B aligned");
-  MMGL_REQUIRE(lddo % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && lddq % 8 == 0 &&
-               lddk % 8 == 0 && lddv % 8 == 0, "mmgl_attn_bwd: leading dims must be multiples of 8");
-  Maps mp;
-  if (int rc = build_maps(mp, a->q, a->ldq, a->k, a->ldk, a->v, a->ldv, d_o, lddo, a->batch, a->seq_q, a->seq_k, a->heads, (int)a->head_dim)) return rc;
-  float* ws = reinterpret_cast<float*>(workspace);
-  if (a->head_dim == 64)
-    return launch_bwd<64>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, ws, a->batch, s);
-  return launch_bwd<128>(mp, p, a->o, a->ldo, d_o, lddo, a->stats, dq, lddq, dk, lddk, dv, lddv, ws, a->batch, s);
-}

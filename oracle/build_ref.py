@@ -2,11 +2,11 @@
 
 The reference is pure Python, so "compiling it from the sources where they lie" means byte-compiling
 ``/root/reference/model/{modelling_cross_attention,modelling_self_attention,graph}.py`` with ``py_compile`` into
-``oracle/_ref/model/*.pyc`` (source-less, unchecked-hash pycs).  No reference source text enters the repository;
+``oracle/_ref/model/*.bytecode`` (source-less, unchecked-hash pyc files under another extension).  No reference source text enters the repository;
 ``oracle/_ref/`` is git-ignored but travels to the GPU box with the snapshot, like the built ``.so`` (same image, same
 CPython 3.12 magic number on both sides).  ``__graft_entry__.build()`` runs this when ``/root/reference`` exists.
 
-    python oracle/build_ref.py            # -> oracle/_ref/model/*.pyc + oracle/_ref/MANIFEST.json
+    python oracle/build_ref.py            # -> oracle/_ref/model/*.bytecode + oracle/_ref/MANIFEST.json
 
 ``oracle/ref_loader.py`` imports the result; bench.py's ``--impl reference`` (CPU arm, kind "reference") and
 ``--impl eager`` (the same modules on the B200: the honest GPU baseline) run it.  Nothing in the product
@@ -33,7 +33,7 @@ def build(force: bool = False) -> str | None:
     manifest = {"python": sys.version.split()[0], "magic": __import__("importlib.util").util.MAGIC_NUMBER.hex(), "files": {}}
     for rel in FILES:
         src = os.path.join(REF_ROOT, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + ".bytecode")   # a .pyc by content; gpurun snapshots skip *.pyc
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         with open(src, "rb") as f:
             digest = hashlib.sha256(f.read()).hexdigest()

@@ -27,6 +27,35 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
+# ----------------------------------------------------------------------------
+# optional emulation of the CUDA path's bf16 STORAGE points
+# ----------------------------------------------------------------------------
+# The reference arithmetic is fp32 end to end.  The kernels keep fp32 accumulators but STORE activations in bf16
+# (LayerNorm outputs, q / k / v, the attention output, FFN hidden, block outputs).  A ReLU whose pre-activation sits
+# within one bf16 ulp of zero can then take the other branch -- a discontinuity, so gradients downstream differ from the
+# pure-fp32 oracle by O(sqrt(flipped fraction)) however exact the kernels are.  Inside ``with bf16_storage():`` the oracle
+# rounds the same tensors at the same points (straight-through: value rounded, gradient untouched), which makes the two
+# sides take the same branches and lets the parity tests use a TIGHT tolerance for the kernel algebra; the comparison
+# with the unrounded oracle / reference fixtures stays as the (looser) statement of bf16 accuracy.
+_STORE = [False]
+
+
+class bf16_storage:
+    def __enter__(self):
+        self.prev = _STORE[0]
+        _STORE[0] = True
+        return self
+
+    def __exit__(self, *exc):
+        _STORE[0] = self.prev
+        return False
+
+
+def _st(t: Tensor) -> Tensor:
+    if not _STORE[0]:
+        return t
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
 
 # ----------------------------------------------------------------------------
 # masks / positions
@@ -82,9 +111,9 @@ def mpt_attention(
     b, s, h = x.shape
     d = h // num_heads
     scaling = d ** -0.5
-    q = F.linear(x, p[prefix + "q_proj.weight"], p.get(prefix + "q_proj.bias")) * scaling      # :194
-    k = F.linear(kv_src, p[prefix + "k_proj.weight"], p.get(prefix + "k_proj.bias"))         # :198
-    v = F.linear(kv_src, p[prefix + "v_proj.weight"], p.get(prefix + "v_proj.bias"))         # :199
+    q = _st(F.linear(x, p[prefix + "q_proj.weight"], p.get(prefix + "q_proj.bias")) * scaling) # :194
+    k = _st(F.linear(kv_src, p[prefix + "k_proj.weight"], p.get(prefix + "k_proj.bias")))    # :198
+    v = _st(F.linear(kv_src, p[prefix + "v_proj.weight"], p.get(prefix + "v_proj.bias")))    # :199
     nk = kv_src.shape[1]
 
     def shape(t, n):                                                                           # :176-177
@@ -98,7 +127,7 @@ def mpt_attention(
         w = w.view(b * num_heads, s, nk)
     w = F.softmax(w, dim=-1)                                                                   # :235
     o = torch.bmm(w, v)                                                                        # :258
-    o = o.view(b, num_heads, s, d).transpose(1, 2).reshape(b, s, h)                            # :266-271
+    o = _st(o.view(b, num_heads, s, d).transpose(1, 2).reshape(b, s, h))                       # :266-271
     return F.linear(o, p[prefix + "out_proj.weight"], p.get(prefix + "out_proj.bias"))        # :273
 
 
@@ -236,7 +265,7 @@ def mpt_decoder_layer(
     residual = x
     hs = x
     if do_layer_norm_before:                                                                   # :319-320
-        hs = F.layer_norm(hs, (h,), p["self_attn_layer_norm.weight"], p["self_attn_layer_norm.bias"], eps)
+        hs = _st(F.layer_norm(hs, (h,), p["self_attn_layer_norm.weight"], p["self_attn_layer_norm.bias"], eps))
     if cross_attention:
         hs = mpt_attention(hs, bank, bank_add_mask, p, num_heads)                              # :323-331
     else:
@@ -247,14 +276,15 @@ def mpt_decoder_layer(
         hs = residual + torch.tanh(p["gating1"]) * hs
     else:
         hs = residual + hs
+    hs = _st(hs)
     if not do_layer_norm_before:                                                               # :340-341
-        hs = F.layer_norm(hs, (h,), p["self_attn_layer_norm.weight"], p["self_attn_layer_norm.bias"], eps)
+        hs = _st(F.layer_norm(hs, (h,), p["self_attn_layer_norm.weight"], p["self_attn_layer_norm.bias"], eps))
     shape = hs.shape
     hs = hs.reshape(-1, h)
     residual = hs
     if do_layer_norm_before:                                                                   # :349-350
-        hs = F.layer_norm(hs, (h,), p["final_layer_norm.weight"], p["final_layer_norm.bias"], eps)
-    hs = F.relu(F.linear(hs, p["fc1.weight"], p.get("fc1.bias")))                              # :352-353 (OPT: relu)
+        hs = _st(F.layer_norm(hs, (h,), p["final_layer_norm.weight"], p["final_layer_norm.bias"], eps))
+    hs = _st(F.relu(F.linear(hs, p["fc1.weight"], p.get("fc1.bias"))))                         # :352-353 (OPT: relu)
     hs = F.linear(hs, p["fc2.weight"], p.get("fc2.bias"))                                      # :355
     if drop2 is not None:                                                                      # :356
         hs = hs * drop2.view(hs.shape)
@@ -262,8 +292,9 @@ def mpt_decoder_layer(
         hs = (residual + torch.tanh(p["gating2"]) * hs).view(shape)
     else:
         hs = (residual + hs).view(shape)
+    hs = _st(hs)
     if not do_layer_norm_before:                                                               # :364-365
-        hs = F.layer_norm(hs, (h,), p["final_layer_norm.weight"], p["final_layer_norm.bias"], eps)
+        hs = _st(F.layer_norm(hs, (h,), p["final_layer_norm.weight"], p["final_layer_norm.bias"], eps))
     return hs
 
 
@@ -300,7 +331,7 @@ def mpt_causal_lm(
     pos = F.embedding(learned_positions(attention_mask), p[dec + "embed_positions.weight"])   # :548
     if dec + "project_in.weight" in p:
         x = F.linear(x, p[dec + "project_in.weight"])                                          # :550-551
-    x = x + pos                                                                                # :553
+    x = _st(x + pos)                                                                           # :553
     nlw = cfg["neighbor_layer_wise"]
     for idx in range(cfg["num_layers"]):                                                       # :576
         x = mpt_decoder_layer(x, sub(p, f"{dec}layers.{idx}."), nh, cross_attention=False,
@@ -311,7 +342,7 @@ def mpt_causal_lm(
                                   bank=bank, bank_add_mask=bank_add, do_layer_norm_before=pre_ln,
                                   flamingo=cfg.get("flamingo", True))
     if dec + "final_layer_norm.weight" in p:                                                   # :635-636
-        x = F.layer_norm(x, (x.shape[-1],), p[dec + "final_layer_norm.weight"], p[dec + "final_layer_norm.bias"])
+        x = _st(F.layer_norm(x, (x.shape[-1],), p[dec + "final_layer_norm.weight"], p[dec + "final_layer_norm.bias"]))
     if dec + "project_out.weight" in p:
         x = F.linear(x, p[dec + "project_out.weight"])                                         # :638-639
     logits = F.linear(x, p["lm_head.weight"])                                                  # :826
@@ -462,4 +493,5 @@ def cross_attention_model_from_pooled(
         bank = lpe_add(bank, batch["lpe"], p["lpe_embeddings.weight"], p["lpe_embeddings.bias"], n_tok)
     if "graph" in batch and "gnn.w1.weight" in p:
         bank = gnn_add(bank, batch["graph"], p["gnn.w1.weight"], p["gnn.w2.weight"], n_tok)
+    bank = _st(bank)
     return mpt_causal_lm(sub(p, "lm."), cfg, batch["input_ids"], batch["attention_mask"], batch["labels"], bank, mask)

@@ -30,7 +30,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_DIR, "model", "modelling_cross_attention.pyc"))
+    return os.path.exists(os.path.join(REF_DIR, "model", "modelling_cross_attention.bytecode"))
 
 
 def manifest() -> dict:
@@ -53,7 +53,7 @@ _cache = {}
 
 def cross_attention_module():
     if "xa" not in _cache:
-        _cache["xa"] = _load_pyc("mmgl_ref_xattn", "model/modelling_cross_attention.pyc")
+        _cache["xa"] = _load_pyc("mmgl_ref_xattn", "model/modelling_cross_attention.bytecode")
     return _cache["xa"]
 
 

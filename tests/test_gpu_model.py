@@ -70,9 +70,27 @@ def test_cross_attention_model_forward_backward_vs_reference(golden):
         elif k.endswith("k_proj.bias"):
             rep.absolute("d " + k, params[k].grad, gr, 1e-4)      # analytically zero
         else:
-            rep.close("d " + k, params[k].grad, gr, 8e-2)
+            rep.close("d " + k, params[k].grad, gr, 1e-1)
     frozen_with_grad = [n for n, p in params.items() if not p.requires_grad and p.grad is not None]
     assert not frozen_with_grad
+    # the same step against the oracle with the kernels' bf16 storage points emulated (oracle.bf16_storage): both sides take
+    # the same ReLU branches, so this comparison checks the kernel algebra at a tight tolerance; the comparison with the
+    # fp32 reference fixture above states the bf16 accuracy of a 128-wide toy model (one flipped unit of 256 is visible)
+    from oracle import mmgl_oracle as O
+    po = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state"].items()}
+    with O.bf16_storage():
+        loss_o, logits_o = O.cross_attention_model_from_pooled(po, dict(g["cfg"], flamingo=True), g["batch"],
+                                                               g["text_pooled"], g["visual_pooled"])
+    loss_o.backward()
+    rep.close("[bf16-storage] logits", out.logits, logits_o, 1e-2)
+    rep.scalar("[bf16-storage] loss", out.loss, loss_o, 0.0, 5e-3)
+    for k in g["grads"]:
+        if po[k].grad is None or k.endswith("k_proj.bias"):
+            continue
+        if po[k].numel() == 1:
+            rep.scalar("[bf16-storage] d " + k, params[k].grad, po[k].grad, 4e-2, 1e-3)
+        else:
+            rep.close("[bf16-storage] d " + k, params[k].grad, po[k].grad, 3e-2)
     rep.finish()
 
 
@@ -137,14 +155,23 @@ def test_skipping_padding_neighbors_changes_nothing(golden):
     g = golden("wrapper_cross_d64")
     from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig
     from mmgl_b200 import modules as M
+    # the frozen encoders run on the package's kernels (head_dim 64; the fixture's own encoders have head_dim 16, which the
+    # product rejects), so this test builds its own small towers and uses the fixture for the LM weights and the batch only
+    txt = RobertaConfig(vocab_size=512, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                        max_position_embeddings=40, pad_token_id=1)
+    vis = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                           image_size=32, patch_size=16)
     args = types.SimpleNamespace(
         context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=2, n_visual_tokens=2,
-        model_name_or_path=OPTConfig(**g["lm_config"]), text_model=RobertaConfig(**g["text_config"]),
-        visual_model=CLIPVisionConfig(**g["visual_config"]), max_output_length=16, freeze_lm=False,
-        neighbor_layer_wise=2, lora_r=64, lora_alpha=1, lora_dropout=0.0)
+        model_name_or_path=OPTConfig(**g["lm_config"]), text_model=txt, visual_model=vis, max_output_length=16,
+        freeze_lm=False, neighbor_layer_wise=2, lora_r=64, lora_alpha=1, lora_dropout=0.0)
     torch.manual_seed(5)
     model = M.CrossAttentionModel(args, tokenizer=None)
-    model.load_state_dict(g["state"], strict=False)
+    model.load_state_dict({k: v for k, v in g["state"].items() if k.startswith("lm.")}, strict=False)
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if "gating" in n:
+                prm.fill_(0.5)
     M.prepare_for_training(model, "cuda").eval()
     batch = {k: v.cuda() for k, v in g["batch"].items()}
     batch["neighbor_pos_ids"] = torch.tensor([[1, 2, 0], [1, 0, 0]]).cuda()         # padding neighbors present

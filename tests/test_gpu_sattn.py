@@ -41,6 +41,9 @@ def _oracle(qkv, key_mask, heads, causal, scale, d_o=None):
     (2, 300, 2, 64, False, "right"),       # bidirectional with key padding (encoder-style)
     (2, 130, 1, 128, True, "segments"),    # head_dim 128
     (1, 96, 2, 64, True, "none"),          # shorter than one block
+    (6, 640, 32, 64, True, "segments"),    # cfg2 layer shape, 192 (sample, head) items > 148 SMs: CTAs walk several items
+    (3, 1152, 32, 128, True, "segments"),  # cfg5 layer shape (head_dim 128, 9 query tiles)
+    (5, 300, 40, 64, False, "right"),      # 200 items, bidirectional, ragged tail tile
 ])
 def test_self_attention_forward_backward(b, s, heads, d, causal, pad):
     from mmgl_b200 import ops
@@ -65,6 +68,22 @@ def test_self_attention_forward_backward(b, s, heads, d, causal, pad):
     rep.close("dK", x.grad[..., h:2 * h], g_ref[..., h:2 * h], 1e-2)
     rep.close("dV", x.grad[..., 2 * h:], g_ref[..., 2 * h:], 1e-2)
     rep.finish()
+
+
+def test_backward_is_run_to_run_deterministic():
+    """dQ is summed over key blocks in a per-CTA scratch in a fixed order (csrc/sattn_bwd_sm100.cu): bit-identical reruns."""
+    from mmgl_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    b, s, heads, d = 5, 640, 32, 64
+    h = heads * d
+    qkv = randn(gen, b, s, 3 * h).to(BF16)
+    d_o = randn(gen, b, s, h).to(BF16)
+    grads = []
+    for _ in range(3):
+        x = qkv.clone().requires_grad_(True)
+        ops.self_attention(x, None, heads, causal=True, scale=d ** -0.5).backward(d_o)
+        grads.append(x.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
 
 
 def test_padding_keys_have_zero_influence():

@@ -65,10 +65,17 @@ def test_concat_path_inputs_match_reference(golden, lm, pt):
 def test_lora_model_trains_and_is_identity_at_init(lm):
     """Invariant I5: with B = 0 (init) the LoRA-adapted LM equals the base LM; after one backward the LoRA
     matrices (and only adapter / projection parameters) have gradients."""
+    from transformers import OPTConfig, T5Config
     from mmgl_b200.self_attention import LoRALinear, SelfAttentionModel
     torch.manual_seed(0)
     a = _args(lm, "none", lm == "opt")
     a.peft_type = "lora"
+    # head_dim 64: the LM runs on the package's kernels (the fixtures' head_dim-16 models are rejected, no HF fallback)
+    a.model_name_or_path = (T5Config(vocab_size=512, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_decoder_layers=2,
+                                     num_heads=2, decoder_start_token_id=0) if lm == "t5" else
+                            OPTConfig(vocab_size=512, hidden_size=128, num_hidden_layers=4, ffn_dim=256, num_attention_heads=2,
+                                      max_position_embeddings=200, word_embed_proj_dim=128, dropout=0.0))
+    a.context = "text_only"      # no frozen encoders needed: the test isolates the adapters
     model = SelfAttentionModel(a, tokenizer=None).cuda()
     n_lora = sum(isinstance(m, LoRALinear) for m in model.modules())
     assert n_lora == (2 * (2 + 2 * 2) if lm == "t5" else 2 * 4), n_lora   # q and v of every attention block
