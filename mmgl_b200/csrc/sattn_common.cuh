@@ -2,6 +2,7 @@
 // parameters, bit-mask construction, dropout keep words, UMMA issue helpers over precomputed descriptor bases.
 #pragma once
 #include <cfloat>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -45,6 +46,7 @@ struct AttnParams {
   uint32_t drop_thresh;      // 0: no dropout; else round(p * 65536)
   float drop_scale;          // 1 / (1 - p)
   uint64_t drop_seed;
+  int dq_red;                // backward (experiment switch MMGL_SATTN_RED=1): fold dQ parts with red.global.add instead of ld + add + st
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -182,6 +184,10 @@ inline int fill_params(const char* who, const mmgl_attn_args* a, AttnParams& p) 
   p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
   p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
   p.drop_seed = a->dropout_seed;
+  {
+    static const int red = [] { const char* e = getenv("MMGL_SATTN_RED"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.dq_red = red;
+  }
   return 0;
 }
 
