@@ -24,8 +24,11 @@ TOL_Y = 5e-3
 TOL_G = 1.5e-2        # smooth cases / operators without a kink
 TOL_G_RELU = 4e-2     # natural cases, downstream of bf16-induced ReLU mask flips
 TOL_G_FFN = 7e-2      # fc1 / final_layer_norm gradients in the natural cases
-TOL_Y_ST = 5e-3       # against the oracle that emulates the kernels' bf16 storage points (same ReLU branches on both sides)
-TOL_G_ST = 1.5e-2
+# test_gated_cross_layer_at_benchmarked_sizes (H = 2048 / 4096): MEASURED on B200 (profiles/r02_parity_measured.txt) and set to
+# about 2x the measurement.  fp32 oracle: y 2.6e-3; attention-side gradients 1.6e-2; fc1 / final_layer_norm 3.9e-2.
+# Oracle with the kernels' bf16 storage points emulated (oracle.bf16_storage): y 1.9e-3; 1.1e-2; 2.5e-2 -- what remains is
+# the bf16 rounding of the backward intermediates (dO, dS, P: 2^-9 each), not branch flips.
+TOL_BIG = dict(fp32=(5e-3, 3.2e-2, 8e-2), storage=(4e-3, 2.2e-2, 5e-2))
 
 
 def _leaf(t, dtype=None):
@@ -194,8 +197,8 @@ def test_gated_cross_layer_at_benchmarked_sizes(b, s, nk, heads, h, f):
     rep = Report()
     # (1) accuracy: the plain fp32 oracle; (2) algebra: the oracle with the kernels' bf16 storage points emulated, so both
     # sides take the same ReLU branches (oracle.bf16_storage) -- tight tolerance
-    for label, ctx, tol_y, tol_g, tol_ffn in (("fp32", contextlib.nullcontext(), TOL_Y, TOL_G_RELU, TOL_G_FFN),
-                                              ("bf16-storage", O.bf16_storage(), TOL_Y_ST, TOL_G_ST, TOL_G_ST)):
+    for label, ctx, (tol_y, tol_g, tol_ffn) in (("fp32", contextlib.nullcontext(), TOL_BIG["fp32"]),
+                                                ("bf16-storage", O.bf16_storage(), TOL_BIG["storage"])):
         cp = {k: _cpu32(v) for k, v in p.items()}
         xc, bc = _cpu32(x), _cpu32(bank)
         with ctx:

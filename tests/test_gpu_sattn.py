@@ -2,7 +2,7 @@
 oracle's mpt_attention core: the reference's MPTAttention self branch with the additive causal + padding mask
 (model/modelling_cross_attention.py:201-275, :455-476), fp32 on the bf16-rounded inputs.
 
-Tolerances (rel-L2): O 4e-3 (bf16 output + bf16 P operand), gradients 1e-2.  Rows that are padding QUERIES are compared
+Tolerances (rel-L2): O 4e-3 (bf16 output + bf16 P operand), gradients 6e-3 (measured on B200: O 2.2e-3, dQ / dK / dV 2.4e-3 .. 2.8e-3; profiles/r02_parity_measured.txt).  Rows that are padding QUERIES are compared
 too (the reference's loss covers them)."""
 import pytest
 import torch
@@ -64,9 +64,9 @@ def test_self_attention_forward_backward(b, s, heads, d, causal, pad):
     o_ref, g_ref = _oracle(qkv, key_mask if pad != "none" else None, heads, causal, d ** -0.5, d_o)
     rep = Report()
     rep.close("O", o, o_ref, 4e-3)
-    rep.close("dQ", x.grad[..., :h], g_ref[..., :h], 1e-2)
-    rep.close("dK", x.grad[..., h:2 * h], g_ref[..., h:2 * h], 1e-2)
-    rep.close("dV", x.grad[..., 2 * h:], g_ref[..., 2 * h:], 1e-2)
+    rep.close("dQ", x.grad[..., :h], g_ref[..., :h], 6e-3)
+    rep.close("dK", x.grad[..., h:2 * h], g_ref[..., h:2 * h], 6e-3)
+    rep.close("dV", x.grad[..., 2 * h:], g_ref[..., 2 * h:], 6e-3)
     rep.finish()
 
 
@@ -146,9 +146,9 @@ def test_general_attention_forward_backward(b, sq, sk, heads, d, causal, bias, p
     rep = Report()
     rep.close("O", o, o_ref, 4e-3)
     for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
-        rep.close(name, x.grad, r.grad, 1e-2)
+        rep.close(name, x.grad, r.grad, 6e-3)
     if bias:
-        rep.close("d rel_bias", dvec.grad, vec.grad, 1e-2)
+        rep.close("d rel_bias", dvec.grad, vec.grad, 6e-3)
     rep.finish()
 
 
@@ -178,7 +178,7 @@ def test_attention_probability_dropout(b, sq, sk, heads, causal, p):
     rep = Report()
     rep.close("O", o, o_ref, 5e-3)
     for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
-        rep.close(name, x.grad, r.grad, 1.2e-2)
+        rep.close(name, x.grad, r.grad, 7e-3)
     rep.finish()
 
 
@@ -226,5 +226,5 @@ def test_causal_attention_over_prefix_keys(b, sq, prefix, heads, pad):
     rep = Report()
     rep.close("O", o, o_ref, 4e-3)
     for name, x, r in zip(("dQ", "dK", "dV"), xs, rs):
-        rep.close(name, x.grad, r.grad, 1e-2)
+        rep.close(name, x.grad, r.grad, 6e-3)
     rep.finish()

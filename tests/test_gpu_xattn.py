@@ -13,7 +13,7 @@ from util import BF16, assert_close, randn
 pytestmark = pytest.mark.gpu
 
 TOL_O = 4e-3
-TOL_GRAD = 1e-2
+TOL_GRAD = 6e-3   # measured on B200: 2.4e-3 .. 2.8e-3 (profiles/r02_parity_measured.txt)
 
 
 def _case(seed, b, s, nk, heads, d, mask_kind="ragged", scale=1.0):
