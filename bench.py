@@ -48,7 +48,7 @@ def parse():
                     help="control: run the frozen text encoder on all T x 512 padded tokens and on padding neighbors, as the reference does")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--batches", type=int, default=8, help="distinct seeded synthetic batches cycled through")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "tiny"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
     ap.add_argument("--profile-step", action="store_true",
@@ -68,6 +68,10 @@ WORKLOADS = {
     # (python bench.py --workload cfg3); the judged line is cfg2
     "cfg3": dict(kind="self", lm="t5-base", text="roberta-base", visual="clip-vit-base-patch16", s_in=512, s_out=128, t=11,
                  i=5, position_type="none"),
+    # configs[4]: Llama-2-7B + flamingo, ViT-L/14, seq 1024(+128), <=32 neighbors -- an EXTENSION (the reference has no Llama
+    # wrapper): frozen HF Llama layers on the kernels + the reference's gated block (mmgl_b200/llama.py)
+    "cfg5": dict(kind="llama", lm="llama-2-7b", text="roberta-base", visual="clip-vit-large-patch14", s_in=1024, s_out=128,
+                 t=22, i=10, position_type="none", vocab=32000),
     # plumbing-size model for quick checks
     "tiny": dict(lm="opt-125m", text="roberta-base", visual="clip-vit-base-patch16", s_in=128, s_out=128, t=3, i=2,
                  position_type="none"),
@@ -93,6 +97,8 @@ def spec_for(w, batch):
     extra = {}
     if w.get("kind") == "self" and "t5" in w["lm"]:
         extra = dict(vocab_size=32128, decoder_only=False, pad_token_id=0)
+    if w.get("vocab"):
+        extra = dict(vocab_size=w["vocab"], pad_token_id=0)
     return synth.BatchSpec(batch=batch, max_input_length=w["s_in"], max_output_length=w["s_out"], text_neighbors=w["t"],
                            image_neighbors=w["i"], with_lpe=w["position_type"] == "laplacian",
                            with_graph=w["position_type"] == "gnn", **extra)
@@ -224,6 +230,10 @@ def run_reference(a, w):
     if rank != 0:
         return
     os.environ.setdefault("MMGL_ALLOW_RANDOM_INIT", "1")
+    if w.get("kind") == "llama":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no Llama wrapper (run_generation.py:286-301 "
+                          "dispatches t5 / opt / mpt only); cfg5 is an extension, SURVEY 8f row f4"}), flush=True)
+        return
     bsz = a.cpu_sample_batch
     sec, losses, kind, threads, _ = cpu_reference_run(a, w, a.steps, a.warmup, bsz)
     val = bsz / sec
@@ -279,8 +289,9 @@ def run_eager(a, w):
         return
     os.environ.setdefault("MMGL_ALLOW_RANDOM_INIT", "1")
     from oracle import ref_loader as R
-    if not R.available() or not torch.cuda.is_available():
-        print(json.dumps({"impl": "eager", "unavailable": "oracle/_ref not built or no CUDA device"}), flush=True)
+    if not R.available() or not torch.cuda.is_available() or w.get("kind") in ("llama", "self"):
+        print(json.dumps({"impl": "eager", "unavailable": "oracle/_ref not built, no CUDA device, or a workload the reference's "
+                          "CrossAttentionModel cannot run"}), flush=True)
         return
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
@@ -299,6 +310,8 @@ def run_eager(a, w):
 
 def workload_name(a, w):
     peft = "lora (concat / self-attention path)" if w.get("kind") == "self" else "flamingo"
+    if w.get("kind") == "llama":
+        peft += " (extension: no reference Llama wrapper exists)"
     return (f"{a.workload}: {w['lm']} context=all neighbor_mode=embedding PEFT={peft} + {w['text']} + {w['visual']}, "
             f"seq {w['s_in']}+{w['s_out']}, {w['t']} text + {w['i']} image neighbors x 4 tokens, "
             f"position_type={w['position_type']}")
@@ -331,10 +344,14 @@ def run_ours(a, w):
     torch.manual_seed(1234)
     args = make_args(w)
     self_path = w.get("kind") == "self"
+    no_reference = self_path or w.get("kind") == "llama"     # workloads the reference's CrossAttentionModel cannot run
     with torch.device(dev):
         if self_path:
             from mmgl_b200.self_attention import SelfAttentionModel
             model = SelfAttentionModel(args, tokenizer=None)
+        elif w.get("kind") == "llama":
+            from mmgl_b200.llama import LlamaCrossAttentionModel
+            model = LlamaCrossAttentionModel(args, tokenizer=None)
         else:
             model = modules.CrossAttentionModel(args, tokenizer=None)
     with torch.no_grad():
@@ -533,12 +550,12 @@ def run_ours(a, w):
                             "memory after step i+1 is enqueued (K copies + K reads inside the timed region)"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
         "roofline": roofline, "roofline_attention": extra,
-        "roofline_block": None if self_path else block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev),
+        "roofline_block": None if no_reference else block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev),
         "clocks": clocks,
         "loss": [float(loss_res.detach()), float(loss_e2e)],
         "trainable_params": sum(p.numel() for p in params),
     }
-    if world == 1 and not a.no_cpu_baseline and not self_path:
+    if world == 1 and not a.no_cpu_baseline and not no_reference:
         del opt, net, resident
         model.to("cpu")
         torch.cuda.empty_cache()

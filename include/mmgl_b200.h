@@ -271,6 +271,26 @@ int mmgl_gcn_concat_fwd(const void* x, const float* adj, void* out, int64_t batc
 int mmgl_gcn_combine_bwd(const void* dc, const float* adj, const void* relu_mask, void* dx, int64_t batch,
                          int64_t nodes, int64_t dim, int32_t drop_root, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise pieces of frozen Llama decoder layers (BASELINE configs[4], SURVEY 8f row f4: Llama-2-7B with the gated
+ * cross-attention blocks interleaved; the reference has no Llama wrapper, so these restate HF transformers'
+ * models/llama/modeling_llama.py).
+ *
+ * mmgl_rope_inplace: rotary position embedding applied in place to the first `sections` (q, k) thirds of a fused
+ *   Q|K|V buffer x [rows, ld] bf16 (heads interleaved: column = section * heads * head_dim + head * head_dim + i):
+ *   (x[i], x[i + d/2]) -> (x[i] cos - x[i+d/2] sin, x[i+d/2] cos + x[i] sin), cos / sin = cos_sin[pos][i] (fp32 pairs,
+ *   [seq, head_dim / 2, 2]), pos = row % seq.  inverse != 0 applies the transposed rotation (the backward).
+ *   Replaces apply_rotary_pos_emb / rotate_half (HF modeling_llama.py:110-140).
+ * mmgl_swiglu_fwd / _bwd: h = silu(g) * u over gu = [g | u] ([M, 2F] bf16, one GEMM over the row-concatenated gate_proj |
+ *   up_proj weights); backward writes dgu = [dg | du].  Replaces LlamaMLP.forward's act_fn(gate_proj(x)) * up_proj(x)
+ *   (HF modeling_llama.py:155-165) and its autograd backward.
+ */
+int mmgl_rope_inplace(void* x, int64_t ld, int64_t rows, int64_t seq, int64_t heads, int64_t head_dim, int64_t sections,
+                      const float* cos_sin, int32_t inverse, void* stream);
+int mmgl_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int64_t m, int64_t f, void* stream);
+int mmgl_swiglu_bwd(const void* gu, int64_t ldgu, const void* dh, int64_t lddh, void* dgu, int64_t lddgu, int64_t m, int64_t f,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

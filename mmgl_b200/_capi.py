@@ -105,6 +105,9 @@ SIGNATURES = {
     "mmgl_bank_pack_bwd": (c_i32, [C.POINTER(BankBwdArgs), c_vp]),
     "mmgl_gcn_concat_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp]),
     "mmgl_gcn_combine_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp]),
+    "mmgl_rope_inplace": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i32, c_vp]),
+    "mmgl_swiglu_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "mmgl_swiglu_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
 }
 
 
@@ -467,3 +470,29 @@ def gcn_combine_bwd(dc, adj, relu_mask, dx, batch, nodes, dim, drop_root):
     _req_cuda(dc, adj, dx)
     _check(lib().mmgl_gcn_combine_bwd(_p(dc), _p(adj), _p(relu_mask), _p(dx), batch, nodes, dim, int(drop_root),
                                       _stream()), "mmgl_gcn_combine_bwd")
+
+
+# ------------------------------------------------------------------------------------------- llama pieces
+def rope_inplace(x, rows, seq, heads, head_dim, sections, cos_sin, inverse=False):
+    """x: [rows, >= sections*heads*head_dim] bf16 row-major view, rotated in place; cos_sin fp32 [seq, head_dim/2, 2]."""
+    _req_cuda(x, cos_sin)
+    assert x.dtype == torch.bfloat16 and cos_sin.dtype == torch.float32 and cos_sin.is_contiguous()
+    assert tuple(cos_sin.shape) == (seq, head_dim // 2, 2)
+    with _Timed("rope", float(rows * sections * heads * head_dim * 4)):
+        _check(lib().mmgl_rope_inplace(_p(x), _ld(x), rows, seq, heads, head_dim, sections, _p(cos_sin), int(inverse),
+                                       _stream()), "mmgl_rope_inplace")
+
+
+def swiglu_fwd(gu, h):
+    _req_cuda(gu, h)
+    m, f = h.shape
+    assert gu.shape[1] == 2 * f and gu.dtype == torch.bfloat16 and h.dtype == torch.bfloat16
+    with _Timed("swiglu_fwd", float(m * f * 6)):
+        _check(lib().mmgl_swiglu_fwd(_p(gu), _ld(gu), _p(h), _ld(h), m, f, _stream()), "mmgl_swiglu_fwd")
+
+
+def swiglu_bwd(gu, dh, dgu):
+    _req_cuda(gu, dh, dgu)
+    m, f = dh.shape
+    with _Timed("swiglu_bwd", float(m * f * 10)):
+        _check(lib().mmgl_swiglu_bwd(_p(gu), _ld(gu), _p(dh), _ld(dh), _p(dgu), _ld(dgu), m, f, _stream()), "mmgl_swiglu_bwd")

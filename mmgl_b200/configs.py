@@ -29,6 +29,12 @@ def lm_config(name: str):
     # opt-2.7b (head_dim 80) is not listed: the attention kernels cover head_dim 64 / 128 only
     if key == "opt-6.7b":
         return _opt(4096, 32, 32, 16384)
+    if key in ("llama-2-7b", "llama-2-7b-hf"):
+        from transformers import LlamaConfig
+        return LlamaConfig(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                           num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, rms_norm_eps=1e-5,
+                           rope_theta=10000.0, hidden_act="silu", tie_word_embeddings=False, pad_token_id=0, bos_token_id=1,
+                           eos_token_id=2)
     if key in ("t5-base", "t5-small", "t5-large"):
         from transformers import T5Config
         dims = {"t5-small": (512, 64, 2048, 6, 8), "t5-base": (768, 64, 3072, 12, 12), "t5-large": (1024, 64, 4096, 24, 16)}

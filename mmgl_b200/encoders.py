@@ -139,6 +139,19 @@ def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=None):
     return x
 
 
+_pad_cache = {}
+
+
+def _padded_weight(param, w2d, pad):
+    key = (id(param), param._version, pad)
+    t = _pad_cache.get(key)
+    if t is None:
+        t = torch.nn.functional.pad(w2d, (0, pad)).contiguous()
+        _pad_cache.clear()
+        _pad_cache[key] = t
+    return t
+
+
 @torch.no_grad()
 def clip_pooler_output(model, pixel_values):
     """``model(pixel_values).pooler_output`` of a HF CLIPVisionModel, [N, hidden] bf16.
@@ -147,17 +160,23 @@ def clip_pooler_output(model, pixel_values):
     vm = model.vision_model
     p = cfg.patch_size
     n, c, hh, ww = pixel_values.shape
-    if not _supported(cfg) or hh % p or ww % p or (c * p * p) % 8:
+    if not _supported(cfg) or hh % p or ww % p:
         raise NotImplementedError("mmgl_b200 runs the frozen vision tower on its own kernels: head_dim 64 / 128, image size a "
-                                  "multiple of the patch size, 3 * patch^2 a multiple of 8; there is no library fallback")
+                                  "multiple of the patch size; there is no library fallback")
     gh, gw = hh // p, ww // p
     s = gh * gw + 1
     h, heads = cfg.hidden_size, cfg.num_attention_heads
     d = h // heads
     emb = vm.embeddings
     # stride-p convolution == GEMM over unfolded patches ([c, kh, kw] order of the conv weight)
-    patches = pixel_values.reshape(n, c, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(n * gh * gw, c * p * p)
-    pe = _gemm(patches.to(BF16).contiguous(), w16(emb.patch_embedding.weight).reshape(h, c * p * p))
+    kdim = c * p * p
+    patches = pixel_values.reshape(n, c, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(n * gh * gw, kdim).to(BF16)
+    wpe = w16(emb.patch_embedding.weight).reshape(h, kdim)
+    if kdim % 8:   # ViT-L/14: 3 * 14 * 14 = 588; the GEMM's TMA rows need a 16-byte pitch -> zero-pad K (cached weight copy)
+        pad = 8 - kdim % 8
+        patches = torch.nn.functional.pad(patches, (0, pad))
+        wpe = _padded_weight(emb.patch_embedding.weight, wpe, pad)
+    pe = _gemm(patches.contiguous(), wpe)
     x = torch.empty((n, s, h), dtype=BF16, device=pe.device)
     x[:, 0] = emb.class_embedding.to(BF16)
     x[:, 1:] = pe.reshape(n, gh * gw, h)

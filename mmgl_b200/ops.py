@@ -994,3 +994,57 @@ class GCNFn(torch.autograd.Function):
 
 def gcn(x, adj, w1, w2):
     return GCNFn.apply(x, adj, w1, w2)
+
+
+# --------------------------------------------------------------------------------------------- Llama pieces
+class RoPEFn(torch.autograd.Function):
+    """Rotary position embedding on the q and k thirds of a fused Q|K|V projection [B,S,3H] (HF
+    models/llama/modeling_llama.py: apply_rotary_pos_emb / rotate_half).  ``cos_sin`` fp32 [S, head_dim/2, 2].  The rotation
+    is orthogonal, so the backward is the same kernel with the sign of sin flipped."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos_sin, heads):
+        b, s, h3 = qkv.shape
+        d = h3 // 3 // heads
+        out = _as2d(qkv).clone()
+        K.rope_inplace(out, b * s, s, heads, d, 2, cos_sin, inverse=False)
+        ctx.save_for_backward(cos_sin)
+        ctx.cfg = (b, s, heads, d)
+        return out.reshape(b, s, h3)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (cos_sin,) = ctx.saved_tensors
+        b, s, heads, d = ctx.cfg
+        g = _as2d(d_out).clone()
+        K.rope_inplace(g, b * s, s, heads, d, 2, cos_sin, inverse=True)
+        return g.reshape(d_out.shape), None, None
+
+
+def rope_qk(qkv, cos_sin, heads):
+    return RoPEFn.apply(qkv, cos_sin, heads)
+
+
+class SwiGLUFn(torch.autograd.Function):
+    """h = silu(g) * u over gu = [g | u] (HF LlamaMLP.forward, models/llama/modeling_llama.py:155-165)."""
+
+    @staticmethod
+    def forward(ctx, gu):
+        gu2 = _as2d(gu)
+        f = gu2.shape[1] // 2
+        h = _new(gu2.shape[0], f, gu2)
+        K.swiglu_fwd(gu2, h)
+        ctx.save_for_backward(gu2)
+        ctx.shape = gu.shape
+        return h.reshape(*gu.shape[:-1], f)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (gu2,) = ctx.saved_tensors
+        dgu = torch.empty_like(gu2)
+        K.swiglu_bwd(gu2, _as2d(dh), dgu)
+        return dgu.reshape(ctx.shape)
+
+
+def swiglu(gu):
+    return SwiGLUFn.apply(gu)
