@@ -98,7 +98,7 @@ def spec_for(w, batch):
     if w.get("kind") == "self" and "t5" in w["lm"]:
         extra = dict(vocab_size=32128, decoder_only=False, pad_token_id=0)
     if w.get("vocab"):
-        extra = dict(vocab_size=w["vocab"], pad_token_id=0)
+        extra = dict(vocab_size=w["vocab"], pad_token_id=0, neighbor_length=min(512, w["s_in"]))
     return synth.BatchSpec(batch=batch, max_input_length=w["s_in"], max_output_length=w["s_out"], text_neighbors=w["t"],
                            image_neighbors=w["i"], with_lpe=w["position_type"] == "laplacian",
                            with_graph=w["position_type"] == "gnn", **extra)

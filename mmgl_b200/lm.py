@@ -20,7 +20,8 @@ modules' own fp32 forward / backward on the same weights.
 
 ``supports(lm)`` says whether a model can run here; SelfAttentionModel raises when it cannot (head_dim not in {64, 128},
 gated-GELU T5 variants, LayerDrop): there is no HF / eager fallback.  Prefix tuning is implemented for OPT
-(``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions); T5 prefix tuning is not.
+(``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions) and for T5
+(``t5_forward(prefix_kv=...)``: the decoder's self- and cross-attention, as peft does for seq2seq models).
 """
 from __future__ import annotations
 
@@ -78,11 +79,13 @@ def _t5_bucket(rel, bidirectional, num_buckets, max_distance):
     return buckets + torch.where(is_small, rel, large)
 
 
-def t5_rel_bias(attn, sq, sk):
+def t5_rel_bias(attn, sq, sk, shift=0):
     """The position bias of T5Attention.compute_bias (:236-251) in the kernel's compact form: it depends on
-    key - query only, so [heads, sq + sk - 1] fp32 (entry d + sq - 1 = bias at distance d) replaces [1,nh,sq,sk]."""
+    key - query only, so [heads, sq + sk - 1] fp32 (entry d + sq - 1 = bias at distance d) replaces [1,nh,sq,sk].
+    ``shift``: the queries sit ``shift`` positions after key 0 (virtual-token K / V of prefix tuning in front of the
+    decoder's own keys: HF computes the bias for the full key length and keeps the last ``sq`` query rows)."""
     dev = attn.relative_attention_bias.weight.device
-    rel = torch.arange(-(sq - 1), sk, device=dev)
+    rel = torch.arange(-(sq - 1), sk, device=dev) - shift
     bucket = _t5_bucket(rel, not attn.is_decoder, attn.relative_attention_num_buckets, attn.relative_attention_max_distance)
     w = attn.relative_attention_bias.weight
     if not w.requires_grad:
@@ -90,32 +93,51 @@ def t5_rel_bias(attn, sq, sk):
     return w.float()[bucket].t().contiguous()     # differentiable when the table is trainable (peft "none")
 
 
-def _t5_attention(attn, x, kv, key_mask, rel_bias, causal, p_drop):
-    """T5Attention.forward (:253-345) for training (no cache): q / k / v without bias or scaling, o projection."""
+def _t5_attention(attn, x, kv, key_mask, rel_bias, causal, p_drop, prefix=None):
+    """T5Attention.forward (:253-345) for training: q / k / v without bias or scaling, o projection.  ``prefix`` = (k, v)
+    [n_virtual, inner_dim] of prefix tuning: the virtual tokens' keys / values go in front of the projected ones, exactly
+    what HF does with a pre-filled cache (``curr_past_key_values.update`` concatenates along the key axis)."""
     q = _proj(attn.q, x)
     k = _proj(attn.k, kv)
     v = _proj(attn.v, kv)
+    if prefix is not None:
+        b = k.shape[0]
+        k = torch.cat((prefix[0].to(BF16)[None].expand(b, -1, -1), k), dim=1)
+        v = torch.cat((prefix[1].to(BF16)[None].expand(b, -1, -1), v), dim=1)
     return ops.attention(q, k, v, key_mask=key_mask, rel_bias=rel_bias, heads=attn.n_heads, causal=causal, scale=1.0,
                          dropout_p=p_drop)
 
 
-def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0):
-    """T5Stack.forward (:637-790): dropout(embeds) -> blocks -> final RMSNorm -> dropout."""
+def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0, prefix_kv=None):
+    """T5Stack.forward (:637-790): dropout(embeds) -> blocks -> final RMSNorm -> dropout.  ``prefix_kv`` (decoder only)
+    [n_virtual, layers, 2, inner_dim]: peft prefix tuning for seq2seq models hands every decoder layer the SAME virtual
+    K / V for its self- and its cross-attention (peft get_prompt: ``torch.cat([past_key_values, past_key_values], dim=2)``)."""
     cfg = stack.config
     eps = cfg.layer_norm_epsilon
-    s = h.shape[1]
+    b, s = h.shape[:2]
     h = ops.dropout(h, p)
     self0 = stack.block[0].layer[0].SelfAttention
-    bias = t5_rel_bias(self0, s, s)                      # shared by every layer of the stack (:768-774)
-    for block in stack.block:
+    n_pre = 0 if prefix_kv is None else prefix_kv.shape[0]
+    bias = t5_rel_bias(self0, s, s + n_pre, shift=n_pre)     # shared by every layer of the stack (:768-774)
+    if n_pre:
+        ones = torch.ones((b, n_pre), dtype=torch.uint8, device=h.device)
+        self_mask = ones if key_mask is None else torch.cat((ones, key_mask), dim=1)
+        if key_mask is None:
+            self_mask = torch.cat((ones, torch.ones((b, s), dtype=torch.uint8, device=h.device)), dim=1)
+        cross_mask = torch.cat((ones, enc_mask if enc_mask is not None
+                                else torch.ones((b, enc.shape[1]), dtype=torch.uint8, device=h.device)), dim=1)
+    else:
+        self_mask, cross_mask = key_mask, enc_mask
+    for li, block in enumerate(stack.block):
+        pre = None if not n_pre else (prefix_kv[:, li, 0], prefix_kv[:, li, 1])
         sa = block.layer[0]
         xn, h = ops.rms_norm_fork(h, sa.layer_norm.weight, eps)     # (norm, residual): one backward kernel for both
-        a = _t5_attention(sa.SelfAttention, xn, xn, key_mask, bias, stack.is_decoder, p)
+        a = _t5_attention(sa.SelfAttention, xn, xn, self_mask, bias, stack.is_decoder, p, prefix=pre)
         h = ops.linear(a, _weight(sa.SelfAttention.o), None, residual=h, dropout_p=p)
         if stack.is_decoder:
             ca = block.layer[1]
             xn, h = ops.rms_norm_fork(h, ca.layer_norm.weight, eps)
-            a = _t5_attention(ca.EncDecAttention, xn, enc, enc_mask, None, False, p)
+            a = _t5_attention(ca.EncDecAttention, xn, enc, cross_mask, None, False, p, prefix=pre)
             h = ops.linear(a, _weight(ca.EncDecAttention.o), None, residual=h, dropout_p=p)
         ff = block.layer[-1]
         dense = ff.DenseReluDense
@@ -142,9 +164,12 @@ def _shift_right(lm, labels):
     return dec.masked_fill(dec == -100, cfg.pad_token_id)
 
 
-def t5_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None):
+def t5_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, prefix_kv=None):
     """T5ForConditionalGeneration.forward (:992-1130) for training: returns loss (mean CE, ignore_index -100) and
-    logits [B, S_dec, V]."""
+    logits [B, S_dec, V].  ``prefix_kv`` [n_virtual, decoder layers, 2, inner_dim]: prefix tuning
+    (model/modelling_self_attention.py:88-92; peft hands the virtual K / V to the DECODER as past_key_values -- its
+    self- and cross-attention -- and leaves the encoder alone; semantics restated, peft absent: parity unpinned against
+    peft itself, pinned against HF's own forward fed the same tensors as an EncoderDecoderCache)."""
     if labels is None:
         raise ValueError("t5_forward is the training forward: labels are required")
     p = lm.config.dropout_rate if lm.training else 0.0
@@ -156,7 +181,7 @@ def t5_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labe
     enc_mask = (attention_mask != 0).to(torch.uint8).contiguous()
     enc = _t5_stack(lm.encoder, inputs_embeds.to(BF16), enc_mask, p=p)
     dec_in = lm.shared(_shift_right(lm, labels)).to(BF16)
-    dec = _t5_stack(lm.decoder, dec_in, None, enc=enc, enc_mask=enc_mask, p=p)
+    dec = _t5_stack(lm.decoder, dec_in, None, enc=enc, enc_mask=enc_mask, p=p, prefix_kv=prefix_kv)
     scale = lm.model_dim ** -0.5 if getattr(lm.config, "scale_decoder_outputs", lm.config.tie_word_embeddings) else 1.0
     logits = ops.linear(dec, lm.lm_head.weight, None, alpha=scale)       # (x * s) W^T == s * (x W^T)
     loss = ops.cross_entropy(logits, labels.to(logits.device), ignore_index=-100)

@@ -79,10 +79,15 @@ class _PeftShim(nn.Module):
             # layer by layer, the key then the value of virtual token t (peft's view(.., layers * 2, heads, head_dim))
             cfg = model.config
             if cfg.is_encoder_decoder:
-                raise NotImplementedError("prefix tuning is implemented for decoder-only (OPT) language models")
-            self.prefix_layers, self.prefix_dim = cfg.num_hidden_layers, cfg.hidden_size
+                # seq2seq (T5): peft sizes the table for num_transformer_submodules = 2 (2 x 20 rows) but get_prompt only
+                # ever reads the first num_virtual_tokens rows and feeds them to the decoder's self- AND cross-attention
+                self.prefix_layers, self.prefix_dim = cfg.num_decoder_layers, cfg.num_heads * cfg.d_kv
+                rows = 2 * prefix_tokens
+            else:
+                self.prefix_layers, self.prefix_dim = cfg.num_hidden_layers, cfg.hidden_size
+                rows = prefix_tokens
             self.prompt_encoder = nn.ModuleDict({"default": nn.ModuleDict(
-                {"embedding": nn.Embedding(prefix_tokens, self.prefix_layers * 2 * self.prefix_dim)})})
+                {"embedding": nn.Embedding(rows, self.prefix_layers * 2 * self.prefix_dim)})})
 
     def get_input_embeddings(self):
         return self.base_model.model.get_input_embeddings()
@@ -92,10 +97,11 @@ class _PeftShim(nn.Module):
         if self.num_prefix_tokens:    # prefix tuning: per-layer K / V of the virtual tokens in front of every layer's keys
             if not lm_kernels.supports(lm):
                 raise NotImplementedError("prefix tuning needs a language model the package's kernels can run")
-            w = self.prompt_encoder["default"]["embedding"].weight
+            w = self.prompt_encoder["default"]["embedding"].weight[: self.num_prefix_tokens]
             prefix = w.view(self.num_prefix_tokens, self.prefix_layers, 2, self.prefix_dim)
-            return lm_kernels.opt_forward(lm, input_ids=input_ids, attention_mask=attention_mask,
-                                          inputs_embeds=inputs_embeds, labels=labels, prefix_kv=prefix)
+            fwd = lm_kernels.t5_forward if lm.config.is_encoder_decoder else lm_kernels.opt_forward
+            return fwd(lm, input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds, labels=labels,
+                       prefix_kv=prefix)
         if self.num_virtual_tokens:   # prompt tuning: learned embeddings prepended to the (encoder) input
             if inputs_embeds is None:
                 inputs_embeds = lm.get_input_embeddings()(input_ids)

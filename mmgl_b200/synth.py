@@ -34,6 +34,8 @@ class BatchSpec:
     with_lpe: bool = False
     with_graph: bool = False
     decoder_only: bool = True
+    neighbor_length: int = 0      # padded length of every text neighbor; 0 = max_input_length (data.py:457).  RoBERTa's 514
+                                  # learned positions cap it at 512 when the section itself is longer (cfg5: seq 1024)
 
 
 def make_batch(spec: BatchSpec, seed: int, pin: bool = False) -> dict:
@@ -65,10 +67,11 @@ def make_batch(spec: BatchSpec, seed: int, pin: bool = False) -> dict:
     n_img = rint(0, i + 1, (b,)) if i > 0 else torch.zeros(b, dtype=torch.long)
     tpos = torch.where(torch.arange(t)[None, :] < n_text[:, None], torch.arange(1, t + 1)[None, :], torch.tensor(0))
     ipos = torch.where(torch.arange(i)[None, :] < n_img[:, None], torch.arange(1, i + 1)[None, :], torch.tensor(0))
-    nlen = rint(min(16, s_in), s_in + 1, (b, t))
-    nmask = (torch.arange(s_in)[None, None, :] < nlen[:, :, None]) & (tpos > 0)[:, :, None]
+    s_nb = spec.neighbor_length or s_in
+    nlen = rint(min(16, s_nb), s_nb + 1, (b, t))
+    nmask = (torch.arange(s_nb)[None, None, :] < nlen[:, :, None]) & (tpos > 0)[:, :, None]
     nmask[:, :, 0] = True  # an empty-string neighbor still tokenises to <s> (data.py:444-457)
-    nids = torch.where(nmask, rint(4, spec.neighbor_vocab_size, (b, t, s_in)), torch.tensor(spec.pad_token_id))
+    nids = torch.where(nmask, rint(4, spec.neighbor_vocab_size, (b, t, s_nb)), torch.tensor(1))   # RoBERTa pad id
     images = torch.randn((b, i, 3, spec.image_size, spec.image_size), generator=g)
     images = images * (ipos > 0)[:, :, None, None, None]
 

@@ -325,3 +325,88 @@ def test_self_attention_model_prefix_tuning_trains():
     assert g is not None and float(g.abs().max()) > 0
     trainable = {n for n, p in model.named_parameters() if p.requires_grad}
     assert all(n.startswith(("lm.prompt_encoder", "text_", "visual_")) for n in trainable), trainable
+
+
+def test_t5_prefix_tuning_matches_hf_past_key_values():
+    """Prefix tuning on T5 (peft PrefixTuningConfig for SEQ_2_SEQ_LM, model/modelling_self_attention.py:88-92; peft absent
+    -> semantics restated from its get_prompt: every DECODER layer receives the same 20 virtual K / V for its self- and its
+    cross-attention, the encoder none).  Oracle: HF T5 fp32 handed the same tensors as a pre-filled EncoderDecoderCache --
+    loss, logits, d prefix, d encoder inputs.  (No encoder padding here: HF's cross-attention mask is built for the
+    encoder length only and cannot be combined with cached cross-attention keys.)"""
+    from transformers import DynamicCache, EncoderDecoderCache, T5Config, T5ForConditionalGeneration
+    from mmgl_b200 import lm as L
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(6)
+    cfg = T5Config(vocab_size=384, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_decoder_layers=3, num_heads=2,
+                   decoder_start_token_id=0, dropout_rate=0.0)
+    reference = T5ForConditionalGeneration(cfg)
+    product = T5ForConditionalGeneration(cfg)
+    product.load_state_dict(reference.state_dict())
+    for m in (product, reference):
+        for p in m.parameters():
+            p.data = p.data.to(BF16).float()
+            p.requires_grad = False
+    product.cuda().eval()
+    reference.cuda().eval()
+    n_pre, b, s, sd, heads, d = 20, 2, 150, 40, 2, 64
+    table = (torch.randn(n_pre, cfg.num_decoder_layers, 2, heads * d, generator=gen) * 0.5).to(BF16).float().cuda()
+    emb = (torch.randn(b, s, cfg.d_model, generator=gen) * 0.5).cuda()
+    labels = torch.randint(1, cfg.vocab_size, (b, sd), generator=gen)
+    labels[1, 30:] = -100
+    labels = labels.cuda()
+
+    w = table.clone().requires_grad_(True)
+    x = emb.to(BF16).requires_grad_(True)
+    out = L.t5_forward(product, inputs_embeds=x, attention_mask=None, labels=labels, prefix_kv=w)
+    out.loss.backward()
+
+    wr = table.clone().requires_grad_(True)
+    xr = emb.to(BF16).float().requires_grad_(True)
+    sc, cc = DynamicCache(config=cfg), DynamicCache(config=cfg)
+    for l in range(cfg.num_decoder_layers):
+        k = wr[:, l, 0].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
+        v = wr[:, l, 1].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
+        sc.update(k, v, l)
+        cc.update(k, v, l)
+    ref_out = reference(inputs_embeds=xr, labels=labels, past_key_values=EncoderDecoderCache(sc, cc),
+                        decoder_attention_mask=torch.ones(b, n_pre + sd, dtype=torch.long, device="cuda"))
+    ref_out.loss.backward()
+    plain = L.t5_forward(product, inputs_embeds=x.detach(), attention_mask=None, labels=labels)
+    assert abs(float(plain.loss) - float(out.loss)) > 1e-3, "the prefix must change the loss (path is live)"
+    rep = Report()
+    rep.scalar("loss", out.loss, ref_out.loss, 0.0, 2e-2)
+    rep.close("logits", out.logits, ref_out.logits, 2e-2)
+    rep.close("d prefix table", w.grad, wr.grad, 6e-2)
+    rep.close("d inputs_embeds", x.grad, xr.grad, 6e-2)
+    rep.finish()
+
+
+def test_self_attention_model_t5_prefix_tuning_trains():
+    """the wrapper with peft_type == 'prefix' on T5: peft's table shape (2 x 20 rows: num_transformer_submodules = 2, of
+    which get_prompt reads the first 20), only the table and the neighbor projections train"""
+    from transformers import CLIPVisionConfig, RobertaConfig, T5Config
+    from mmgl_b200 import synth
+    from mmgl_b200.self_attention import SelfAttentionModel
+    torch.manual_seed(0)
+    lm_cfg = T5Config(vocab_size=512, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_decoder_layers=2, num_heads=2,
+                      decoder_start_token_id=0, dropout_rate=0.1)
+    txt = RobertaConfig(vocab_size=512, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                        intermediate_size=256, max_position_embeddings=80, pad_token_id=1)
+    vis = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                           image_size=32, patch_size=16)
+    args = types.SimpleNamespace(context="all", decoder_only=False, neighbor_mode="embedding", position_type="none",
+                                 n_text_tokens=2, n_visual_tokens=2, model_name_or_path=lm_cfg, peft_type="prefix",
+                                 text_model=txt, visual_model=vis, max_output_length=16, freeze_lm=False,
+                                 max_text_neighbors=3, max_image_neighbors=2, lora_r=8, lora_alpha=1, lora_dropout=0.0)
+    model = SelfAttentionModel(args, tokenizer=None).cuda().train()
+    assert tuple(model.lm.prompt_encoder["default"]["embedding"].weight.shape) == (40, 2 * 2 * 128)
+    spec = synth.BatchSpec(batch=2, max_input_length=48, max_output_length=16, text_neighbors=3, image_neighbors=2,
+                           vocab_size=512, neighbor_vocab_size=512, image_size=32, decoder_only=False, pad_token_id=0)
+    batch = synth.to_device(synth.make_batch(spec, seed=3), torch.device("cuda"))
+    out = model(**batch)
+    out.loss.backward()
+    assert torch.isfinite(out.loss)
+    g = model.lm.prompt_encoder["default"]["embedding"].weight.grad
+    assert g is not None and float(g[:20].abs().max()) > 0 and float(g[20:].abs().max()) == 0.0
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert all(n.startswith(("lm.prompt_encoder", "text_", "visual_")) for n in trainable), trainable

@@ -104,8 +104,8 @@ def test_apply_lora_adapts_q_and_v_of_every_attention_and_keeps_peft_key_names()
 
 def test_peft_shim_prompt_and_prefix_tables_have_pefts_shapes():
     """Prompt tuning: Embedding(20, hidden); prefix tuning (OPT): Embedding(20, layers * 2 * hidden), both under
-    `prompt_encoder.default.embedding` (peft's PromptEmbedding / PrefixEncoder without projection); T5 prefix tuning is
-    declared unsupported instead of silently doing something else."""
+    `prompt_encoder.default.embedding` (peft's PromptEmbedding / PrefixEncoder without projection); T5 (seq2seq) prefix
+    tuning: Embedding(2 * 20, decoder layers * 2 * heads * d_kv) as peft sizes it for num_transformer_submodules = 2."""
     from transformers import OPTConfig, OPTForCausalLM, T5Config, T5ForConditionalGeneration
     from mmgl_b200.self_attention import _PeftShim
     opt = OPTForCausalLM(OPTConfig(vocab_size=64, hidden_size=32, ffn_dim=64, num_hidden_layers=3, num_attention_heads=4,
@@ -113,9 +113,8 @@ def test_peft_shim_prompt_and_prefix_tables_have_pefts_shapes():
     assert _PeftShim(opt, prompt_tokens=20).state_dict()["prompt_encoder.default.embedding.weight"].shape == (20, 32)
     assert _PeftShim(opt, prefix_tokens=20).state_dict()["prompt_encoder.default.embedding.weight"].shape == (20, 3 * 2 * 32)
     t5 = T5ForConditionalGeneration(T5Config(vocab_size=64, d_model=32, d_kv=8, d_ff=64, num_layers=1,
-                                             num_decoder_layers=1, num_heads=4, decoder_start_token_id=0))
-    with pytest.raises(NotImplementedError):
-        _PeftShim(t5, prefix_tokens=20)
+                                             num_decoder_layers=3, num_heads=4, decoder_start_token_id=0))
+    assert _PeftShim(t5, prefix_tokens=20).state_dict()["prompt_encoder.default.embedding.weight"].shape == (40, 3 * 2 * 32)
 
 
 def test_lm_support_matrix():
