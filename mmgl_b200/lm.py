@@ -21,7 +21,7 @@ modules' own fp32 forward / backward on the same weights.
 ``supports(lm)`` says whether a model can run here; SelfAttentionModel raises when it cannot (head_dim not in {64, 128},
 gated-GELU T5 variants, LayerDrop): there is no HF / eager fallback.  Prefix tuning is implemented for OPT
 (``opt_forward(prefix_kv=...)``: the causal kernel takes keys = virtual tokens + own positions) and for T5
-(``t5_forward(prefix_kv=...)``: the decoder's self- and cross-attention, as peft does for seq2seq models).
+(``t5_forward(prefix_kv=...)``: the decoder's self-attention, the effective behaviour of peft + the reference-era HF).
 """
 from __future__ import annotations
 
@@ -110,8 +110,12 @@ def _t5_attention(attn, x, kv, key_mask, rel_bias, causal, p_drop, prefix=None):
 
 def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0, prefix_kv=None):
     """T5Stack.forward (:637-790): dropout(embeds) -> blocks -> final RMSNorm -> dropout.  ``prefix_kv`` (decoder only)
-    [n_virtual, layers, 2, inner_dim]: peft prefix tuning for seq2seq models hands every decoder layer the SAME virtual
-    K / V for its self- and its cross-attention (peft get_prompt: ``torch.cat([past_key_values, past_key_values], dim=2)``)."""
+    [n_virtual, layers, 2, inner_dim]: the virtual K / V of prefix tuning go in front of every decoder layer's SELF-attention
+    keys.  peft's get_prompt also hands the same tensors over as cross-attention "past" K / V, but the transformers of the
+    reference's era (4.2x, T5Attention.project: "checking that the sequence_length of the past_key_value is the same as the
+    provided key_value_states to support prefix tuning") discards them there and projects the encoder output as usual --
+    while transformers 5.x would attend to the 20 virtual tokens INSTEAD of the encoder (a pre-filled cross-attention cache
+    counts as final).  The era's behaviour is the one restated: cross-attention is untouched."""
     cfg = stack.config
     eps = cfg.layer_norm_epsilon
     b, s = h.shape[:2]
@@ -124,10 +128,8 @@ def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0, prefix_kv=None
         self_mask = ones if key_mask is None else torch.cat((ones, key_mask), dim=1)
         if key_mask is None:
             self_mask = torch.cat((ones, torch.ones((b, s), dtype=torch.uint8, device=h.device)), dim=1)
-        cross_mask = torch.cat((ones, enc_mask if enc_mask is not None
-                                else torch.ones((b, enc.shape[1]), dtype=torch.uint8, device=h.device)), dim=1)
     else:
-        self_mask, cross_mask = key_mask, enc_mask
+        self_mask = key_mask
     for li, block in enumerate(stack.block):
         pre = None if not n_pre else (prefix_kv[:, li, 0], prefix_kv[:, li, 1])
         sa = block.layer[0]
@@ -137,7 +139,7 @@ def _t5_stack(stack, h, key_mask, enc=None, enc_mask=None, p=0.0, prefix_kv=None
         if stack.is_decoder:
             ca = block.layer[1]
             xn, h = ops.rms_norm_fork(h, ca.layer_norm.weight, eps)
-            a = _t5_attention(ca.EncDecAttention, xn, enc, cross_mask, None, False, p, prefix=pre)
+            a = _t5_attention(ca.EncDecAttention, xn, enc, enc_mask, None, False, p)
             h = ops.linear(a, _weight(ca.EncDecAttention.o), None, residual=h, dropout_p=p)
         ff = block.layer[-1]
         dense = ff.DenseReluDense
@@ -167,9 +169,10 @@ def _shift_right(lm, labels):
 def t5_forward(lm, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, prefix_kv=None):
     """T5ForConditionalGeneration.forward (:992-1130) for training: returns loss (mean CE, ignore_index -100) and
     logits [B, S_dec, V].  ``prefix_kv`` [n_virtual, decoder layers, 2, inner_dim]: prefix tuning
-    (model/modelling_self_attention.py:88-92; peft hands the virtual K / V to the DECODER as past_key_values -- its
-    self- and cross-attention -- and leaves the encoder alone; semantics restated, peft absent: parity unpinned against
-    peft itself, pinned against HF's own forward fed the same tensors as an EncoderDecoderCache)."""
+    (model/modelling_self_attention.py:88-92; peft hands the virtual K / V to the DECODER as past_key_values and leaves the
+    encoder alone; they act on the decoder's self-attention, see _t5_stack; semantics restated, peft absent: parity unpinned
+    against peft itself, pinned against HF's own forward fed the same tensors as the self-attention half of an
+    EncoderDecoderCache)."""
     if labels is None:
         raise ValueError("t5_forward is the training forward: labels are required")
     p = lm.config.dropout_rate if lm.training else 0.0

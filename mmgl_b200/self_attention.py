@@ -80,7 +80,7 @@ class _PeftShim(nn.Module):
             cfg = model.config
             if cfg.is_encoder_decoder:
                 # seq2seq (T5): peft sizes the table for num_transformer_submodules = 2 (2 x 20 rows) but get_prompt only
-                # ever reads the first num_virtual_tokens rows and feeds them to the decoder's self- AND cross-attention
+                # ever reads the first num_virtual_tokens rows (decoder self-attention prefix, see lm._t5_stack)
                 self.prefix_layers, self.prefix_dim = cfg.num_decoder_layers, cfg.num_heads * cfg.d_kv
                 rows = 2 * prefix_tokens
             else:

@@ -329,10 +329,10 @@ def test_self_attention_model_prefix_tuning_trains():
 
 def test_t5_prefix_tuning_matches_hf_past_key_values():
     """Prefix tuning on T5 (peft PrefixTuningConfig for SEQ_2_SEQ_LM, model/modelling_self_attention.py:88-92; peft absent
-    -> semantics restated from its get_prompt: every DECODER layer receives the same 20 virtual K / V for its self- and its
-    cross-attention, the encoder none).  Oracle: HF T5 fp32 handed the same tensors as a pre-filled EncoderDecoderCache --
-    loss, logits, d prefix, d encoder inputs.  (No encoder padding here: HF's cross-attention mask is built for the
-    encoder length only and cannot be combined with cached cross-attention keys.)"""
+    -> semantics restated: every DECODER layer's self-attention sees 20 virtual K / V in front of its own keys; the
+    cross-attention and the encoder are untouched -- the effective behaviour of peft with the reference-era transformers,
+    see lm._t5_stack).  Oracle: HF T5 fp32 handed the same tensors as the self-attention half of an EncoderDecoderCache
+    (empty cross-attention half) -- loss, logits, d prefix, d encoder inputs, with encoder padding."""
     from transformers import DynamicCache, EncoderDecoderCache, T5Config, T5ForConditionalGeneration
     from mmgl_b200 import lm as L
     torch.manual_seed(0)
@@ -354,24 +354,26 @@ def test_t5_prefix_tuning_matches_hf_past_key_values():
     labels = torch.randint(1, cfg.vocab_size, (b, sd), generator=gen)
     labels[1, 30:] = -100
     labels = labels.cuda()
+    am = torch.ones(b, s, dtype=torch.long)
+    am[1, 120:] = 0
+    am = am.cuda()
 
     w = table.clone().requires_grad_(True)
     x = emb.to(BF16).requires_grad_(True)
-    out = L.t5_forward(product, inputs_embeds=x, attention_mask=None, labels=labels, prefix_kv=w)
+    out = L.t5_forward(product, inputs_embeds=x, attention_mask=am, labels=labels, prefix_kv=w)
     out.loss.backward()
 
     wr = table.clone().requires_grad_(True)
     xr = emb.to(BF16).float().requires_grad_(True)
-    sc, cc = DynamicCache(config=cfg), DynamicCache(config=cfg)
+    sc, cc = DynamicCache(), DynamicCache()   # (config=cfg would size both for num_layers, not num_decoder_layers)
     for l in range(cfg.num_decoder_layers):
         k = wr[:, l, 0].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
         v = wr[:, l, 1].view(n_pre, heads, d).permute(1, 0, 2)[None].expand(b, -1, -1, -1)
         sc.update(k, v, l)
-        cc.update(k, v, l)
-    ref_out = reference(inputs_embeds=xr, labels=labels, past_key_values=EncoderDecoderCache(sc, cc),
+    ref_out = reference(inputs_embeds=xr, attention_mask=am, labels=labels, past_key_values=EncoderDecoderCache(sc, cc),
                         decoder_attention_mask=torch.ones(b, n_pre + sd, dtype=torch.long, device="cuda"))
     ref_out.loss.backward()
-    plain = L.t5_forward(product, inputs_embeds=x.detach(), attention_mask=None, labels=labels)
+    plain = L.t5_forward(product, inputs_embeds=x.detach(), attention_mask=am, labels=labels)
     assert abs(float(plain.loss) - float(out.loss)) > 1e-3, "the prefix must change the loss (path is live)"
     rep = Report()
     rep.scalar("loss", out.loss, ref_out.loss, 0.0, 2e-2)
