@@ -2,7 +2,7 @@
 //
 //   O = softmax(max(Q K^T + mask, -FLT_MAX)) V          per (sample, head); Q pre-scaled by d^-1/2
 //
-// One CTA = one 128-query tile of one (sample, head):
+// One 128-query tile of one (sample, head) at a time (persistent CTAs walk runs of tiles, see the kernel):
 //   * thread 0 TMA-loads the Q tile and the head's whole K / V neighbor bank (Nk <= 256 rows, zero-filled tails)
 //     into 128B-swizzled shared memory (cp.async.bulk.tensor, one mbarrier),
 //   * thread 0 issues tcgen05.mma  S[128 x Nk] = Q K^T  into TMEM (fp32),
@@ -26,6 +26,20 @@
 
 namespace mmgl {
 
+#ifdef MMGL_TRACE
+__device__ unsigned long long g_xtrace[1024];
+#define XTR(idx_var, tag)                                                         \
+  do {                                                                            \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (idx_var) < 511) {                 \
+      g_xtrace[2 * (idx_var)] = (unsigned long long)(tag);                        \
+      g_xtrace[2 * (idx_var) + 1] = clock64();                                    \
+      ++(idx_var);                                                                \
+    }                                                                             \
+  } while (0)
+#else
+#define XTR(idx_var, tag) do { } while (0)
+#endif
+
 constexpr float kLog2eF = 1.4426950408889634f;
 
 // 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled [rows][64 bf16] slab
@@ -36,147 +50,248 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Persistent form (round 2): the grid is a few CTAs per SM and every CTA walks a CONTIGUOUS run of (sample, head, query tile)
+// items, so the tensor-map fetch, barrier set-up, TMEM allocation and the mask row are paid once per CTA instead of once per
+// tile, the head's K / V tiles stay in shared memory across its query tiles, the NEXT tile's Q is requested as soon as the
+// S = Q K^T MMA has consumed the current one, and S of the next tile is issued right behind P V of this one (separate TMEM
+// columns) so it completes while this tile's output is being written.
+// Attend bits of sample b's bank row, one 32-key word per chunk: the byte mask is read once per (CTA, sample) with one
+// coalesced load per chunk and a ballot.  (Round 1 kept a float mask row in
+// shared memory behind a pointer whose address space the compiler could not see: 2 x Nk generic LD per thread and tile.)
+// (kept in shared memory as nchunks words: one broadcast LDS per 32 keys)
+__device__ __forceinline__ void load_mask_words(const uint8_t* __restrict__ mask, int b, int nk, int nchunks, uint32_t* saw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < nchunks; c += (blockDim.x >> 5)) {
+    const int key = c * 32 + lane;
+    const uint32_t w = __ballot_sync(0xffffffffu, key < nk && mask[(int64_t)b * nk + key] != 0);
+    if (lane == 0) saw[c] = w;
+  }
+}
+__device__ __forceinline__ uint32_t low_bits32(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
+
 template <int D>
 __global__ void __launch_bounds__(128)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const uint8_t* __restrict__ mask,
                     __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats, int seq, int nk, int nkp,
-                    int heads, uint32_t tmem_cols) {
+                    int heads, int batch, int items_per_cta, uint32_t tmem_cols) {
   constexpr int DS = D / 64;  // 64-wide (128-byte) slabs along the head dim
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int ps = (nkp + 63) / 64;                       // slabs of P along the key dim
-  uint8_t* sQ = smem;                                   // DS x [128][64]
-  uint8_t* sK = sQ + DS * 16384;                        // DS x [nkp][64]   (K-major B operand of S = Q K^T)
+  constexpr int NQ = 2;                                 // Q tiles in flight: the kernel is bound by HBM latency x bytes in flight
+  uint8_t* sQ = smem;                                   // NQ x DS x [128][64]
+  uint8_t* sK = sQ + NQ * DS * 16384;                   // DS x [nkp][64]   (K-major B operand of S = Q K^T)
   uint8_t* sV = sK + DS * nkp * 128;                    // DS x [nkp][64]   (MN-major B operand of O = P V)
   uint8_t* sP = sV + DS * nkp * 128;                    // ps x [128][64]
-  float* sMask = reinterpret_cast<float*>(sP + ps * 16384);          // [ps * 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + ps * 64);     // load, mma1, mma2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ps * 16384);     // mma1, mma2, kv, q[NQ]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 + NQ);
+  uint32_t* saw = tmem_ptr + 2;                                      // [8] attend words of the current sample
+  // barrier roles: bars[1] S done, bars[2] P V done, bars[0] K / V landed, bars[3 + slot] Q tile of that ring slot landed
 
-  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 128;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const int ntiles = (seq + 127) / 128;
+  const int n_items = batch * heads * ntiles;
+  const int item0 = blockIdx.x * items_per_cta;
+  const int item_end = min(n_items, item0 + items_per_cta);
+  if (item0 >= item_end) return;                        // (whole CTA, before any barrier)
+  // item -> (sample, head, tile): tiles of one (sample, head) are consecutive
+  auto bh_of = [&](int item) { return item / ntiles; };
 
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    for (int i = 0; i < 3 + NQ; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
-  for (int j = tid; j < ps * 64; j += 128)
-    sMask[j] = (j < nk) ? (mask[(int64_t)b * nk + j] ? 0.f : -FLT_MAX) : -INFINITY;
+  const int nchunks = (nkp + 31) / 32;
+  load_mask_words(mask, bh_of(item0) / heads, nk, nchunks, saw);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t p_base = smem_u32(sP);
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], DS * (16384 + 2 * nkp * 128));
+  // thread 0 helpers.  Tile `it` (local index) lives in Q ring slot it % NQ; its barrier completes once per use of the slot.
+  auto load_q = [&](int item, int it) {
+    const int bh = bh_of(item), t = item % ntiles, slot = it % NQ;
+    mbar_arrive_expect_tx(&bars[3 + slot], DS * 16384);
+#pragma unroll
+    for (int j = 0; j < DS; ++j)
+      tma_load_2d(sQ + (slot * DS + j) * 16384, &map_q, &bars[3 + slot], (bh % heads) * D + 64 * j, (bh / heads) * seq + t * 128);
+  };
+  auto load_kv = [&](int item) {
+    const int bh = bh_of(item);
+    mbar_arrive_expect_tx(&bars[0], 2 * DS * nkp * 128);
 #pragma unroll
     for (int j = 0; j < DS; ++j) {
-      tma_load_2d(sQ + j * 16384, &map_q, &bars[0], h * D + 64 * j, b * seq + r0);
-      tma_load_2d(sK + j * nkp * 128, &map_k, &bars[0], h * D + 64 * j, b * nk);
-      tma_load_2d(sV + j * nkp * 128, &map_v, &bars[0], h * D + 64 * j, b * nk);
+      tma_load_2d(sK + j * nkp * 128, &map_k, &bars[0], (bh % heads) * D + 64 * j, (bh / heads) * nk);
+      tma_load_2d(sV + j * nkp * 128, &map_v, &bars[0], (bh % heads) * D + 64 * j, (bh / heads) * nk);
     }
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    // S[128 x nkp] = Q K^T : A, B both K-major
-    const uint32_t idesc = make_idesc_bf16(128, nkp, 0, 0);
-    const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK);
+  };
+  // descriptor bases are built once; the issuing thread only adds (byte offset >> 4) per instruction
+  const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_k = make_smem_desc(smem_u32(sK), 16, 1024);
+  const uint64_t desc_p = make_smem_desc(p_base, 16, 1024), desc_v = make_smem_desc(smem_u32(sV), nkp * 128, 1024);
+  const uint32_t idesc_s = make_idesc_bf16(128, nkp, 0, 0);
+  const uint64_t kslab = (uint64_t)((nkp * 128) >> 4);       // next 64-column slab of the K tile
+  auto issue_s = [&](int it) {   // S[128 x nkp] = Q K^T : A, B both K-major
+    const uint64_t dq = desc_q + (uint64_t)(((it % NQ) * DS * 16384) >> 4);
 #pragma unroll
-    for (int k = 0; k < D / 16; ++k) {
-      const uint64_t da = make_smem_desc(aq + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-      const uint64_t db = make_smem_desc(bk + (k >> 2) * nkp * 128 + (k & 3) * 32, 16, 1024);
-      umma_f16_ss(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
-    }
+    for (int k = 0; k < D / 16; ++k)
+      umma_f16_ss(tmem_base, dq + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                  desc_k + (uint64_t)(k >> 2) * kslab + (uint64_t)(((k & 3) * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
     umma_commit(&bars[1]);
-  }
-  __syncwarp();
+  };
 
-  // ---- softmax: this thread owns query row `tid` (TMEM lane tid)
-  mbar_wait(&bars[1], 0);
-  tc_fence_after();
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  const int nchunks = (nkp + 31) / 32;
-  float mx = -FLT_MAX;
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float mk = sMask[c * 32 + j];
-      const float x = (mk == 0.f) ? fmaxf(__uint_as_float(r[j]), -FLT_MAX) : mk;   // max(s + mask, finfo.min)
-      mx = fmaxf(mx, x);
-    }
-  }
-  float sum = 0.f;
-  const uint32_t p_base = smem_u32(sP);
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(lane_addr + c * 32, r);
-    tmem_ld_wait();
-    float p[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float mk = sMask[c * 32 + j];
-      const float x = (mk == 0.f) ? fmaxf(__uint_as_float(r[j]), -FLT_MAX) : mk;
-      p[j] = exp2f((x - mx) * kLog2eF);
-      sum += p[j];
-    }
-    const uint32_t slab = p_base + (c >> 1) * 16384;
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      st_shared_v4(swz128(slab, tid, (c & 1) * 4 + g), pack_bf16(p[8 * g], p[8 * g + 1]),
-                   pack_bf16(p[8 * g + 2], p[8 * g + 3]), pack_bf16(p[8 * g + 4], p[8 * g + 5]),
-                   pack_bf16(p[8 * g + 6], p[8 * g + 7]));
-  }
-  const float inv = 1.f / sum;
-  fence_proxy_async();   // generic-proxy smem writes (P) -> visible to the tensor core's async proxy
-  tc_fence_before();
-  __syncthreads();
-
+  int xi = 0; (void)xi;
+  XTR(xi, 1);
+  uint32_t kv_uses = 0;       // thread 0: completed K / V loads (phase of bars[0])
   if (tid == 0) {
+    load_kv(item0);
+    for (int a = 0; a < NQ && item0 + a < item_end; ++a) load_q(item0 + a, a);
+    mbar_wait(&bars[0], kv_uses & 1); ++kv_uses;
+    mbar_wait(&bars[3], 0);
+    XTR(xi, 2);
     tc_fence_after();
-    // O[128 x D] = P V : A = P K-major (K = keys), B = V MN-major ([key rows][d cols] as loaded)
-    const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-    const uint32_t bv = smem_u32(sV);
-    for (int k = 0; k < nkp / 16; ++k) {
-      const uint64_t da = make_smem_desc(p_base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-      const uint64_t db = make_smem_desc(bv + k * 2048, nkp * 128, 1024);
-      umma_f16_ss(tmem_base + ps * 64, da, db, idesc, k != 0 ? 1u : 0u);
-    }
-    umma_commit(&bars[2]);
+    issue_s(0);
   }
   __syncwarp();
-  mbar_wait(&bars[2], 0);
-  tc_fence_after();
 
-  const int row = r0 + tid;
-  const uint32_t o_addr = lane_addr + ps * 64;
+  for (int item = item0, it = 0; item < item_end; ++item, ++it) {
+    const uint32_t par = it & 1;
+    const int bh = bh_of(item), b = bh / heads, h = bh % heads, r0 = (item % ntiles) * 128;
+    const bool has_next = item + 1 < item_end;
+    const bool next_same_bh = has_next && bh_of(item + 1) == bh;
+
+    // ---- softmax: this thread owns query row `tid` (TMEM lane tid)
+    mbar_wait(&bars[1], par);
+    XTR(xi, 100 + it * 10);
+    tc_fence_after();
+    if (tid == 0 && item + NQ < item_end) load_q(item + NQ, it + NQ);   // S has consumed this slot: refill it NQ tiles ahead
+    // pass 1: row maximum over the attended keys (-FLT_MAX when the row attends nothing: the clamp of the reference then
+    // makes every existing key's score finfo.min, i.e. uniform attention over the bank)
+    float mx = -FLT_MAX;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(lane_addr + c * 32, r);
+      const uint32_t w = saw[c];
+      tmem_ld_wait();
+      float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+      if (w == 0xffffffffu) {      // warp-uniform: all 32 keys attended
 #pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(o_addr + c * 32, r);
-    tmem_ld_wait();
-    if (row < seq) {
-      __nv_bfloat16* op = o + ((int64_t)b * seq + row) * ldo + h * D + c * 32;
+        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
+      } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
-        v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
-        v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
-        v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
-        *reinterpret_cast<uint4*>(op + 8 * g) = v;
+        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], ((w >> j) & 1u) ? __uint_as_float(r[j]) : -FLT_MAX);
+      }
+      mx = fmaxf(fmaxf(mx, fmaxf(m4[0], m4[1])), fmaxf(m4[2], m4[3]));
+    }
+    // pass 2: p = 2^((max(s, finfo.min) - mx) log2 e) on attended keys; masked existing keys: 1 when the row attends nothing,
+    // else exactly 0 (exp of -3.4e38 - mx); zero-filled tail keys: 0
+    const bool none = !(mx > -FLT_MAX);
+    const float c1 = none ? 0.f : kLog2eF, off = none ? 0.f : mx * kLog2eF, pmask = none ? 1.f : 0.f;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(lane_addr + c * 32, r);
+      const uint32_t w = saw[c];
+      const uint32_t ex = low_bits32(nk - c * 32);      // keys of the chunk that exist
+      tmem_ld_wait();
+      float p[32];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (w == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          p[j] = exp2f(fmaf(fmaxf(__uint_as_float(r[j]), -FLT_MAX), c1, -off));
+          s4[j & 3] += p[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = exp2f(fmaf(fmaxf(__uint_as_float(r[j]), -FLT_MAX), c1, -off));
+          p[j] = ((w >> j) & 1u) ? e : (((ex >> j) & 1u) ? pmask : 0.f);
+          s4[j & 3] += p[j];
+        }
+      }
+      sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const uint32_t slab = p_base + (c >> 1) * 16384;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(swz128(slab, tid, (c & 1) * 4 + g), pack_bf16(p[8 * g], p[8 * g + 1]),
+                     pack_bf16(p[8 * g + 2], p[8 * g + 3]), pack_bf16(p[8 * g + 4], p[8 * g + 5]),
+                     pack_bf16(p[8 * g + 6], p[8 * g + 7]));
+    }
+    const float inv = 1.f / sum;
+    fence_proxy_async();   // generic-proxy smem writes (P) -> visible to the tensor core's async proxy
+    tc_fence_before();
+    XTR(xi, 101 + it * 10);
+    __syncthreads();       // P complete; every thread has finished reading S (and, from the previous tile, O)
+    XTR(xi, 102 + it * 10);
+
+    if (tid == 0) {
+      tc_fence_after();
+      // O[128 x D] = P V : A = P K-major (K = keys), B = V MN-major ([key rows][d cols] as loaded)
+      constexpr uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+      for (int k4 = 0; k4 < nkp / 16; k4 += 4) {        // one 64-key slab of P per outer step
+        const uint64_t da = desc_p + (uint64_t)(((k4 >> 2) * 16384) >> 4), db = desc_v + (uint64_t)((k4 * 2048) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (k4 + kk < nkp / 16)
+            umma_f16_ss(tmem_base + ps * 64, da + (uint64_t)((kk * 32) >> 4), db + (uint64_t)((kk * 2048) >> 4), idesc,
+                        (k4 + kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(&bars[2]);
+      if (has_next) {
+        if (!next_same_bh) {                   // new head: its K / V replace this one's once P V has read them
+          mbar_wait(&bars[2], par);
+          load_kv(item + 1);
+          mbar_wait(&bars[0], kv_uses & 1); ++kv_uses;
+        }
+        XTR(xi, 103 + it * 10);
+        mbar_wait(&bars[3 + (it + 1) % NQ], ((it + 1) / NQ) & 1);
+        XTR(xi, 104 + it * 10);
+        tc_fence_after();
+        issue_s(it + 1);                       // runs behind P V on the tensor pipe, ready when the epilogue below is done
       }
     }
+    __syncwarp();
+    if (has_next && bh_of(item + 1) / heads != b) {    // next item belongs to another sample: its mask row
+      load_mask_words(mask, bh_of(item + 1) / heads, nk, nchunks, saw);
+      __syncthreads();
+    }
+    mbar_wait(&bars[2], par);
+    XTR(xi, 105 + it * 10);
+    tc_fence_after();
+
+    const int row = r0 + tid;
+    const uint32_t o_addr = lane_addr + ps * 64;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(o_addr + c * 32, r);
+      tmem_ld_wait();
+      if (row < seq) {
+        __nv_bfloat16* op = o + ((int64_t)b * seq + row) * ldo + h * D + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + 8 * g) = v;
+        }
+      }
+    }
+    if (row < seq) {
+      float* st = stats + (((int64_t)b * heads + h) * seq + row) * 2;
+      *reinterpret_cast<float2*>(st) = make_float2(mx, inv);
+    }
+    XTR(xi, 106 + it * 10);
+    tc_fence_before();       // the next tile's P V overwrites the O columns after the next block barrier
   }
-  if (row < seq) {
-    float* st = stats + (((int64_t)b * heads + h) * seq + row) * 2;
-    *reinterpret_cast<float2*>(st) = make_float2(mx, inv);
-  }
-  tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc_dyn(tmem_base, tmem_cols);
 }
@@ -193,7 +308,7 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   const uint32_t need_cols = (uint32_t)(ps * 64 + D);
   uint32_t tmem_cols = 32;
   while (tmem_cols < need_cols) tmem_cols <<= 1;
-  const size_t smem = 1024 + (size_t)DS * 16384 + 2 * (size_t)DS * nkp * 128 + (size_t)ps * 16384 + ps * 64 * 4 + 64;
+  const size_t smem = 2 * (size_t)DS * 16384 + 2 * (size_t)DS * nkp * 128 + (size_t)ps * 16384 + 128;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_tensor_map_2d(&mq, q, (uint64_t)(heads * D), (uint64_t)(batch * seq), (uint64_t)ldq, 64, 128))) return rc;
@@ -201,11 +316,30 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   if ((rc = make_tensor_map_2d(&mv, v, (uint64_t)(heads * D), (uint64_t)(batch * nk), (uint64_t)ldv, 64, (uint32_t)nkp))) return rc;
   auto kern = xattn_fwd_tc_kernel<D>;
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((seq + 127) / 128), (unsigned)heads, (unsigned)batch);
-  kern<<<grid, 128, smem, stream>>>(mq, mk, mv, mask, (__nv_bfloat16*)o, ldo, stats, (int)seq, (int)nk, nkp, (int)heads,
-                                    tmem_cols);
+  // persistent: as many CTAs as fit per SM (shared memory / TMEM columns), each walking a contiguous run of items; runs are
+  // whole (sample, head)s when that costs at most one extra wave, so K / V are loaded once per head
+  const int ntiles = (int)((seq + 127) / 128);
+  const int64_t n_items = batch * heads * ntiles;
+  int per_sm = (int)(512 / tmem_cols);
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  if (by_smem < per_sm) per_sm = by_smem;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t slots = (int64_t)sm_count() * per_sm;
+  int64_t per_cta = (n_items + slots - 1) / slots;
+  if (per_cta < 1) per_cta = 1;
+  if (per_cta < ntiles && ntiles <= 2 * per_cta) per_cta = ntiles;   // (longer runs simply straddle heads: K / V reload at the seam)
+  const int64_t grid = (n_items + per_cta - 1) / per_cta;
+  kern<<<dim3((unsigned)grid), 128, smem, stream>>>(mq, mk, mv, mask, (__nv_bfloat16*)o, ldo, stats, (int)seq, (int)nk, nkp,
+                                                    (int)heads, (int)batch, (int)per_cta, tmem_cols);
   return check_launch("mmgl_xattn_fwd");
 }
+
+#ifdef MMGL_TRACE
+extern "C" int mmgl_debug_trace_xattn(unsigned long long* host_dst) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_dst, g_xtrace, sizeof(g_xtrace));
+}
+#endif
 
 int xattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* mask,
                  void* o, int64_t ldo, float* stats, int64_t batch, int64_t seq, int64_t nk, int64_t heads, int64_t d,
@@ -234,8 +368,7 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     __nv_bfloat16* __restrict__ dv, int64_t lddv, int seq, int nk, int nkp, int heads,
                     uint32_t tmem_cols, int alias_dq) {
   constexpr int DS = D / 64;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int ps = (nkp + 63) / 64;
   uint8_t* sK = smem;                         // DS x [nkp][64]
   uint8_t* sV = sK + DS * nkp * 128;          // DS x [nkp][64]
@@ -243,9 +376,9 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* sdO = sQ + DS * 16384;             // DS x [128][64]
   uint8_t* sP = sdO + DS * 16384;             // ps x [128][64]
   uint8_t* sdS = sP + ps * 16384;             // ps x [128][64]  (+ one slab of slack: M = 128 reads a 2nd key atom)
-  float* sMask = reinterpret_cast<float*>(sdS + (ps + 1) * 16384);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + ps * 64);   // kv, q, a, b
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + (ps + 1) * 16384);   // kv, q, a, b
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* saw = tmem_ptr + 2;                                           // [8] attend words of this sample
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -258,8 +391,7 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
-  for (int j = tid; j < ps * 64; j += 128)
-    sMask[j] = (j < nk) ? (mask[(int64_t)b * nk + j] ? 0.f : -FLT_MAX) : -INFINITY;
+  load_mask_words(mask, b, nk, nchunks, saw);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -329,24 +461,36 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncwarp();
     mbar_wait(&bars[2], par);
     tc_fence_after();
+    // P = 2^((max(s, finfo.min) - m) log2 e) / l on attended keys; masked existing keys: 1 / l when the row attends nothing,
+    // else exactly 0; tail keys 0.  Masked entries tie in the reference's clamp max(S + mask, finfo.min): torch halves a
+    // tie's gradient, hence the 1/2 on their dS.
+    const bool none = !(m > -FLT_MAX);
+    const float c1 = none ? 0.f : kLog2eF, off = none ? 0.f : m * kLog2eF, inv_ok = row_ok ? inv : 0.f;
+    const float pmask = none ? inv_ok : 0.f;
+#pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       uint32_t rs[32], rp[32];
       tmem_ld_32x32(lane_addr + cS + c * 32, rs);
       tmem_ld_32x32(lane_addr + cdP + c * 32, rp);
+      const uint32_t w = saw[c];
+      const uint32_t ex = low_bits32(nk - c * 32);
       tmem_ld_wait();
       uint32_t pk[16], dk16[16];
+      const bool full = w == 0xffffffffu;      // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         float pv[2], dsv[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float mk = sMask[c * 32 + j + e];
-          const float x = (mk == 0.f) ? fmaxf(__uint_as_float(rs[j + e]), -FLT_MAX) : mk;
-          const float p = row_ok ? exp2f((x - m) * kLog2eF) * inv : 0.f;
-          // masked entries tie in the reference's clamp max(S + mask, finfo.min): torch halves a tie's gradient
-          const float half = (mk == 0.f) ? 1.f : 0.5f;
+          float p = exp2f(fmaf(fmaxf(__uint_as_float(rs[j + e]), -FLT_MAX), c1, -off)) * inv_ok;
+          float half = 1.f;
+          if (!full) {
+            const bool att = (w >> (j + e)) & 1u;
+            p = att ? p : (((ex >> (j + e)) & 1u) ? pmask : 0.f);
+            half = att ? 1.f : 0.5f;
+          }
           pv[e] = p;
-          dsv[e] = row_ok ? half * p * (__uint_as_float(rp[j + e]) - delta) : 0.f;
+          dsv[e] = half * p * (__uint_as_float(rp[j + e]) - delta);
         }
         pk[j >> 1] = pack_bf16(pv[0], pv[1]);
         dk16[j >> 1] = pack_bf16(dsv[0], dsv[1]);
@@ -457,7 +601,7 @@ static int launch_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t l
   if (need_cols > 512) { set_error("mmgl_xattn_bwd: Nk = %lld with head_dim %d needs more than 512 TMEM columns", (long long)nk, D); return 2; }
   uint32_t tmem_cols = 32;
   while (tmem_cols < need_cols) tmem_cols <<= 1;
-  const size_t smem = 1024 + 2 * (size_t)DS * nkp * 128 + 2 * (size_t)DS * 16384 + (size_t)(2 * ps + 1) * 16384 + ps * 64 * 4 + 64;
+  const size_t smem = 2 * (size_t)DS * nkp * 128 + 2 * (size_t)DS * 16384 + (size_t)(2 * ps + 1) * 16384 + 96;
   CUtensorMap mq, mdo, mk, mv;
   int rc;
   if ((rc = make_tensor_map_2d(&mq, q, (uint64_t)(heads * D), (uint64_t)(batch * seq), (uint64_t)ldq, 64, 128))) return rc;
