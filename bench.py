@@ -48,6 +48,9 @@ def parse():
                     help="control: run the frozen text encoder on all T x 512 padded tokens and on padding neighbors, as the reference does")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--batches", type=int, default=8, help="distinct seeded synthetic batches cycled through")
+    ap.add_argument("--no-plan", action="store_true",
+                    help="control: let the module read the ragged-neighbor sizes back from the device (two host syncs per step) "
+                         "instead of taking them from the host-made plan (mmgl_b200.plan)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
@@ -378,6 +381,11 @@ def run_ours(a, w):
     spec = spec_for(w, a.batch)
     nb = max(2, a.batches)
     host = [synth.make_batch(spec, seed=1234 + rank * 100 + s, pin=True) for s in range(nb)]
+    if not a.no_plan and not a.no_packing:
+        # the data pipeline's part of the ragged-neighbor bookkeeping (which neighbors are valid, how long each text is):
+        # integer work on the host batch, shipped with it -- the step then issues no device->host read
+        from mmgl_b200 import plan as plan_mod
+        host = [dict(b, neighbor_plan=plan_mod.make_plan(b).pin_memory()) for b in host]
     resident = [synth.to_device(b, dev) for b in host]
     h2d = synth.batch_nbytes(host[0])
     tokens = token_stats(host, w)
@@ -543,7 +551,8 @@ def run_ours(a, w):
                    "l2": f"per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; {nb} seeded batches cycled",
                    "packing": "off (control): padded tokens and padding neighbors are encoded like the reference does" if a.no_packing
                    else "text encoder runs on real tokens of valid neighbors only (f2)",
-                   "weights": "random-init (MMGL_ALLOW_RANDOM_INIT=1: no checkpoints offline)", **tokens},
+                   "weights": "random-init (MMGL_ALLOW_RANDOM_INIT=1: no checkpoints offline)",
+                   "host_plan": not (a.no_plan or a.no_packing), **tokens},
         "e2e": {"value": sections / (ms_e2e * 1e-3), "unit": "sections/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "pipeline": "batch i+1 H2D prefetched on a copy stream during step i; loss of step i read from pinned "

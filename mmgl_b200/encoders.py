@@ -88,7 +88,7 @@ def _supported(cfg) -> bool:
 
 
 @torch.no_grad()
-def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=None):
+def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=None, plan=None):
     """``model(input_ids, attention_mask).last_hidden_state[:, 0]`` of a HF RobertaModel, [N, hidden] bf16.
     (HF: models/roberta/modeling_roberta.py -- embeddings :70-150, layer :400-470; post-LN blocks.)"""
     cfg = model.config
@@ -105,7 +105,12 @@ def roberta_cls_hidden(model, input_ids, attention_mask, pack_padding=None):
     pos = torch.cumsum(not_pad, dim=1) * not_pad + pad
     heads, h = cfg.num_attention_heads, cfg.hidden_size
     d = h // heads
-    plan = _pack_plan(attention_mask) if pack_padding else None
+    # plan: (token index, cu_seqlens, total, longest) made on the host (mmgl_b200.plan: no sync), False = do not pack,
+    # None = derive it here from the device mask (one device->host read)
+    if plan is None:
+        plan = _pack_plan(attention_mask) if pack_padding else None
+    elif plan is False:
+        plan = None
     if plan is None:
         x = emb.word_embeddings(input_ids) + emb.position_embeddings(pos) + emb.token_type_embeddings.weight[0]
         x = x.reshape(n * s, -1)

@@ -163,15 +163,15 @@ class LlamaCrossAttentionModel(nn.Module, _NeighborEncoderMixin):
 
     def forward(self, input_ids, attention_mask, labels, images=None, image_positions=None, neighbor_input_ids=None,
                 neighbor_attention_mask=None, neighbor_pos_ids=None, text_locations=None, neighbor_images=None,
-                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None):
+                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None, neighbor_plan=None):
         if self.neighbor_mode == "raw" or self.context == "section_only":
             bank = mask = None
         elif self.context == "text_only":
-            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None)
+            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None, plan=neighbor_plan)
         elif self.context in ("section_all", "all"):
             bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, text_locations,
                                          neighbor_images, neighbor_images_pos_ids, image_locations,
-                                         lpe=lpe if self.position_type == "laplacian" else None)
+                                         lpe=lpe if self.position_type == "laplacian" else None, plan=neighbor_plan)
             if self.position_type == "gnn" and graph is not None:
                 b, nk, h = bank.shape
                 flat = bank.reshape(b, nk // self.n_text_tokens, self.n_text_tokens * h)

@@ -426,12 +426,14 @@ class _NeighborEncoderMixin:
             for p in self.visual_model.parameters():
                 p.requires_grad = False
 
-    def encode_text(self, input_ids, attention_mask):
+    def encode_text(self, input_ids, attention_mask, pack=None):
         """frozen text encoder (+ trainable pooler) -> pooled features [B*T, E]
-        (model/modelling_cross_attention.py:988-996)."""
+        (model/modelling_cross_attention.py:988-996).  ``pack``: host-made packing plan (mmgl_b200.plan), or None."""
         l = input_ids.shape[-1]
         ids2, am2 = input_ids.reshape(-1, l), attention_mask.reshape(-1, l)
         # frozen RoBERTa on this package's kernels; only the [CLS] row is consumed (TextPooler: hidden[:, 0])
+        if pack is not None:
+            return self.text_pooler.pool_cls(encoders.roberta_cls_hidden(self.text_model, ids2, am2, plan=pack))
         return self.text_pooler.pool_cls(encoders.roberta_cls_hidden(self.text_model, ids2, am2))
 
     def encode_images(self, pixel_values):
@@ -462,20 +464,29 @@ class _NeighborEncoderMixin:
         full = torch.zeros((total, y.shape[-1]), dtype=y.dtype, device=y.device)
         return full.index_copy(0, idx, y)
 
-    def text_projection(self, input_ids, attention_mask, pos_ids=None):
+    def text_projection(self, input_ids, attention_mask, pos_ids=None, plan=None):
         """pooled [B*T, E] -> Linear(E -> n_tok*H): [B, T, n_tok*H] (the position-embedding add is fused into the
-        bank packing kernel; :997)."""
+        bank packing kernel; :997).  With a host-made ``plan`` (mmgl_b200.plan.NeighborPlan) no device->host read happens."""
         b, n, l = input_ids.shape
-        idx = self._needed(pos_ids)
+        use_plan = plan is not None and self._plan_usable()
+        idx = plan.text_idx if use_plan else self._needed(pos_ids)
         ids2, am2 = input_ids.reshape(-1, l), attention_mask.reshape(-1, l)
         if idx is not None:
             ids2, am2 = ids2.index_select(0, idx), am2.index_select(0, idx)
-        y = ops.linear(self.encode_text(ids2, am2), self.text_embeddings.weight, self.text_embeddings.bias)
+        pack = None
+        if use_plan:
+            pack = (plan.tok_idx, plan.cu, plan.total, plan.max_len) if plan.pack else False
+        pooled = self.encode_text(ids2, am2, pack) if use_plan else self.encode_text(ids2, am2)
+        y = ops.linear(pooled, self.text_embeddings.weight, self.text_embeddings.bias)
         return self._scatter_rows(y, idx, b * n).reshape(b, n, -1)
 
-    def visual_projection(self, pixel_values, pos_ids=None):
+    def _plan_usable(self):
+        """a plan made with the default rules is only valid while the module still follows them"""
+        return self.skip_padding_neighbors and getattr(self, "position_type", "none") != "gnn" and encoders.PACK_PADDING
+
+    def visual_projection(self, pixel_values, pos_ids=None, plan=None):
         b, n = pixel_values.shape[:2]
-        idx = self._needed(pos_ids)
+        idx = plan.image_idx if (plan is not None and self._plan_usable()) else self._needed(pos_ids)
         px = pixel_values.reshape(b * n, 1, *pixel_values.shape[2:])
         if idx is not None:
             px = px.index_select(0, idx)
@@ -488,13 +499,13 @@ class _NeighborEncoderMixin:
 
     def build_bank(self, neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, text_locations,
                    neighbor_images=None, neighbor_images_pos_ids=None, image_locations=None, lpe=None,
-                   use_pos_tables=True):
+                   use_pos_tables=True, plan=None):
         """bank [B,(T+I)*n_tok,H] bf16 + byte mask [B,(T+I)*n_tok]
         (model/modelling_cross_attention.py:1072-1104; model/modelling_self_attention.py:263-315)."""
         if neighbor_images is not None and self.n_text_tokens != self.n_visual_tokens:
             raise ValueError("the packed bank needs n_text_tokens == n_visual_tokens (reference :1093-1098)")
-        tp = self.text_projection(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids)
-        ip = self.visual_projection(neighbor_images, neighbor_images_pos_ids) if neighbor_images is not None else None
+        tp = self.text_projection(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, plan)
+        ip = self.visual_projection(neighbor_images, neighbor_images_pos_ids, plan) if neighbor_images is not None else None
         lpe_lin = getattr(self, "lpe_embeddings", None) if lpe is not None else None
         return ops.bank_pack(
             tp, self._table("text_position_embeddings") if use_pos_tables else None, neighbor_pos_ids, text_locations,
@@ -583,15 +594,18 @@ class CrossAttentionModel(nn.Module, _NeighborEncoderMixin):
 
     def forward(self, input_ids, attention_mask, labels, images=None, image_positions=None, neighbor_input_ids=None,
                 neighbor_attention_mask=None, neighbor_pos_ids=None, text_locations=None, neighbor_images=None,
-                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None):
+                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None, neighbor_plan=None):
+        """``neighbor_plan`` (extension, optional): mmgl_b200.plan.attach_plan(batch) made on the host by the data pipeline;
+        with it the step issues no device->host read."""
         if self.neighbor_mode == "raw" or self.context == "section_only":
             bank = mask = None                                                                     # :1068-1071
         elif self.neighbor_mode == "cross_attention" and self.context == "text_only":
-            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None)
+            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None,
+                                         plan=neighbor_plan)
         elif self.neighbor_mode == "cross_attention" and self.context in ("section_all", "all"):
             bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids,
                                          text_locations, neighbor_images, neighbor_images_pos_ids, image_locations,
-                                         lpe=lpe if self.position_type == "laplacian" else None)
+                                         lpe=lpe if self.position_type == "laplacian" else None, plan=neighbor_plan)
             if self.position_type == "gnn" and graph is not None:                                  # D9 extension
                 b, nk, h = bank.shape
                 flat = bank.reshape(b, nk // self.n_text_tokens, self.n_text_tokens * h)

@@ -217,7 +217,7 @@ class SelfAttentionModel(nn.Module, _NeighborEncoderMixin):
 
     def forward(self, input_ids, attention_mask, labels, images=None, image_positions=None, neighbor_input_ids=None,
                 neighbor_attention_mask=None, neighbor_pos_ids=None, text_locations=None, neighbor_images=None,
-                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None):
+                neighbor_images_pos_ids=None, image_locations=None, lpe=None, graph=None, neighbor_plan=None):
         if self.neighbor_mode == "raw" and self.context in _TEXT_ONLY:                               # :244-246
             return self._run_lm(input_ids=input_ids, attention_mask=attention_mask, labels=labels)
         if self.neighbor_mode == "raw" and self.context in _ALL:                                    # :248-261
@@ -236,13 +236,13 @@ class SelfAttentionModel(nn.Module, _NeighborEncoderMixin):
         use_pos = self.position_type != "none"
         if self.context in _TEXT_ONLY:                                                              # :263-280
             bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None,
-                                         use_pos_tables=use_pos)
+                                         use_pos_tables=use_pos, plan=neighbor_plan)
         else:                                                                                       # :282-320
             is_all = self.context == "all"
             bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, text_locations,
                                          neighbor_images, neighbor_images_pos_ids, image_locations,
                                          lpe=lpe if (is_all and self.position_type == "laplacian") else None,
-                                         use_pos_tables=use_pos)
+                                         use_pos_tables=use_pos, plan=neighbor_plan)
             if is_all and self.position_type == "gnn":
                 b, nk, h = bank.shape
                 flat = bank.reshape(b, nk // self.n_text_tokens, self.n_text_tokens * h)

@@ -243,3 +243,40 @@ def test_cross_attention_model_with_graph_position_encodings_vs_oracle(golden, p
         assert params[k].grad is not None, f"{k} received no gradient"
         rep.close("d " + k, params[k].grad, p[k].grad, 8e-2)
     rep.finish()
+
+
+def test_host_plan_changes_nothing(golden):
+    """mmgl_b200.plan (the data pipeline's ragged-neighbor bookkeeping, shipped with the batch) removes the per-step host
+    syncs; loss, logits and gradients must be IDENTICAL to the run that reads the sizes back from the device."""
+    from transformers import CLIPVisionConfig, OPTConfig, RobertaConfig
+    from mmgl_b200 import modules as M, plan, synth
+    g = golden("wrapper_cross_d64")
+    txt = RobertaConfig(vocab_size=512, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                        max_position_embeddings=80, pad_token_id=1)
+    vis = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                           image_size=32, patch_size=16)
+    args = types.SimpleNamespace(
+        context="all", neighbor_mode="embedding", peft_type="flamingo", n_text_tokens=2, n_visual_tokens=2,
+        model_name_or_path=OPTConfig(**g["lm_config"]), text_model=txt, visual_model=vis, max_output_length=16,
+        freeze_lm=False, neighbor_layer_wise=2, lora_r=64, lora_alpha=1, lora_dropout=0.0)
+    torch.manual_seed(7)
+    model = M.CrossAttentionModel(args, tokenizer=None)
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if "gating" in n:
+                prm.fill_(0.5)
+    M.prepare_for_training(model, "cuda").eval()
+    spec = synth.BatchSpec(batch=4, max_input_length=48, max_output_length=16, text_neighbors=5, image_neighbors=3,
+                           vocab_size=512, neighbor_vocab_size=512, image_size=32)
+    host = synth.make_batch(spec, seed=11)
+    res = []
+    for with_plan in (False, True):
+        batch = plan.attach_plan(host) if with_plan else host
+        batch = {k: v.cuda() for k, v in batch.items()}
+        model.zero_grad()
+        out = model(**batch)
+        out.loss.backward()
+        res.append((out.loss.detach().clone(), out.logits.detach().clone(),
+                    {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert res[0][2].keys() == res[1][2].keys() and all(torch.equal(res[0][2][k], res[1][2][k]) for k in res[0][2])

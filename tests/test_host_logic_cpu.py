@@ -243,3 +243,29 @@ def test_gnn_disables_the_padding_neighbor_skip():
     assert m._needed(pos).tolist() == [0, 1, 3]
     m.position_type = "gnn"
     assert m._needed(pos) is None
+
+
+def test_host_plan_equals_the_device_side_bookkeeping():
+    """mmgl_b200.plan.make_plan (data-pipeline side, no sync) must reproduce what the module derives from the device tensors:
+    modules._needed (valid neighbors) and encoders._pack_plan (real-token index, cu_seqlens, totals).  Integer work: exact."""
+    from mmgl_b200 import encoders, plan, synth
+    from mmgl_b200.modules import _NeighborEncoderMixin
+    for seed in range(6):
+        b = synth.make_batch(synth.BatchSpec(batch=5, max_input_length=64, max_output_length=16, text_neighbors=6,
+                                             image_neighbors=3, image_size=8), seed=seed)
+        p = plan.make_plan(b)
+        m = _NeighborEncoderMixin()
+        m.position_type = "none"
+        idx = m._needed(b["neighbor_pos_ids"])
+        want_idx = idx if idx is not None else torch.arange(b["neighbor_pos_ids"].numel())
+        assert torch.equal(p.text_idx, want_idx)
+        iidx = m._needed(b["neighbor_images_pos_ids"])
+        assert torch.equal(p.image_idx, iidx if iidx is not None else torch.arange(b["neighbor_images_pos_ids"].numel()))
+        am2 = b["neighbor_attention_mask"].reshape(-1, 64).index_select(0, want_idx)
+        dev = encoders._pack_plan(am2)
+        assert (dev is not None) == p.pack
+        if dev is not None:
+            tok, cu, total, max_len = dev
+            assert torch.equal(tok, p.tok_idx) and torch.equal(cu, p.cu) and (total, max_len) == (p.total, p.max_len)
+    moved = p.to("cpu").pin_memory() if torch.cuda.is_available() else p.to("cpu")
+    assert moved.total == p.total and torch.equal(moved.text_idx, p.text_idx)
