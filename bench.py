@@ -456,8 +456,10 @@ def run_ours(a, w):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        t_host = time.perf_counter()
         for i in range(steps):
             last = fn(i)
+        state["host_enqueue_ms"] = (time.perf_counter() - t_host) * 1e3 / steps   # host time to ENQUEUE a step (no sync)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -480,6 +482,15 @@ def run_ours(a, w):
     n0 = _capi.launch_count()
     ms_res, loss_res = timed(step_resident, a.steps)
     launches = _capi.launch_count() - n0
+    # host time to enqueue ONE step into an empty launch queue (no blocking on a full queue): the Python / ctypes cost
+    hs = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t_h = time.perf_counter()
+        step_resident(i)
+        hs.append((time.perf_counter() - t_h) * 1e3)
+    torch.cuda.synchronize()
+    state["host_enqueue_ms_resident"] = sorted(hs)[1]
     # untimed warm-up of the end-to-end loop itself (copy-stream allocations, pinned buffers, copy engine), then K timed steps
     e2e_begin()
     for i in range(max(3, a.warmup)):
@@ -558,6 +569,7 @@ def run_ours(a, w):
                 "pipeline": "batch i+1 H2D prefetched on a copy stream during step i; loss of step i read from pinned "
                             "memory after step i+1 is enqueued (K copies + K reads inside the timed region)"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
+        "host_enqueue_ms_per_step": state.get("host_enqueue_ms_resident"),
         "roofline": roofline, "roofline_attention": extra,
         "roofline_block": None if no_reference else block_roofline(model, a.batch, w["s_in"] + w["s_out"], pk, dev),
         "clocks": clocks,
