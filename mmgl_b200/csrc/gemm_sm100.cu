@@ -40,7 +40,8 @@ template <int BN> struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);  // two accumulator stages, pow2
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
+  static constexpr int kStoreStageBytes = 8 * 2048;   // one 32-row x 64-byte transpose buffer per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kStoreStageBytes + 1024;  // +1024: manual alignment
 };
 
 struct GemmParams {
@@ -64,6 +65,7 @@ struct GemmParams {
   __nv_bfloat16* aux; int64_t ldaux;
   const __nv_bfloat16* relu_mask; int64_t ldmask;
   int32_t vec_ok;
+  int32_t staged_store;   // bf16 fast path: transpose each chunk through shared memory for 64-byte row segments per store
   uint32_t drop_thresh; float drop_scale; uint64_t drop_seed; int64_t drop_groups;  // drop_thresh == 0: no dropout
 };
 
@@ -201,20 +203,50 @@ __device__ __forceinline__ void epilogue_store1(const GemmParams& p, float v, in
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 o;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(addr) : "memory");
+  return o;
+}
+
 // Epilogue of one warp: its 32 accumulator rows x the 32-column chunks [c_begin, c_end) of the tile at TMEM `taddr`.
 // For short-K tiles the epilogue, not the MMA, is the critical path, so the common case (bf16 output, 16-byte aligned
 // operands) issues the residual / ReLU-mask loads of chunk c+1 before it touches chunk c: their global latency hides
 // behind the TMEM load and the arithmetic of the current chunk.
+//
+// Stores: a thread owns one output ROW, so a direct store instruction of the warp touches 32 different 128-byte lines
+// with 16 bytes each.  When the warp's 32 rows are all inside the matrix the bf16 chunk (32 rows x 64 bytes) is instead
+// transposed through `stg`, the warp's private 2 KB of shared memory (16-byte units XOR-swizzled so that neither side
+// has bank conflicts), and written back as 8 rows x 64 contiguous bytes per instruction: a quarter of the lines per
+// store.  stg == 0 keeps the direct stores.
 __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t taddr, int64_t row, int n0, int c_begin,
-                                                int c_end, float gate_t) {
+                                                int c_end, float gate_t, uint32_t stg = 0) {
   const bool fast = p.vec_ok && !p.out_fp32 && !p.accumulate;
   const bool row_ok = row < p.m;
+  const int lane = threadIdx.x & 31;
+  const bool staged = stg != 0 && (row - lane + 31) < p.m;     // warp-uniform: every row of this warp is valid
   uint4 res_n[4], msk_n[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) { res_n[g] = make_uint4(0, 0, 0, 0); msk_n[g] = make_uint4(0, 0, 0, 0); }
   auto prefetch = [&](int c) {
     const int64_t col0 = n0 + c * 32;
-    if (row_ok && col0 + 32 <= p.n) {
+    if (staged && col0 + 32 <= p.n) {
+      // coalesced pattern: instruction i fetches rows 8i .. 8i+7 of the warp, 64 contiguous bytes each; transpose_in()
+      // hands every thread its own row afterwards
+      const int64_t r0 = row - lane + (lane >> 2);
+      const int cg = (lane & 3) * 8;
+      if (p.residual != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res_n[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (r0 + 8 * i) * p.ldres + col0 + cg));
+      }
+      if (p.relu_mask != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) msk_n[i] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + (r0 + 8 * i) * p.ldmask + col0 + cg));
+      }
+    } else if (row_ok && col0 + 32 <= p.n) {
       if (p.residual != nullptr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) res_n[g] = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldres + col0) + g);
@@ -222,6 +254,45 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       if (p.relu_mask != nullptr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) msk_n[g] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + row * p.ldmask + col0) + g);
+      }
+    }
+  };
+  auto transpose_in = [&](uint4 (&t)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r_in = 8 * i + (lane >> 2), cg = lane & 3;
+      st_shared_v4(stg + r_in * 64 + ((cg ^ ((r_in >> 1) & 3)) << 4), t[i].x, t[i].y, t[i].z, t[i].w);
+    }
+    __syncwarp();
+    const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) t[g] = ld_shared_v4(stg + lane * 64 + ((g ^ sw) << 4));
+    __syncwarp();
+  };
+  auto store_chunk = [&](const float (&v)[32], __nv_bfloat16* base, int64_t ld, int64_t col0) {
+    if (staged) {
+      const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(stg + lane * 64 + ((g ^ sw) << 4), pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]),
+                     pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+      __syncwarp();
+      __nv_bfloat16* dbase = base + (row - lane) * ld + col0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r_in = 8 * i + (lane >> 2), cg = lane & 3;
+        const uint4 o = ld_shared_v4(stg + r_in * 64 + ((cg ^ ((r_in >> 1) & 3)) << 4));
+        *reinterpret_cast<uint4*>(dbase + (int64_t)r_in * ld + cg * 8) = o;
+      }
+      __syncwarp();
+    } else {
+      __nv_bfloat16* dp = base + row * ld + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * g], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+        o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+        reinterpret_cast<uint4*>(dp)[g] = o;
       }
     }
   };
@@ -241,6 +312,10 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
     const int64_t col0 = n0 + c * 32;
     if (!row_ok || col0 >= p.n) continue;
     if (fast && col0 + 32 <= p.n) {
+      if (staged) {
+        if (p.residual != nullptr) transpose_in(res);
+        if (p.relu_mask != nullptr) transpose_in(msk);
+      }
       if (p.bias != nullptr) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -272,15 +347,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
           for (int j = 0; j < 8; ++j) v[8 * g + j] = dropout_keep(bits, j, p.drop_thresh) ? v[8 * g + j] * p.drop_scale : 0.f;
         }
       }
-      if (p.aux != nullptr) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(v[8 * g], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-          o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-          reinterpret_cast<uint4*>(p.aux + row * p.ldaux + col0)[g] = o;
-        }
-      }
+      if (p.aux != nullptr) store_chunk(v, p.aux, p.ldaux, col0);
       if (p.gate != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= gate_t;
@@ -293,14 +360,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
           for (int j = 0; j < 4; ++j) { v[8 * g + 2 * j] += bf16lo(w[j]); v[8 * g + 2 * j + 1] += bf16hi(w[j]); }
         }
       }
-      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col0;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_bf16(v[8 * g], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-        o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-        reinterpret_cast<uint4*>(dp)[g] = o;
-      }
+      store_chunk(v, reinterpret_cast<__nv_bfloat16*>(p.d), p.ldd, col0);
     } else if (p.vec_ok && col0 + 32 <= p.n) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -419,6 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     const int half = (warp - 2) >> 2;
     constexpr int kChunksPerHalf = BN / 64;
     const float gate_t = (p.gate != nullptr) ? tanh_precise(__ldg(p.gate)) : 1.f;
+    const uint32_t stg = p.staged_store ? smem_u32(smem + kStages * Cfg::kStageBytes + 256 + (warp - 2) * 2048) : 0u;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (p.n_fastest ? tile / p.n_blocks : tile % p.m_blocks) * BM;
@@ -427,7 +488,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       tc_fence_after();
       const int64_t row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      epilogue_chunks(p, taddr, row, n0, half * kChunksPerHalf, (half + 1) * kChunksPerHalf, gate_t);
+      epilogue_chunks(p, taddr, row, n0, half * kChunksPerHalf, (half + 1) * kChunksPerHalf, gate_t, stg);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -480,7 +541,8 @@ template <int BN> struct PairCfg {
   static constexpr int kStageBytes = kATileBytes + kBHalfBytes;   // per CTA
   static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kStoreStageBytes = 8 * 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kStoreStageBytes + 1024;
 };
 
 template <int BN, int A_MN, int B_MN>
@@ -592,6 +654,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     const int quarter = warp & 3;
     const int c_begin = ((warp - 2) >> 2) * (BN / 64), c_end = c_begin + BN / 64;
     const float gate_t = (p.gate != nullptr) ? tanh_precise(__ldg(p.gate)) : 1.f;
+    const uint32_t stg = p.staged_store ? smem_u32(smem + kStages * Cfg::kStageBytes + 256 + (warp - 2) * 2048) : 0u;
     int as = 0; uint32_t aphase = 0;
     PairWork w;
     for (int it = 0; pair_next_work(p, cluster, num_clusters, num_tiles, kblocks, it, w); ++it) {
@@ -667,7 +730,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
           }
         }
       } else {
-        epilogue_chunks(p, taddr, row, n0, c_begin, c_end, gate_t);
+        epilogue_chunks(p, taddr, row, n0, c_begin, c_end, gate_t, stg);
       }
       tc_fence_before();
       __syncwarp();
@@ -995,6 +1058,8 @@ extern "C" int mmgl_gemm_bf16(const mmgl_gemm_args* a, void* stream_) {
   if (a->aux) vec = vec && aligned16(a->aux) && a->ldaux % 8 == 0;
   if (a->relu_mask) vec = vec && aligned16(a->relu_mask) && a->ldmask % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
+  static const int staged_env = [] { const char* e = getenv("MMGL_GEMM_STAGED"); return e ? atoi(e) : 1; }();
+  p.staged_store = staged_env;
   MMGL_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "mmgl_gemm_bf16: dropout_p must be in [0,1)");
   p.drop_thresh = (uint32_t)(a->dropout_p * 65536.f + 0.5f);
   p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
