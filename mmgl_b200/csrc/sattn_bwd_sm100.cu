@@ -152,7 +152,8 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::nbars);
   const int kb_stride = 4 * nbk + ((4 * nbk) & 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  // warp index / TMEM base through a lane-0 broadcast: ptxas then treats them as warp-uniform (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, tid = threadIdx.x;
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < C::nbars; ++i) {
@@ -168,7 +169,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -197,7 +198,10 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the schedule (barrier waits included) and one elected lane issues: every operand then derives
+    // from warp-uniform values, the descriptors stay in uniform registers and the UTCHMMAs of a group go out back to back
+    // (under `if (lane == 0)` ptxas wraps each MMA in an ELECT / R2UR waterfall: ~100 cycles of issue latency per MMA).
+    {
       const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 16, 1024), desc_do = make_smem_desc(smem_u32(sdO), 16, 1024);
       const uint64_t desc_k = make_smem_desc(smem_u32(sK), 16, 1024), desc_v = make_smem_desc(smem_u32(sV), 16, 1024);
       const uint64_t desc_ds = make_smem_desc(smem_u32(sdS), 16, 1024);
@@ -220,10 +224,13 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (x >= C::NSB) mbar_wait(&bars[C::sfree + sb], ((x / C::NSB) - 1) & 1);
         tc_fence_after();
         const uint64_t qoff = (uint64_t)((qb * TB) >> 4), koff = (uint64_t)((kb * TB + la_half * 8192) >> 4);
-        mma_qk_half<D>(tmem_base + C::cS + sb * 128, desc_q + qoff, desc_k + koff);          // S  = Q_i  K_j[half]^T
-        mma_qk_half<D>(tmem_base + C::cS + sb * 128 + 64, desc_do + qoff, desc_v + koff);    // dP = dO_i V_j[half]^T
-        umma_commit(&bars[C::sfull + sb]);
-        TR(2, tri, 2000 + x);
+        if (elect_one()) {
+          mma_qk_half<D>(tmem_base + C::cS + sb * 128, desc_q + qoff, desc_k + koff);          // S  = Q_i  K_j[half]^T
+          mma_qk_half<D>(tmem_base + C::cS + sb * 128 + 64, desc_do + qoff, desc_v + koff);    // dP = dO_i V_j[half]^T
+          umma_commit(&bars[C::sfull + sb]);
+          TR(2, tri, 2000 + x);
+        }
+        __syncwarp();
         if (la_half == 1) la.next(p, gridDim.x);
         la_half ^= 1;
       };
@@ -234,17 +241,20 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         while (!la.done(p) && 2 * la.sc + la_half <= x_max) issue_s();
         const int qb = cur.sc % C::NQ, kb = cur.jc % C::NKV;
         mbar_wait(&bars[C::pfull], cur.sc & 1);
-        TR(2, tri, 3000 + cur.sc);
         tc_fence_after();
         const uint64_t qoff = (uint64_t)((qb * TB) >> 4), koff = (uint64_t)((kb * TB) >> 4);
         const bool acc = !cur.first_of_j(p);
-        mma_tn_desc<D>(tmem_base + C::cdV, desc_p_mn, desc_do_mn + qoff, acc);     // dV_j += P~^T dO_i
-        mma_tn_desc<D>(tmem_base + C::cdK, desc_ds_mn, desc_q_mn + qoff, acc);     // dK_j += dS^T Q_i
-        mma_pv_desc<D>(tmem_base + C::cdQ + (cur.sc % C::NDQ) * D, desc_ds, desc_k_mn + koff, false);   // dQ part = dS K_j
-        umma_commit(&bars[C::mma2done]);
-        umma_commit(&bars[C::qfree + qb]);
-        if (cur.last_of_j(p)) umma_commit(&bars[C::kvfree + kb]);
-        TR(2, tri, 4000 + cur.sc);
+        if (elect_one()) {
+          TR(2, tri, 3000 + cur.sc);
+          mma_tn_desc<D>(tmem_base + C::cdV, desc_p_mn, desc_do_mn + qoff, acc);     // dV_j += P~^T dO_i
+          mma_tn_desc<D>(tmem_base + C::cdK, desc_ds_mn, desc_q_mn + qoff, acc);     // dK_j += dS^T Q_i
+          mma_pv_desc<D>(tmem_base + C::cdQ + (cur.sc % C::NDQ) * D, desc_ds, desc_k_mn + koff, false);   // dQ part = dS K_j
+          umma_commit(&bars[C::mma2done]);
+          umma_commit(&bars[C::qfree + qb]);
+          if (cur.last_of_j(p)) umma_commit(&bars[C::kvfree + kb]);
+          TR(2, tri, 4000 + cur.sc);
+        }
+        __syncwarp();
         cur.next(p, gridDim.x);
       }
     }

@@ -140,6 +140,16 @@ __device__ __forceinline__ void mma_pv_half(uint32_t tmem, uint64_t da0, uint64_
   for (int k = 0; k < 4; ++k)
     umma_f16_ss(tmem, da0 + (uint64_t)((k * 32) >> 4), db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
 }
+// the same with P read from tensor memory (TS form): the 64 keys of the half block are packed bf16 pairs in two groups of
+// 16 columns, keys 0..31 at a_tmem + 0 and keys 32..63 at a_tmem + 32 (each softmax thread overwrites the head of the
+// score columns it has just read)
+template <int D>
+__device__ __forceinline__ void mma_pv_half_ts(uint32_t tmem, uint32_t a_tmem, uint64_t db0, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_f16_ts(tmem, a_tmem + (k >> 1) * 32 + (k & 1) * 8, db0 + (uint64_t)((k * 2048) >> 4), idesc, (accumulate || k != 0) ? 1u : 0u);
+}
 template <int D>
 __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0) {
 #pragma unroll

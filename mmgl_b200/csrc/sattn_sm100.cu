@@ -146,7 +146,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const int nbk = (sk + 127) / 128;
   const int ntq = (sq + 127) / 128;
   if (ntq - 1 - 2 * (int)blockIdx.x < 0) return;   // a shorter sample has no such tile pair (whole CTA, before any barrier)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a lane-0 broadcast: ptxas then knows it is warp-uniform and keeps everything derived from it (the
+  // MMA issuers' descriptors) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   int tri = 0; (void)tri;
   if (threadIdx.x == 0) TR(0, tri, 1);
   // tile 0 of the pair is the later (heavier when causal) query tile; tile 1 the one before it (absent if < 0)
@@ -172,7 +174,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   if (threadIdx.x == 0) TR(0, tri, 2);
 
   if (warp == 18) {
@@ -200,21 +202,25 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncwarp();
   } else if (warp >= 16) {
     // ------------------------------------------------------------------ MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1
+    // The WHOLE warp walks the loops (barrier waits included) and one elected lane issues: with every operand derived
+    // from warp-uniform values the descriptors live in uniform registers and the UTCHMMAs of a block go out back to
+    // back.  (Under `if (lane == 0)` ptxas wrapped every MMA in an ELECT / 5 x R2UR waterfall loop, ~100 cycles of
+    // dependent issue latency per 48-cycle MMA: the issuer thread, not the tensor pipe, set the pace of pass 2.)
     const int t = warp - 16;
-    const int nb = nblk[t];
-    if (lane == 0 && nb > 0) {
+    const int nb = t ? nblk[1] : nblk[0];
+    const int nb1 = nblk[1];
+    if (nb > 0) {
       const uint64_t dq = make_smem_desc(smem_u32(sQ + t * TB), 16, 1024);
-      const uint64_t dp = make_smem_desc(smem_u32(sP + t * 32768), 16, 1024);
       const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 1024);
       const uint64_t dv0 = make_smem_desc(smem_u32(sV), 16384, 1024);
       const uint32_t cS = tmem_base + t * 128;
       // a K / V stage is released by two arrivals, one per tile; the only tile using a block arrives twice
       auto release = [&](uint64_t* bar, int j) {
         umma_commit(bar);
-        if (j >= nblk[1]) umma_commit(bar);
+        if (j >= nb1) umma_commit(bar);
       };
       mbar_wait(&bars[B::qfull + t], 0);
-      if (t == 0) TR(2, tri, 10);
+      if (t == 0 && lane == 0) TR(2, tri, 10);
       // pass 1: S_t(j) for the row maxima, double-buffered (block j at column offset (j & 1) * 256; the O columns are
       // not in use yet), so the tensor core runs one block ahead of the max reduction
       for (int j = 0; j < nb; ++j) {
@@ -222,11 +228,14 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         mbar_wait(&bars[B::kfull + s], (j / NS) & 1);
         if (j >= 2) mbar_wait(&bars[B::sfree + 2 * (j & 1) + t], ((j >> 1) - 1) & 1);
         tc_fence_after();
-        if (t == 0) TR(2, tri, 100 + j);
-        mma_qk_desc<D>(cS + (j & 1) * 256, dq, dk0 + (uint64_t)((s * TB) >> 4));
-        umma_commit(&bars[B::sfull + 2 * (j & 1) + t]);
-        release(&bars[B::kfree + s], j);
-        if (t == 0) TR(2, tri, 150 + j);
+        if (elect_one()) {
+          if (t == 0) TR(2, tri, 100 + j);
+          mma_qk_desc<D>(cS + (j & 1) * 256, dq, dk0 + (uint64_t)((s * TB) >> 4));
+          umma_commit(&bars[B::sfull + 2 * (j & 1) + t]);
+          release(&bars[B::kfree + s], j);
+          if (t == 0) TR(2, tri, 150 + j);
+        }
+        __syncwarp();
       }
       // pass 2 prologue: S_t(0) once BOTH tiles' pass-1 reads are done (tile 0's O columns alias tile 1's second S buffer
       // and vice versa); barrier phases are consumed in order
@@ -239,7 +248,6 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       constexpr int NSB = (D == 64) ? 3 : 2;                 // S buffers per tile in pass 2 (TMEM: 2 * NSB * 64 + 2 * D <= 512)
       const uint32_t cS2 = tmem_base + t * (NSB * 64);       // + v * 64
       const uint32_t cO2 = tmem_base + 2 * NSB * 64 + t * D;
-      const uint64_t dp2[2] = {dp, dp + (uint64_t)(16384 >> 4)};
       const int nsub = 2 * nb;
       // S of half block x (half x & 1 of key block x >> 1) into S buffer x % NSB; the first half waits for its K stage, the
       // second releases it
@@ -247,24 +255,30 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int jn = x >> 1, hk = x & 1, n = nbmax + jn, st = n % NS;
         if (hk == 0) mbar_wait(&bars[B::kfull + st], (n / NS) & 1);
         tc_fence_after();
-        mma_qk_half<D>(cS2 + (x % NSB) * 64, dq, dk0 + (uint64_t)((st * TB + hk * 8192) >> 4));
-        umma_commit(&bars[B::s2full + 2 * (x % NSB) + t]);
-        if (hk == 1) release(&bars[B::kfree + st], jn);
+        if (elect_one()) {
+          mma_qk_half<D>(cS2 + (x % NSB) * 64, dq, dk0 + (uint64_t)((st * TB + hk * 8192) >> 4));
+          umma_commit(&bars[B::s2full + 2 * (x % NSB) + t]);
+          if (hk == 1) release(&bars[B::kfree + st], jn);
+        }
+        __syncwarp();
       };
-      if (t == 0) TR(2, tri, 198);
+      if (t == 0 && lane == 0) TR(2, tri, 198);
       for (int x = 0; x < NSB && x < nsub; ++x) issue_s(x);   // the tensor core starts NSB half blocks ahead of the softmax
-      if (t == 0) TR(2, tri, 199);
+      if (t == 0 && lane == 0) TR(2, tri, 199);
       for (int jj = 0; jj < nsub; ++jj) {
         const int pp = jj & 1, j = jj >> 1, sv = j % NS;
         mbar_wait(&bars[B::pfull + 2 * pp + t], (jj >> 1) & 1);
-        if (t == 0) TR(2, tri, 200 + jj);
+        if (t == 0 && lane == 0) TR(2, tri, 200 + jj);
         if (pp == 0) mbar_wait(&bars[B::vfull + sv], (j / NS) & 1);
         tc_fence_after();
-        mma_pv_half<D>(cO2, dp2[pp], dv0 + (uint64_t)((sv * TB + pp * 8192) >> 4), jj != 0);
-        umma_commit(&bars[B::pfree + 2 * pp + t]);
-        if (pp == 1) release(&bars[B::vfree + sv], j);
+        if (elect_one()) {
+          mma_pv_half_ts<D>(cO2, cS2 + (jj % NSB) * 64, dv0 + (uint64_t)((sv * TB + pp * 8192) >> 4), jj != 0);
+          umma_commit(&bars[B::pfree + 2 * pp + t]);
+          if (pp == 1) release(&bars[B::vfree + sv], j);
+        }
+        __syncwarp();
         if (jj + NSB < nsub) issue_s(jj + NSB);               // into the S buffer the softmax warps have just finished reading
-        if (t == 0) TR(2, tri, 300 + jj);
+        if (t == 0 && lane == 0) TR(2, tri, 300 + jj);
       }
     }
     __syncwarp();
@@ -334,7 +348,6 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       // block jj, the tensor core already holds S(jj + 1) (and S(jj + 2)) and is free to run P V(jj - 1) and S(jj + NSB), so the
       // softmax -> MMA -> softmax hand-off latency stays off the critical path.  This thread owns chunk 2u + hf.
       float sum = 0.f;
-      const uint32_t p_base = smem_u32(sP + t * 32768);
       const int64_t drow = ((int64_t)b * p.heads + h) * sq + row;
       const int64_t dgroups = (sk + 7) >> 3;
       const int nsub = 2 * nb;
@@ -363,10 +376,14 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 32; ++e) rc[e] = (keep >> e) & 1u ? __float_as_uint(__uint_as_float(rc[e]) * p.drop_scale) : 0u;
         }
-        if (jj >= 2) mbar_wait(&bars[B::pfree + 2 * u + t], ((jj >> 1) - 1) & 1);   // P V(jj - 2) done: buffer reusable
-        // P buffer u is one 64-column slab; this thread's chunk fills its 16-byte columns 4 hf .. 4 hf + 3
-        store_chunk_bf16(p_base + u * 16384, tid, hf, rc);
-        fence_proxy_async();
+        if (jj >= 2) mbar_wait(&bars[B::pfree + 2 * u + t], ((jj >> 1) - 1) & 1);   // consume every phase: the final wait is by parity
+        // P (bf16 pairs) overwrites the head of the score columns this thread has just read: the P V MMA takes it from
+        // tensor memory, and S(jj + NSB) is issued behind that MMA, so the buffer is not rewritten before it is consumed
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(__uint_as_float(rc[2 * e]), __uint_as_float(rc[2 * e + 1]));
+        tmem_st_32x16(cS2 + v * 64 + hf * 32, pk);
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars[B::pfull + 2 * u + t]);
         if (threadIdx.x == 0) TR(0, tri, 250 + jj);
