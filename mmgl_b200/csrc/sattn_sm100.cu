@@ -122,15 +122,14 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p,
                  __nv_bfloat16* __restrict__ o, int64_t ldo, float* __restrict__ stats) {
   constexpr int TB = (D / 64) * 16384;   // bytes of one [128][D] tile
-  constexpr int NS = (D == 64) ? 3 : 1;  // K / V ring stages
+  constexpr int NS = (D == 64) ? 4 : 2;  // K / V ring stages
   using B = FwdBars<NS>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                    // 2 tiles
   uint8_t* sK = sQ + 2 * TB;             // NS stages
   uint8_t* sV = sK + NS * TB;            // NS stages
-  uint8_t* sP = sV + NS * TB;            // 2 x [128][128] bf16 (2 slabs each)
   const int nbk_max = (p.seq_k + 127) / 128;                       // layout: sized for the longest sample
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(sP + 2 * 32768);   // 4 * nbk words
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(sV + NS * TB);     // 4 * nbk words (P lives in tensor memory: no P tile here)
   uint64_t* bars = reinterpret_cast<uint64_t*>(kbits + 4 * nbk_max + ((4 * nbk_max) & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + B::count);
   float* xch = reinterpret_cast<float*>(tmem_ptr + 4);   // [2 tiles][2 column halves][128 rows]: row max, then row sum
@@ -160,7 +159,10 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const int nbmax = nblk[0];
   const int colq = h * D;
 
-  if (threadIdx.x == 0) {
+  // The producer lane initialises the barriers and starts the first loads (both Q tiles, the first NS K blocks) BEFORE the
+  // block-wide set-up (TMEM allocation, key-bit words): the ~3000-cycle first-touch latency of the CTA's operands overlaps it.
+  constexpr int kTmaThread = 18 * 32;
+  if (threadIdx.x == kTmaThread) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < B::count; ++i) {
       const bool wide = (i >= B::sfree && i < B::sfree + 4) || (i >= B::pfull && i < B::pfull + 4);
@@ -168,6 +170,15 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_init(&bars[i], wide ? 256 : (two ? 2 : 1));
     }
     fence_barrier_init();
+    for (int t = 0; t < 2; ++t)
+      if (nblk[t] > 0) {
+        mbar_arrive_expect_tx(&bars[B::qfull + t], TB);
+        tma_tile<D>(sQ + t * TB, &map_q, &bars[B::qfull + t], colq, rowq + qts[t] * 128);
+      }
+    for (int n = 0; n < NS && n < nbmax; ++n) {           // pass-1 blocks 0 .. NS-1 (a ring stage each, nothing to wait for)
+      mbar_arrive_expect_tx(&bars[B::kfull + n], TB);
+      tma_tile<D>(sK + n * TB, &map_k, &bars[B::kfull + n], colq, rowk + n * 128);
+    }
   }
   if (warp == 16) tmem_alloc<512>(tmem_ptr);
   build_key_bits(kbits, p.key_mask, b, sk, 4 * nbk);
@@ -180,20 +191,20 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (warp == 18) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int t = 0; t < 2; ++t)
-        if (nblk[t] > 0) {
-          mbar_arrive_expect_tx(&bars[B::qfull + t], TB);
-          tma_tile<D>(sQ + t * TB, &map_q, &bars[B::qfull + t], colq, rowq + qts[t] * 128);
-        }
+      for (int j = 0; j < NS && j < nbmax; ++j) {     // the first V blocks have a ring stage each: fetch them during pass 1
+        mbar_arrive_expect_tx(&bars[B::vfull + j], TB);
+        tma_tile<D>(sV + j * TB, &map_v, &bars[B::vfull + j], colq, rowk + j * 128);
+      }
       for (int n = 0; n < 2 * nbmax; ++n) {           // K block stream: pass 1 then pass 2
         const int j = n < nbmax ? n : n - nbmax, s = n % NS;
+        if (n < NS && n < nbmax) continue;              // issued ahead of the block-wide set-up, above
         if (n >= NS) mbar_wait(&bars[B::kfree + s], ((n / NS) - 1) & 1);
         mbar_arrive_expect_tx(&bars[B::kfull + s], TB);
         tma_tile<D>(sK + s * TB, &map_k, &bars[B::kfull + s], colq, rowk + j * 128);
         TR(3, tri, 100 + n);
-        if (n >= nbmax) {                               // pass 2: V block j rides along
+        if (n >= nbmax && j >= NS) {                    // pass 2: V block j rides along
           const int sv = j % NS;
-          if (j >= NS) mbar_wait(&bars[B::vfree + sv], ((j / NS) - 1) & 1);
+          mbar_wait(&bars[B::vfree + sv], ((j / NS) - 1) & 1);
           mbar_arrive_expect_tx(&bars[B::vfull + sv], TB);
           tma_tile<D>(sV + sv * TB, &map_v, &bars[B::vfull + sv], colq, rowk + j * 128);
         }
@@ -420,8 +431,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 template <int D>
 int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float* stats, int64_t batch, cudaStream_t stream) {
   constexpr int TB = (D / 64) * 16384;
-  constexpr int NS = (D == 64) ? 3 : 1;
-  const size_t smem = (2 + 2 * NS) * (size_t)TB + 65536 + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16 + 2 * 2 * 128 * 4;
+  constexpr int NS = (D == 64) ? 4 : 2;
+  const size_t smem = (2 + 2 * NS) * (size_t)TB + kbits_bytes(p.seq_k) + FwdBars<NS>::count * 8 + 16 + 2 * 2 * 128 * 4;
   const bool bias = p.rel_bias != nullptr, drop = p.drop_thresh != 0;
   auto kern = bias ? (drop ? sattn_fwd_kernel<D, true, true> : sattn_fwd_kernel<D, true, false>)
                    : (drop ? sattn_fwd_kernel<D, false, true> : sattn_fwd_kernel<D, false, false>);
