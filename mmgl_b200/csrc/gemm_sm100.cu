@@ -392,7 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // lane-0 broadcast: provably warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_blocks * p.n_blocks;
   const int kblocks = p.kblocks0 + p.kblocks1;
@@ -409,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -445,8 +445,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp walks the schedule, one elected lane issues =====================
+    // (operands derived from warp-uniform values stay in uniform registers: the four UTCHMMAs of a k-block go out back to
+    // back instead of one ELECT / R2UR waterfall loop each, which `if (lane == 0)` compiles to)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -459,16 +461,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kATileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+              umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            if (kb == kblocks - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);       // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -561,7 +566,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // lane-0 broadcast: provably warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -580,7 +585,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
   tc_fence_before();
   cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote signal
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
@@ -620,8 +625,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread of the LEADER CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (warp 1 of the LEADER CTA; one elected lane issues, see the single-CTA kernel) =====
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -635,16 +640,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kATileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+              umma_f16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);   // frees this stage in BOTH CTAs
+            if (kb == w.kb1 - 1) umma_commit_pair(&tmem_full[as]);   // accumulator complete -> epilogue warps of BOTH CTAs
           }
-          umma_commit_pair(&empty_bar[stage]);   // frees this stage in BOTH CTAs
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[as]);        // accumulator complete -> epilogue warps of BOTH CTAs
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
