@@ -88,7 +88,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint32_t* saw = tmem_ptr + 2;                                      // [8] attend words of the current sample
   // barrier roles: bars[1] S done, bars[2] P V done, bars[0] K / V landed, bars[3 + slot] Q tile of that ring slot landed
 
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
+  // lane-0 broadcast: warp-uniform for ptxas, so warp 0 can issue TMA / MMA from uniform registers (no ELECT / R2UR waterfall)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), tid = threadIdx.x;
   const int ntiles = (seq + 127) / 128;
   const int n_items = batch * heads * ntiles;
   const int item0 = blockIdx.x * items_per_cta;
@@ -108,7 +109,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const uint32_t p_base = smem_u32(sP);
 
@@ -145,17 +146,20 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   int xi = 0; (void)xi;
   XTR(xi, 1);
-  uint32_t kv_uses = 0;       // thread 0: completed K / V loads (phase of bars[0])
-  if (tid == 0) {
-    load_kv(item0);
-    for (int a = 0; a < NQ && item0 + a < item_end; ++a) load_q(item0 + a, a);
+  uint32_t kv_uses = 0;       // warp 0: completed K / V loads (phase of bars[0])
+  if (warp == 0) {            // the whole warp waits; one elected lane issues the TMA / MMA instructions
+    if (elect_one()) {
+      load_kv(item0);
+      for (int a = 0; a < NQ && item0 + a < item_end; ++a) load_q(item0 + a, a);
+    }
+    __syncwarp();
     mbar_wait(&bars[0], kv_uses & 1); ++kv_uses;
     mbar_wait(&bars[3], 0);
     XTR(xi, 2);
     tc_fence_after();
-    issue_s(0);
+    if (elect_one()) issue_s(0);
+    __syncwarp();
   }
-  __syncwarp();
 
   for (int item = item0, it = 0; item < item_end; ++item, ++it) {
     const uint32_t par = it & 1;
@@ -167,7 +171,10 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     mbar_wait(&bars[1], par);
     XTR(xi, 100 + it * 10);
     tc_fence_after();
-    if (tid == 0 && item + NQ < item_end) load_q(item + NQ, it + NQ);   // S has consumed this slot: refill it NQ tiles ahead
+    if (warp == 0 && item + NQ < item_end) {   // S has consumed this slot: refill it NQ tiles ahead
+      if (elect_one()) load_q(item + NQ, it + NQ);
+      __syncwarp();
+    }
     // pass 1: row maximum over the attended keys (-FLT_MAX when the row attends nothing: the clamp of the reference then
     // makes every existing key's score finfo.min, i.e. uniform attention over the bank)
     float mx = -FLT_MAX;
@@ -230,33 +237,37 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();       // P complete; every thread has finished reading S (and, from the previous tile, O)
     XTR(xi, 102 + it * 10);
 
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      // O[128 x D] = P V : A = P K-major (K = keys), B = V MN-major ([key rows][d cols] as loaded)
-      constexpr uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-      for (int k4 = 0; k4 < nkp / 16; k4 += 4) {        // one 64-key slab of P per outer step
-        const uint64_t da = desc_p + (uint64_t)(((k4 >> 2) * 16384) >> 4), db = desc_v + (uint64_t)((k4 * 2048) >> 4);
+      if (elect_one()) {
+        // O[128 x D] = P V : A = P K-major (K = keys), B = V MN-major ([key rows][d cols] as loaded)
+        constexpr uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+        for (int k4 = 0; k4 < nkp / 16; k4 += 4) {        // one 64-key slab of P per outer step
+          const uint64_t da = desc_p + (uint64_t)(((k4 >> 2) * 16384) >> 4), db = desc_v + (uint64_t)((k4 * 2048) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (k4 + kk < nkp / 16)
-            umma_f16_ss(tmem_base + ps * 64, da + (uint64_t)((kk * 32) >> 4), db + (uint64_t)((kk * 2048) >> 4), idesc,
-                        (k4 + kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)
+            if (k4 + kk < nkp / 16)
+              umma_f16_ss(tmem_base + ps * 64, da + (uint64_t)((kk * 32) >> 4), db + (uint64_t)((kk * 2048) >> 4), idesc,
+                          (k4 + kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[2]);
       }
-      umma_commit(&bars[2]);
+      __syncwarp();
       if (has_next) {
         if (!next_same_bh) {                   // new head: its K / V replace this one's once P V has read them
           mbar_wait(&bars[2], par);
-          load_kv(item + 1);
+          if (elect_one()) load_kv(item + 1);
+          __syncwarp();
           mbar_wait(&bars[0], kv_uses & 1); ++kv_uses;
         }
         XTR(xi, 103 + it * 10);
         mbar_wait(&bars[3 + (it + 1) % NQ], ((it + 1) / NQ) & 1);
         XTR(xi, 104 + it * 10);
         tc_fence_after();
-        issue_s(it + 1);                       // runs behind P V on the tensor pipe, ready when the epilogue below is done
+        if (elect_one()) issue_s(it + 1);      // runs behind P V on the tensor pipe, ready when the epilogue below is done
+        __syncwarp();
       }
     }
-    __syncwarp();
     if (has_next && bh_of(item + 1) / heads != b) {    // next item belongs to another sample: its mask row
       load_mask_words(mask, bh_of(item + 1) / heads, nk, nchunks, saw);
       __syncthreads();
@@ -381,7 +392,8 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint32_t* saw = tmem_ptr + 2;                                           // [8] attend words of this sample
 
   const int h = blockIdx.x, b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
+  // lane-0 broadcast: warp-uniform for ptxas, so warp 0 can issue TMA / MMA from uniform registers (no ELECT / R2UR waterfall)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), tid = threadIdx.x;
   const int ntiles = (seq + 127) / 128;
   const int nchunks = (nkp + 31) / 32;
 
@@ -395,32 +407,38 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const uint32_t cS = 0, cdP = ps * 64, cdQ = alias_dq ? 0 : 2 * ps * 64;
   const uint32_t cdV = (alias_dq ? 2 * ps * 64 : 2 * ps * 64 + D), cdK = cdV + D;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP),
                  adS = smem_u32(sdS);
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 2 * DS * nkp * 128);
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bars[0], 2 * DS * nkp * 128);
 #pragma unroll
-    for (int j = 0; j < DS; ++j) {
-      tma_load_2d(sK + j * nkp * 128, &map_k, &bars[0], h * D + 64 * j, b * nk);
-      tma_load_2d(sV + j * nkp * 128, &map_v, &bars[0], h * D + 64 * j, b * nk);
+      for (int j = 0; j < DS; ++j) {
+        tma_load_2d(sK + j * nkp * 128, &map_k, &bars[0], h * D + 64 * j, b * nk);
+        tma_load_2d(sV + j * nkp * 128, &map_v, &bars[0], h * D + 64 * j, b * nk);
+      }
     }
+    __syncwarp();
   }
 
   for (int t = 0; t < ntiles; ++t) {
     const int r0 = t * 128;
     const uint32_t par = t & 1;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bars[1], 2 * DS * 16384);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bars[1], 2 * DS * 16384);
 #pragma unroll
-      for (int j = 0; j < DS; ++j) {
-        tma_load_2d(sQ + j * 16384, &map_q, &bars[1], h * D + 64 * j, b * seq + r0);
-        tma_load_2d(sdO + j * 16384, &map_do, &bars[1], h * D + 64 * j, b * seq + r0);
+        for (int j = 0; j < DS; ++j) {
+          tma_load_2d(sQ + j * 16384, &map_q, &bars[1], h * D + 64 * j, b * seq + r0);
+          tma_load_2d(sdO + j * 16384, &map_do, &bars[1], h * D + 64 * j, b * seq + r0);
+        }
       }
+      __syncwarp();
     }
     // row statistics and delta = sum_d dO * O for this thread's query row (overlaps the TMA)
     const int row = r0 + tid;
@@ -439,26 +457,28 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int e = 0; e < 4; ++e) delta += bf16lo(wo[e]) * bf16lo(wd[e]) + bf16hi(wo[e]) * bf16hi(wd[e]);
       }
     }
-    if (tid == 0) {
+    if (warp == 0) {
       if (t == 0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1], par);
       tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, nkp, 0, 0);
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, nkp, 0, 0);
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) {   // S = Q K^T
-        const uint64_t da = make_smem_desc(aQ + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-        const uint64_t db = make_smem_desc(aK + (k >> 2) * nkp * 128 + (k & 3) * 32, 16, 1024);
-        umma_f16_ss(tmem_base + cS, da, db, idesc, k != 0 ? 1u : 0u);
-      }
+        for (int k = 0; k < D / 16; ++k) {   // S = Q K^T
+          const uint64_t da = make_smem_desc(aQ + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(aK + (k >> 2) * nkp * 128 + (k & 3) * 32, 16, 1024);
+          umma_f16_ss(tmem_base + cS, da, db, idesc, k != 0 ? 1u : 0u);
+        }
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k) {   // dP = dO V^T
-        const uint64_t da = make_smem_desc(adO + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-        const uint64_t db = make_smem_desc(aV + (k >> 2) * nkp * 128 + (k & 3) * 32, 16, 1024);
-        umma_f16_ss(tmem_base + cdP, da, db, idesc, k != 0 ? 1u : 0u);
+        for (int k = 0; k < D / 16; ++k) {   // dP = dO V^T
+          const uint64_t da = make_smem_desc(adO + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(aV + (k >> 2) * nkp * 128 + (k & 3) * 32, 16, 1024);
+          umma_f16_ss(tmem_base + cdP, da, db, idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[2]);
       }
-      umma_commit(&bars[2]);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(&bars[2], par);
     tc_fence_after();
     // P = 2^((max(s, finfo.min) - m) log2 e) / l on attended keys; masked existing keys: 1 / l when the row attends nothing,
@@ -505,7 +525,7 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       {  // dQ[128 x D] = dS K : A = dS K-major (K = keys), B = K tile read MN-major
         const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
