@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
+    ap.add_argument("--timeline", default="",
+                    help="run 3 steps under torch.profiler (CUPTI kernel timeline) and write a busy / idle-gap summary to this file")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
@@ -469,6 +471,9 @@ def run_ours(a, w):
 
     for i in range(max(3, a.warmup)):
         step_resident(i)
+    if a.timeline:
+        timeline(step_resident, a.timeline, rank)
+        return
     if a.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -591,6 +596,61 @@ def run_ours(a, w):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def timeline(step, path, rank):
+    """Device timeline of 3 steps from CUPTI (torch.profiler): busy time, idle time between kernels, the largest gaps and
+    the kernels on either side of them, per-stream totals (NCCL kernels run on their own stream at N > 1).  Not a bench value."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "stream", 0)) for e in evs), key=lambda t: t[0])
+    if not ks:
+        return
+    t0, t1 = ks[0][0], max(k[1] for k in ks)
+    busy, cur_s, cur_e = 0.0, ks[0][0], ks[0][1]
+    gaps = []
+    prev_name = ks[0][2]
+    for s_, e_, name, _ in ks[1:]:
+        if s_ > cur_e:
+            busy += cur_e - cur_s
+            gaps.append((s_ - cur_e, prev_name, name))
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+        if e_ >= cur_e:
+            prev_name = name
+    busy += cur_e - cur_s
+    span = t1 - t0
+    by_name = {}
+    for s_, e_, name, _ in ks:
+        d = by_name.setdefault(name[:90], [0, 0.0])
+        d[0] += 1
+        d[1] += e_ - s_
+    hist = [0, 0, 0, 0, 0]
+    hsum = [0.0] * 5
+    for g, _, _ in gaps:
+        b = 0 if g < 2 else 1 if g < 5 else 2 if g < 20 else 3 if g < 100 else 4
+        hist[b] += 1
+        hsum[b] += g
+    lines = [f"rank {rank}: 3 steps, span {span / 3e3:.3f} ms/step, device busy (union over streams) {busy / 3e3:.3f} ms/step, "
+             f"idle {(span - busy) / 3e3:.3f} ms/step in {len(gaps) // 3} gaps/step over {len(ks) // 3} kernels/step",
+             "idle gaps by length (us): <2: %d (%.2f ms)  2-5: %d (%.2f ms)  5-20: %d (%.2f ms)  20-100: %d (%.2f ms)  >100: %d (%.2f ms)  [3 steps]"
+             % (hist[0], hsum[0] / 1e3, hist[1], hsum[1] / 1e3, hist[2], hsum[2] / 1e3, hist[3], hsum[3] / 1e3, hist[4], hsum[4] / 1e3),
+             "largest gaps (us, after kernel -> before kernel):"]
+    for g, a_, b_ in sorted(gaps, reverse=True)[:25]:
+        lines.append(f"  {g:9.1f}  {a_[:70]}  ->  {b_[:70]}")
+    lines.append("kernel time by name (ms/step):")
+    for name, (n, us) in sorted(by_name.items(), key=lambda kv: -kv[1][1])[:30]:
+        lines.append(f"  {us / 3e3:8.3f}  x{n // 3:4d}  {name}")
+    with open(path if rank == 0 else f"{path}.rank{rank}", "w") as f:
+        f.write("\n".join(lines) + "\n")
+    if rank == 0:
+        print("\n".join(lines[:3]), file=sys.stderr)
 
 
 def block_roofline(model, batch, seq, pk, dev):
