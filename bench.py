@@ -541,12 +541,14 @@ def run_ours(a, w):
     gemm_tf = g["work"] / (g["ms"] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_tcgen05_kernel (tcgen05.mma + TMA, all GEMMs of the step)", "bound": "tensor",
                 "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
-                "traffic": None,
-                "traffic_ncu": {"note": "achieved aggregates all GEMM launches of the step, so there is no single per-launch "
-                                        "figure; DRAM bytes (read + write) of the two dominant shapes from ncu --set full, "
-                                        "profiles/r01c_ncu_full_summary.md",
-                                "M5120_N2048_K8192": {"dram_bytes": 190.3e6, "algorithmic_bytes": 159.5e6},
-                                "M5120_N8192_K2048": {"dram_bytes": 83.4e6, "algorithmic_bytes": 138.5e6}},
+                "traffic": 413.2e6,
+                "traffic_ncu": {"note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant "
+                                        "shape of the step (fc2 forward, 28 launches = 10% of the step), ncu --set full, L2 "
+                                        "flushed before the launch: profiles/r02e_ncu_full_summary.md; `achieved` aggregates all "
+                                        "GEMM launches of the step",
+                                "M10240_N2048_K8192_bias_dropout_residual": {"dram_bytes": 413.2e6, "algorithmic_bytes": 285.2e6},
+                                "M10240_N8192_K2048_bias_relu": {"dram_bytes": 241.7e6, "algorithmic_bytes": 243.3e6},
+                                "M10240_N8192_K2048_dgrad_relu_mask": {"dram_bytes": 464.8e6, "algorithmic_bytes": 411.0e6}},
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "launches_per_step": g["launches"] / prof_steps, "ms_per_step": g["ms"] / prof_steps,
                 "share_of_step": g["ms"] / prof_steps / ms_res}
