@@ -628,6 +628,36 @@ def timeline(step, path, rank):
             prev_name = name
     busy += cur_e - cur_s
     span = t1 - t0
+    # collectives: time of NCCL kernels, and how much of it no compute kernel overlaps ("exposed")
+    comp = [(a_, b_) for a_, b_, n_, _ in ks if "nccl" not in n_.lower()]
+    coll = [(a_, b_) for a_, b_, n_, _ in ks if "nccl" in n_.lower()]
+
+    def union(iv):
+        out = []
+        for a_, b_ in sorted(iv):
+            if out and a_ <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], b_)
+            else:
+                out.append([a_, b_])
+        return out
+
+    def overlap(u1, u2):
+        i = j = 0
+        tot = 0.0
+        while i < len(u1) and j < len(u2):
+            lo, hi = max(u1[i][0], u2[j][0]), min(u1[i][1], u2[j][1])
+            if hi > lo:
+                tot += hi - lo
+            if u1[i][1] < u2[j][1]:
+                i += 1
+            else:
+                j += 1
+        return tot
+
+    ucomp, ucoll = union(comp), union(coll)
+    comp_busy = sum(b_ - a_ for a_, b_ in ucomp)
+    coll_busy = sum(b_ - a_ for a_, b_ in ucoll)
+    coll_hidden = overlap(ucomp, ucoll)
     by_name = {}
     for s_, e_, name, _ in ks:
         d = by_name.setdefault(name[:90], [0, 0.0])
@@ -643,6 +673,8 @@ def timeline(step, path, rank):
              f"idle {(span - busy) / 3e3:.3f} ms/step in {len(gaps) // 3} gaps/step over {len(ks) // 3} kernels/step",
              "idle gaps by length (us): <2: %d (%.2f ms)  2-5: %d (%.2f ms)  5-20: %d (%.2f ms)  20-100: %d (%.2f ms)  >100: %d (%.2f ms)  [3 steps]"
              % (hist[0], hsum[0] / 1e3, hist[1], hsum[1] / 1e3, hist[2], hsum[2] / 1e3, hist[3], hsum[3] / 1e3, hist[4], hsum[4] / 1e3),
+             f"compute kernels busy {comp_busy / 3e3:.3f} ms/step; NCCL kernels {coll_busy / 3e3:.3f} ms/step in {len(coll) // 3} launches/step, "
+             f"of which {coll_hidden / 3e3:.3f} ms overlap compute kernels and {(coll_busy - coll_hidden) / 3e3:.3f} ms are exposed",
              "largest gaps (us, after kernel -> before kernel):"]
     for g, a_, b_ in sorted(gaps, reverse=True)[:25]:
         lines.append(f"  {g:9.1f}  {a_[:70]}  ->  {b_[:70]}")
@@ -652,7 +684,7 @@ def timeline(step, path, rank):
     with open(path if rank == 0 else f"{path}.rank{rank}", "w") as f:
         f.write("\n".join(lines) + "\n")
     if rank == 0:
-        print("\n".join(lines[:3]), file=sys.stderr)
+        print("\n".join(lines[:4]), file=sys.stderr)
 
 
 def block_roofline(model, batch, seq, pk, dev):
