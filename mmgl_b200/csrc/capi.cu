@@ -1,4 +1,5 @@
 // Library-level C ABI: version, thread-local error string, launch counter, device info.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -28,6 +29,11 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MMGL_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
 }
 
 int bind_device_of(const void* device_ptr, const char* who) {

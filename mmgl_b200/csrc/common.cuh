@@ -49,6 +49,28 @@ inline int check_launch(const char* what) {
     if (int rc__ = ::mmgl::bind_device_of((ptr), (who))) return rc__; \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// Kernels of this library are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel on the
+// stream may begin (block scheduling, barrier init, TMEM allocation, descriptor prefetch) while the tail of the previous
+// one drains, instead of paying the ~2-3 us launch gap after every one of the ~800 kernels of a step.  Contract inside
+// every kernel launched this way: pdl_launch() first (dependents may start their prologue), then pdl_wait() -- executed
+// by EVERY thread -- before the first access to global memory: it returns once the preceding grid has completed and its
+// writes are visible, so read-after-write AND write-after-read on recycled buffers stay ordered.  Both are no-ops under a
+// normal launch.  MMGL_PDL=0 switches the attribute off (A/B control).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- small device helpers -------------------------------------------------------------------

@@ -410,6 +410,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_launch();
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -586,6 +588,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __gri
   cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_launch();
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
@@ -911,7 +915,8 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUten
   }
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a0, b0, a1, b1, p);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), GemmCfg<BN>::kSmemBytes, stream, a0, b0, a1, b1, p);
+  if (le != cudaSuccess) { set_error("mmgl_gemm_bf16: launch failed: %s", cudaGetErrorString(le)); return 1; }
   return check_launch("mmgl_gemm_bf16");
 }
 
@@ -944,10 +949,12 @@ static int launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& b0, const 
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = PairCfg<BN>::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, p);
   if (e != cudaSuccess) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                      float* __restrict__ rstd, int64_t rows, int hidden, float eps) {
+  pdl_launch();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -168,6 +170,8 @@ norm_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_launch();
+  pdl_wait();
   const int64_t num_tiles = (rows + kNormRows - 1) / kNormRows;
   int s = 0; uint32_t ph = 0;
   if (warp == kNormWarps) {
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(256)
 col_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_bfloat16* __restrict__ x, int64_t ldx,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ partial,
                    int64_t m, int64_t n, int64_t rows_per_chunk) {
+  pdl_launch();
+  pdl_wait();
   const int64_t col = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= n) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
@@ -322,6 +328,8 @@ col_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_
 __global__ void __launch_bounds__(256)
 col_final_kernel(const float* __restrict__ partial, int chunks, int64_t n, float scale, const float* __restrict__ gate,
                  float* __restrict__ out, int accumulate) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t col = (int64_t)blockIdx.x * 32 + tx;
@@ -344,6 +352,8 @@ col_final_kernel(const float* __restrict__ partial, int chunks, int64_t n, float
 __global__ void __launch_bounds__(256)
 dot_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_bfloat16* __restrict__ b, int64_t ldb,
                    int64_t m, int64_t n, float* __restrict__ partial) {
+  pdl_launch();
+  pdl_wait();
   const int64_t nvec = n >> 3;  // host guarantees n % 8 == 0
   float acc = 0.f;
   for (int64_t r = blockIdx.x; r < m; r += gridDim.x) {
@@ -368,6 +378,8 @@ dot_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const __nv_
 __global__ void __launch_bounds__(256)
 gate_final_kernel(const float* __restrict__ partial, int blocks, const float* __restrict__ gate, float* __restrict__ out,
                   int accumulate) {
+  pdl_launch();
+  pdl_wait();
   float acc = 0.f;
   for (int i = threadIdx.x; i < blocks; i += 256) acc += partial[i];
   __shared__ float red[8];
@@ -479,6 +491,8 @@ ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const int64_
 __global__ void __launch_bounds__(256)
 dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo,
                      int64_t m, int64_t n, uint32_t thresh, float scale, uint64_t seed, int vec) {
+  pdl_launch();
+  pdl_wait();
   const int64_t groups = (n + 7) / 8;
   const int64_t total = m * groups;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -700,10 +714,9 @@ static int norm_fwd(const char* who, const void* x, const float* gamma, const fl
   MMGL_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && (!beta || aligned16(beta)), "%s: unaligned", who);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
-  if (hidden <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
-  else if (hidden <= 2048) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
-  else if (hidden <= 4096) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
-  else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps);
+  auto kern = hidden <= 1024 ? layernorm_fwd_kernel<4> : hidden <= 2048 ? layernorm_fwd_kernel<8>
+              : hidden <= 4096 ? layernorm_fwd_kernel<16> : layernorm_fwd_kernel<32>;
+  MMGL_CUDA(launch_pdl(kern, dim3(grid), dim3(256), 0, s, X, gamma, beta, Y, mean, rstd, rows, (int)hidden, eps));
   return check_launch(who);
 }
 
@@ -748,8 +761,8 @@ static int norm_bwd(const char* who, const void* dy, const void* x, const float*
       cudaFuncSetAttribute(norm_bwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemBudget + 1024);
     });
     const unsigned g = (unsigned)std::min<int64_t>((rows + kNormRows - 1) / kNormRows, sm_count());
-    if (R) norm_bwd_staged_kernel<true><<<g, kNormThreads, smem, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden, stages);
-    else norm_bwd_staged_kernel<false><<<g, kNormThreads, smem, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden, stages);
+    MMGL_CUDA(launch_pdl(R ? norm_bwd_staged_kernel<true> : norm_bwd_staged_kernel<false>, dim3(g), dim3(kNormThreads), smem, s, DY, X,
+                         gamma, mean, rstd, R, DX, rows, (int)hidden, stages));
   } else
   if (hidden <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden);
   else if (hidden <= 2048) layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(DY, X, gamma, mean, rstd, R, DX, rows, (int)hidden);
@@ -762,15 +775,15 @@ static int norm_bwd(const char* who, const void* dy, const void* x, const float*
     dim3 g((unsigned)((hidden + 2047) / 2048), (unsigned)chunks);
     float* ws = reinterpret_cast<float*>(workspace);
     if (dgamma) {
-      col_partial_kernel<1><<<g, 256, 0, s>>>(DY, hidden, X, hidden, mean, rstd, ws, rows, hidden, rpc);
+      MMGL_CUDA(launch_pdl(col_partial_kernel<1>, g, dim3(256), 0, s, DY, hidden, X, hidden, mean, rstd, ws, rows, hidden, rpc));
       if (int rc = check_launch(who)) return rc;
-      col_final_kernel<<<(unsigned)((hidden + 31) / 32), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dgamma, accumulate);
+      MMGL_CUDA(launch_pdl(col_final_kernel, dim3((unsigned)((hidden + 31) / 32)), dim3(256), 0, s, ws, chunks, hidden, 1.f, nullptr, dgamma, accumulate));
       if (int rc = check_launch(who)) return rc;
     }
     if (dbeta) {
-      col_partial_kernel<0><<<g, 256, 0, s>>>(DY, hidden, nullptr, 0, nullptr, nullptr, ws, rows, hidden, rpc);
+      MMGL_CUDA(launch_pdl(col_partial_kernel<0>, g, dim3(256), 0, s, DY, hidden, nullptr, 0, nullptr, nullptr, ws, rows, hidden, rpc));
       if (int rc = check_launch(who)) return rc;
-      col_final_kernel<<<(unsigned)((hidden + 31) / 32), 256, 0, s>>>(ws, chunks, hidden, 1.f, nullptr, dbeta, accumulate);
+      MMGL_CUDA(launch_pdl(col_final_kernel, dim3((unsigned)((hidden + 31) / 32)), dim3(256), 0, s, ws, chunks, hidden, 1.f, nullptr, dbeta, accumulate));
       if (int rc = check_launch(who)) return rc;
     }
   }
@@ -807,9 +820,9 @@ extern "C" int mmgl_colsum(const void* x, int64_t ldx, int64_t m, int64_t n, flo
   const int64_t rpc = (m + chunks - 1) / chunks;
   dim3 g((unsigned)((n + 2047) / 2048), (unsigned)chunks);
   float* ws = reinterpret_cast<float*>(workspace);
-  col_partial_kernel<0><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, ws, m, n, rpc);
+  MMGL_CUDA(launch_pdl(col_partial_kernel<0>, g, dim3(256), 0, s, (const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, ws, m, n, rpc));
   if (int rc = check_launch("mmgl_colsum(partial)")) return rc;
-  col_final_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(ws, chunks, n, scale, gate, out, accumulate);
+  MMGL_CUDA(launch_pdl(col_final_kernel, dim3((unsigned)((n + 31) / 32)), dim3(256), 0, s, ws, chunks, n, scale, gate, out, accumulate));
   return check_launch("mmgl_colsum(final)");
 }
 
@@ -824,9 +837,9 @@ extern "C" int mmgl_gate_grad(const void* dy, int64_t lddy, const void* a, int64
   const int blocks = (int)(m < 592 ? m : 592);
   MMGL_REQUIRE(workspace && workspace_bytes >= (size_t)blocks * sizeof(float), "mmgl_gate_grad: workspace too small");
   float* ws = reinterpret_cast<float*>(workspace);
-  dot_partial_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)a, lda, m, n, ws);
+  MMGL_CUDA(launch_pdl(dot_partial_kernel, dim3(blocks), dim3(256), 0, s, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)a, lda, m, n, ws));
   if (int rc = check_launch("mmgl_gate_grad(partial)")) return rc;
-  gate_final_kernel<<<1, 256, 0, s>>>(ws, blocks, gate, out, accumulate);
+  MMGL_CUDA(launch_pdl(gate_final_kernel, dim3(1), dim3(256), 0, s, ws, blocks, gate, out, accumulate));
   return check_launch("mmgl_gate_grad(final)");
 }
 
@@ -869,8 +882,8 @@ extern "C" int mmgl_dropout_apply(const void* x, int64_t ldx, void* out, int64_t
   const int64_t total = m * ((n + 7) / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dropout_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, m, n,
-                                                       thresh, scale, seed, vec);
+  MMGL_CUDA(launch_pdl(dropout_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, s, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out,
+                       ldo, m, n, thresh, scale, seed, vec));
   return check_launch("mmgl_dropout_apply");
 }
 

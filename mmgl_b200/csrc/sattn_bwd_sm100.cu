@@ -96,6 +96,8 @@ template <int D>
 __global__ void __launch_bounds__(256)
 sattn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ d_o, int64_t lddo,
                    float* __restrict__ delta, int64_t rows, int seq_q, int heads) {
+  pdl_launch();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int chunks = (heads * D + 255) / 256;
   const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -170,6 +172,8 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_launch();
+  pdl_wait();   // the set-up above overlapped the previous kernel's tail (the delta pre-pass, usually)
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -535,13 +539,13 @@ int launch_bwd_v(const Maps& mp, const AttnParams& p, const void* o, int64_t ldo
   {
     const int64_t rows = (int64_t)p.batch * p.seq_q;
     const int64_t warps = rows * ((p.heads * D + 255) / 256);
-    sattn_delta_kernel<D><<<dim3((unsigned)((warps + 7) / 8)), 256, 0, stream>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo,
-                                                                                 delta, rows, p.seq_q, p.heads);
+    MMGL_CUDA(launch_pdl(sattn_delta_kernel<D>, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const __nv_bfloat16*)o, ldo,
+                         (const __nv_bfloat16*)d_o, lddo, delta, rows, p.seq_q, p.heads));
     if (int rc = check_launch("mmgl_attn_bwd(delta)")) return rc;
   }
-  kern<<<dim3((unsigned)grid), 128 * tpr + 64, smem, stream>>>(mp.q, mp.d_o, mp.k, mp.v, p, (const __nv_bfloat16*)o, ldo,
-                                                    (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq,
-                                                    (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, dq_ws, delta);
+  MMGL_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(128 * tpr + 64), smem, stream, mp.q, mp.d_o, mp.k, mp.v, p,
+                       (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, stats, (__nv_bfloat16*)dq, lddq,
+                       (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, dq_ws, delta));
   return check_launch("mmgl_attn_bwd");
 }
 

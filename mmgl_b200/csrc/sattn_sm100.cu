@@ -138,6 +138,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   // this sample's lengths and first rows: uniform batch, or a packed variable-length batch (cu_seqlens)
   int sq = p.seq_q, sk = p.seq_k, rowq = b * p.seq_q, rowk = b * p.seq_k;
   if (p.cu_seqlens != nullptr) {
+    pdl_wait();   // a global read ahead of the common wait point below
     const int c0 = p.cu_seqlens[b], c1 = p.cu_seqlens[b + 1];
     sq = sk = c1 - c0;
     rowq = rowk = c0;
@@ -170,6 +171,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_init(&bars[i], wide ? 256 : (two ? 2 : 1));
     }
     fence_barrier_init();
+    pdl_launch();
+    pdl_wait();                                          // (every other thread waits below, before its first global access)
     for (int t = 0; t < 2; ++t)
       if (nblk[t] > 0) {
         mbar_arrive_expect_tx(&bars[B::qfull + t], TB);
@@ -181,6 +184,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
   }
   if (warp == 16) tmem_alloc<512>(tmem_ptr);
+  if (threadIdx.x != kTmaThread) { pdl_launch(); pdl_wait(); }
   build_key_bits(kbits, p.key_mask, b, sk, 4 * nbk);
   tc_fence_before();
   __syncthreads();
@@ -439,7 +443,7 @@ int launch_fwd(const Maps& mp, const AttnParams& p, void* o, int64_t ldo, float*
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntq = (p.seq_q + 127) / 128;
   dim3 grid((unsigned)((ntq + 1) / 2), (unsigned)p.heads, (unsigned)batch);
-  kern<<<grid, 608, smem, stream>>>(mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats);
+  MMGL_CUDA(launch_pdl(kern, grid, dim3(608), smem, stream, mp.q, mp.k, mp.v, p, (__nv_bfloat16*)o, ldo, stats));
   return check_launch("mmgl_attn_fwd");
 }
 

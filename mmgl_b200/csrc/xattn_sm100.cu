@@ -105,6 +105,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
   if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
   const int nchunks = (nkp + 31) / 32;
+  pdl_launch();
+  pdl_wait();   // barrier init / TMEM allocation overlapped the previous kernel's tail; global memory from here on
   load_mask_words(mask, bh_of(item0) / heads, nk, nchunks, saw);
   tc_fence_before();
   __syncthreads();
@@ -340,8 +342,8 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   if (per_cta < 1) per_cta = 1;
   if (per_cta < ntiles && ntiles <= 2 * per_cta) per_cta = ntiles;   // (longer runs simply straddle heads: K / V reload at the seam)
   const int64_t grid = (n_items + per_cta - 1) / per_cta;
-  kern<<<dim3((unsigned)grid), 128, smem, stream>>>(mq, mk, mv, mask, (__nv_bfloat16*)o, ldo, stats, (int)seq, (int)nk, nkp,
-                                                    (int)heads, (int)batch, (int)per_cta, tmem_cols);
+  MMGL_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(128), smem, stream, mq, mk, mv, mask, (__nv_bfloat16*)o, ldo, stats, (int)seq,
+                       (int)nk, nkp, (int)heads, (int)batch, (int)per_cta, tmem_cols));
   return check_launch("mmgl_xattn_fwd");
 }
 
@@ -403,6 +405,8 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(tmem_ptr, tmem_cols);
+  pdl_launch();
+  pdl_wait();
   load_mask_words(mask, b, nk, nchunks, saw);
   tc_fence_before();
   __syncthreads();
@@ -631,9 +635,9 @@ static int launch_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t l
   auto kern = xattn_bwd_tc_kernel<D>;
   MMGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)heads, (unsigned)batch);
-  kern<<<grid, 128, smem, stream>>>(mq, mdo, mk, mv, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, stats,
-                                    mask, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv,
-                                    (int)seq, (int)nk, nkp, (int)heads, tmem_cols, alias_dq);
+  MMGL_CUDA(launch_pdl(kern, grid, dim3(128), smem, stream, mq, mdo, mk, mv, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o,
+                       lddo, stats, mask, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, (int)seq,
+                       (int)nk, nkp, (int)heads, tmem_cols, alias_dq));
   return check_launch("mmgl_xattn_bwd");
 }
 

@@ -275,11 +275,13 @@ class MPTDecoder(nn.Module):
         if neighbor_embeds is not None and neighbor_embeds.dtype != BF16:
             neighbor_embeds = neighbor_embeds.to(BF16)
         for idx, layer in enumerate(self.layers):
-            h = layer(h, attention_mask=allowed)[0]
+            with ops.nvtx_range(f"lm_layer_{idx}"):
+                h = layer(h, attention_mask=allowed)[0]
             if self.cross_attention and neighbor_embeds is not None and (idx + 1) % self.neighbor_layer_wise == 0:
                 k = (idx + 1) // self.neighbor_layer_wise - 1
-                h = self.neighbor_layers[k](h, neighbor_embeds=neighbor_embeds,
-                                            neighbor_attention_mask=neighbor_attention_mask)[0]
+                with ops.nvtx_range(f"gated_xattn_layer_{k}"):
+                    h = self.neighbor_layers[k](h, neighbor_embeds=neighbor_embeds,
+                                                neighbor_attention_mask=neighbor_attention_mask)[0]
         if self.final_layer_norm is not None:
             ln = self.final_layer_norm
             h = ops.layer_norm(h, ln.weight, ln.bias, ln.eps)
@@ -600,20 +602,23 @@ class CrossAttentionModel(nn.Module, _NeighborEncoderMixin):
         if self.neighbor_mode == "raw" or self.context == "section_only":
             bank = mask = None                                                                     # :1068-1071
         elif self.neighbor_mode == "cross_attention" and self.context == "text_only":
-            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None,
-                                         plan=neighbor_plan)
+            with ops.nvtx_range("neighbor_bank"):
+                bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids, None,
+                                             plan=neighbor_plan)
         elif self.neighbor_mode == "cross_attention" and self.context in ("section_all", "all"):
-            bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids,
-                                         text_locations, neighbor_images, neighbor_images_pos_ids, image_locations,
-                                         lpe=lpe if self.position_type == "laplacian" else None, plan=neighbor_plan)
+            with ops.nvtx_range("neighbor_bank"):
+                bank, mask = self.build_bank(neighbor_input_ids, neighbor_attention_mask, neighbor_pos_ids,
+                                             text_locations, neighbor_images, neighbor_images_pos_ids, image_locations,
+                                             lpe=lpe if self.position_type == "laplacian" else None, plan=neighbor_plan)
             if self.position_type == "gnn" and graph is not None:                                  # D9 extension
                 b, nk, h = bank.shape
                 flat = bank.reshape(b, nk // self.n_text_tokens, self.n_text_tokens * h)
                 bank = (flat + self.gnn(flat, graph)).reshape(b, nk, h)
         else:
             raise ValueError(f"Neighbor mode: {self.neighbor_mode} and context: {self.context} are not supported.")
-        return self.lm(input_ids=input_ids, attention_mask=attention_mask, labels=labels, neighbor_embeds=bank,
-                       neighbor_attention_mask=mask)
+        with ops.nvtx_range("lm_forward_and_loss"):
+            return self.lm(input_ids=input_ids, attention_mask=attention_mask, labels=labels, neighbor_embeds=bank,
+                           neighbor_attention_mask=mask)
 
 
 def prepare_for_training(model: nn.Module, device="cuda") -> nn.Module:

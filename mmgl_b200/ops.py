@@ -13,6 +13,8 @@ There is no CPU or eager fallback: every function raises if the tensors are not 
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import weakref
 from typing import Optional
 
@@ -86,6 +88,23 @@ def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 _seed_counter = [0]
 _MASK64 = (1 << 64) - 1
+
+
+_NVTX = os.environ.get("MMGL_NVTX", "0") not in ("", "0")
+
+
+@contextlib.contextmanager
+def nvtx_range(name: str):
+    """NVTX range around a phase of the step (neighbor encoders, bank, LM layers, loss) when MMGL_NVTX=1, so that ncu
+    (--nvtx --nvtx-include) and Nsight timelines can be cut by phase; a no-op otherwise (no push / pop on the hot path)."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 def next_dropout_seed() -> int:
