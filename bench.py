@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
+    ap.add_argument("--grad-sync", choices=["flat", "ddp"], default="flat",
+                    help="N > 1: 'flat' = mmgl_b200.train.FlatGradSync (one all-reduce after backward), 'ddp' = torch DDP buckets")
     ap.add_argument("--timeline", default="",
                     help="run 3 steps under torch.profiler (CUPTI kernel timeline) and write a busy / idle-gap summary to this file")
     ap.add_argument("--profile-step", action="store_true",
@@ -368,7 +370,11 @@ def run_ours(a, w):
     modules.prepare_for_training(model, dev)
     model.train()
     net = model
-    if world > 1:
+    gsync = None
+    if world > 1 and a.grad_sync == "flat":
+        from mmgl_b200.train import FlatGradSync
+        gsync = FlatGradSync(model)      # one all-reduce of the flat fp32 gradient buffer after backward (see its docstring)
+    elif world > 1:
         # buckets sized so that each gated layer's 201 MB of fp32 gradients travels as one or two NCCL all-reduces (the
         # default 25 MB buckets make 35 small ones); MMGL_DDP_BUCKET_MB / MMGL_DDP_BF16 are tuning knobs
         bucket_mb = int(os.environ.get("MMGL_DDP_BUCKET_MB", "128"))
@@ -395,6 +401,8 @@ def run_ours(a, w):
     def step_resident(i):
         out = net(**resident[i % nb])
         out.loss.backward()
+        if gsync is not None:
+            gsync.all_reduce()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return out.loss
@@ -430,6 +438,8 @@ def run_ours(a, w):
             state["next"] = prefetch(i + 1)
         out = net(**batch)
         out.loss.backward()
+        if gsync is not None:
+            gsync.all_reduce()
         opt.step()
         opt.zero_grad(set_to_none=True)
         loss_host[i % 2].copy_(out.loss.detach(), non_blocking=True)
@@ -565,7 +575,8 @@ def run_ours(a, w):
         "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_res, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a, w), "per_gpu_batch": a.batch, "global_batch": sections,
-                   "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "AdamW(fused) on fp32 master weights",
+                   "parallelism": f"dp{world}", "grad_sync": (a.grad_sync if world > 1 else None),
+                   "grad_sync_copied_params": (getattr(gsync, "last_copied", None) if gsync is not None else None), "dropout": 0.1, "optimizer": "AdamW(fused) on fp32 master weights",
                    "l2": f"per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; {nb} seeded batches cycled",
                    "packing": "off (control): padded tokens and padding neighbors are encoded like the reference does" if a.no_packing
                    else "text encoder runs on real tokens of valid neighbors only (f2)",

@@ -165,7 +165,14 @@ def _new(rows, cols, like, dtype=BF16):
 
 def _wgrad(dy2, x2, param, *, gate=None, alpha=1.0):
     """dW[N_out, K_in] = alpha * tanh?(gate) * dy^T x, in the parameter's dtype (fp32 master or bf16)."""
-    out = torch.empty(param.shape, dtype=param.dtype if param.dtype in (BF16, F32) else F32, device=dy2.device)
+    flat = getattr(param, "_mmgl_grad_flat", None)
+    if flat is not None and not param._mmgl_grad_slot_used and param.dtype == F32:
+        # train.FlatGradSync: the gradient is written straight into the parameter's slot of the flat all-reduce buffer
+        # (a fresh view object, so autograd adopts it as param.grad); a second use in the same backward gets its own tensor
+        out = flat[0][flat[1]:flat[1] + param.numel()].view(param.shape)
+        param._mmgl_grad_slot_used = True
+    else:
+        out = torch.empty(param.shape, dtype=param.dtype if param.dtype in (BF16, F32) else F32, device=dy2.device)
     K.gemm(dy2, x2, out, a_t=True, b_t=True, gate=gate, alpha=alpha)
     return out
 

@@ -55,6 +55,58 @@ def _worker(rank, world, port, accum, out):
     dist.destroy_process_group()
 
 
+class Toy32(Toy):
+    """fp32 twin: its two weight matrices take FlatGradSync's flat-buffer path, its biases the flattened-small path"""
+
+    def __init__(self):
+        super().__init__()
+        self.float()
+
+
+def _worker_flat(rank, world, port, accum, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    net = Toy32()
+    if rank == 1:                       # FlatGradSync broadcasts rank 0's parameters: start rank 1 somewhere else
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(1.0)
+    sync = train.FlatGradSync(net)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.1)
+    f32 = lambda b: {k: v.float() for k, v in b.items()}
+    loss = train.optimizer_step(net, opt, [f32(_batch(rank, s)) for s in range(accum)], lambda m, b: m(**b),
+                                accum_steps=accum, grad_clip=10.0, grad_sync=sync)
+    if rank == 0:
+        torch.save({"state": {k: v.clone() for k, v in net.state_dict().items()}, "loss": loss,
+                    "views": all(p.grad is None or p.grad.data_ptr() == sync.slot(p).data_ptr() for p in sync.big)}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_two_rank_flat_grad_sync_matches_single_process(tmp_path, accum):
+    """FlatGradSync (one all-reduce of a flat gradient buffer after backward, mmgl_b200/train.py) gives the same update as
+    one process running the union of both ranks' micro-batches, from rank 0's initial parameters."""
+    world, port = 2, _free_port()
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_worker_flat, args=(world, port, accum, out), nprocs=world, join=True)
+    got = torch.load(out)
+    ref = Toy32()
+    opt = torch.optim.SGD([p for p in ref.parameters() if p.requires_grad], lr=0.1)
+    total = 0.0
+    for s in range(accum):
+        for r in range(world):
+            b = {k: v.float() for k, v in _batch(r, s).items()}
+            loss = ref(**b) / (accum * world)
+            loss.backward()
+            total += float(loss) if r == 0 else 0.0
+    torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.requires_grad], 10.0)
+    opt.step()
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(got["state"][k], v, rtol=1e-5, atol=1e-6), k
+
+
 @pytest.mark.parametrize("accum", [1, 3])
 def test_two_rank_ddp_matches_single_process(tmp_path, accum):
     world, port = 2, _free_port()

@@ -39,19 +39,19 @@ def time_it(fn, iters=20, warmup=3):
 
 def bench_gemm():
     shapes = [  # (M, N, K, a_t, b_t, label)
-        (5120, 2048, 2048, 0, 0, "q/out proj B=8"),
-        (5120, 6144, 2048, 0, 0, "fused qkv B=8"),
-        (5120, 8192, 2048, 0, 0, "fc1 B=8"),
-        (5120, 2048, 8192, 0, 0, "fc2 B=8"),
-        (512, 2048, 2048, 0, 0, "k/v proj (bank) B=8"),
-        (5120, 2048, 8192, 0, 1, "dgrad fc1 B=8"),
-        (5120, 2048, 6144, 0, 1, "dgrad fused qkv B=8"),
-        (8192, 2048, 5120, 1, 1, "wgrad fc1 B=8"),
-        (2048, 8192, 5120, 1, 1, "wgrad fc2 B=8"),
-        (2048, 2048, 5120, 1, 1, "wgrad q/out B=8"),
+        (10240, 2048, 2048, 0, 0, "q/out proj B=16"),
+        (10240, 6144, 2048, 0, 0, "fused qkv B=16"),
+        (10240, 8192, 2048, 0, 0, "fc1 B=16"),
+        (10240, 2048, 8192, 0, 0, "fc2 B=16"),
+        (1024, 2048, 2048, 0, 0, "k/v proj (bank) B=16"),
+        (10240, 2048, 8192, 0, 1, "dgrad fc1 B=16"),
+        (10240, 2048, 6144, 0, 1, "dgrad fused qkv B=16"),
+        (8192, 2048, 10240, 1, 1, "wgrad fc1 B=16"),
+        (2048, 8192, 10240, 1, 1, "wgrad fc2 B=16"),
+        (2048, 2048, 10240, 1, 1, "wgrad q/out B=16"),
         (8192, 8192, 8192, 0, 0, "square 8k"),
-        (5120, 50272, 2048, 0, 0, "lm_head B=8"),
-        (5120, 2048, 50272, 0, 1, "lm_head dgrad B=8"),
+        (10240, 50272, 2048, 0, 0, "lm_head B=16"),
+        (10240, 2048, 50272, 0, 1, "lm_head dgrad B=16"),
     ]
     for m, n, k, a_t, b_t, label in shapes:
         a = torch.randn((k, m) if a_t else (m, k), device="cuda").to(BF16)
