@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-table", action="store_true", help="print per-shape GEMM timings (stderr) after the run")
+    ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
+                    help="'fused' = mmgl_b200.optim.FusedAdamW (our kernel, writes the bf16 shadows too), 'torch' = torch.optim.AdamW(fused=True)")
     ap.add_argument("--grad-sync", choices=["flat", "ddp"], default="flat",
                     help="N > 1: 'flat' = mmgl_b200.train.FlatGradSync (one all-reduce after backward), 'ddp' = torch DDP buckets")
     ap.add_argument("--timeline", default="",
@@ -384,7 +386,11 @@ def run_ours(a, w):
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+    if a.optimizer == "fused":
+        from mmgl_b200.optim import FusedAdamW     # csrc/optim.cu: AdamW + bf16 shadow of the updated weights in one pass
+        opt = FusedAdamW(params, lr=1e-4, weight_decay=0.01)
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
 
     spec = spec_for(w, a.batch)
     nb = max(2, a.batches)
@@ -576,7 +582,7 @@ def run_ours(a, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a, w), "per_gpu_batch": a.batch, "global_batch": sections,
                    "parallelism": f"dp{world}", "grad_sync": (a.grad_sync if world > 1 else None),
-                   "grad_sync_copied_params": (getattr(gsync, "last_copied", None) if gsync is not None else None), "dropout": 0.1, "optimizer": "AdamW(fused) on fp32 master weights",
+                   "grad_sync_copied_params": (getattr(gsync, "last_copied", None) if gsync is not None else None), "dropout": 0.1, "optimizer": ("mmgl FusedAdamW (+ bf16 shadows)" if a.optimizer == "fused" else "torch AdamW(fused=True)") + " on fp32 master weights",
                    "l2": f"per-step working set (3.6 GB of bf16 weights + activations) >> 126 MB L2; {nb} seeded batches cycled",
                    "packing": "off (control): padded tokens and padding neighbors are encoded like the reference does" if a.no_packing
                    else "text encoder runs on real tokens of valid neighbors only (f2)",

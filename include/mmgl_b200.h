@@ -291,6 +291,18 @@ int mmgl_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int64_t 
 int mmgl_swiglu_bwd(const void* gu, int64_t ldgu, const void* dh, int64_t lddh, void* dgu, int64_t lddgu, int64_t m, int64_t f,
                     void* stream);
 
+/*
+ * mmgl_adamw_step: one AdamW update of ONE fp32 tensor of n elements, in place, with the bf16 shadow of the updated values
+ *   written in the same pass (shadow_bf16 may be NULL).  Arithmetic of torch.optim.AdamW (amsgrad = False, maximize = False):
+ *     p *= 1 - lr * weight_decay;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+ *     p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps),  g = grad * grad_scale.
+ *   `step` is the 1-based count INCLUDING this update.  Replaces optimizer.step() of the torch.optim.AdamW the reference
+ *   builds (language_modelling/run_generation.py:329-333, called at :486) and the fp32 -> bf16 weight conversion that
+ *   model.bfloat16() (:306-307) stands for.  All pointers fp32 device memory except shadow_bf16.
+ */
+int mmgl_adamw_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, void* shadow_bf16, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mmgl_rope_inplace": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i32, c_vp]),
     "mmgl_swiglu_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mmgl_swiglu_bwd": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "mmgl_adamw_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
 }
 
 
@@ -496,3 +497,18 @@ def swiglu_bwd(gu, dh, dgu):
     m, f = dh.shape
     with _Timed("swiglu_bwd", float(m * f * 10)):
         _check(lib().mmgl_swiglu_bwd(_p(gu), _ld(gu), _p(dh), _ld(dh), _p(dgu), _ld(dgu), m, f, _stream()), "mmgl_swiglu_bwd")
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """In-place AdamW update of one fp32 tensor; ``shadow`` (bf16, same shape, or None) receives the updated values."""
+    _req_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("adamw_step: param, grad, exp_avg, exp_avg_sq must be contiguous fp32 tensors of one size")
+    if shadow is not None and (shadow.dtype != torch.bfloat16 or not shadow.is_contiguous() or shadow.numel() != n):
+        raise ValueError("adamw_step: shadow must be a contiguous bf16 tensor of the parameter's size")
+    with _Timed("adamw_step", float(n * 30)):
+        _check(lib().mmgl_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(shadow), n, float(lr), float(beta1),
+                                     float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream()),
+               "mmgl_adamw_step")

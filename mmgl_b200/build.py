@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmmgl_b200.so")
-SOURCES = ["capi.cu", "gemm_sm100.cu", "xattn.cu", "xattn_sm100.cu", "sattn_sm100.cu", "sattn_bwd_sm100.cu", "rowops.cu", "llama_ops.cu"]
+SOURCES = ["capi.cu", "gemm_sm100.cu", "xattn.cu", "xattn_sm100.cu", "sattn_sm100.cu", "sattn_bwd_sm100.cu", "rowops.cu", "llama_ops.cu", "optim.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("MMGL_EXTRA_FLAGS", "").split()

@@ -57,7 +57,7 @@ def optimizer_step(net, optimizer, micro_batches: Iterable, loss_fn: Callable, a
     if grad_clip is not None and grad_clip > 0:
         torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.requires_grad], grad_clip)
     optimizer.step()
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() and not getattr(optimizer, "keeps_shadows_current", False):
         from . import ops   # optimizers that write through param.data (HF Adafactor, T5's default at run_generation.py
         ops.invalidate_weight_cache(trainable_only=True)   # :329-333) do not bump _version: drop the trainable shadows
     if scheduler is not None:
