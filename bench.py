@@ -2,18 +2,20 @@
 """bench.py -- sections/sec of MMGL's neighbor-fusion training step on N B200s (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference|eager]
-                    [--workload cfg2|cfg3|cfg4|tiny] [--no-packing]
+                    [--workload cfg2|cfg3|cfg4|cfg5|tiny] [--no-packing] [--no-plan] [--optimizer fused|torch]
+                    [--grad-sync flat|ddp] [--gemm-table] [--timeline FILE] [--profile-step]
     (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 A "step" is one optimisation step of CrossAttentionModel on one synthetic WikiWeb2M-shaped micro-batch per GPU:
 frozen RoBERTa/CLIP encoders -> neighbor projections -> bank packing -> OPT-1.3B with 4 gated cross-attention
-layers -> shifted CE -> backward -> (DDP all-reduce) -> AdamW on the trainable parameters.  Dropout is ON (p=0.1,
-train mode) exactly as in the reference's loop.  Workload = BASELINE.json configs[1] (cfg2).
+layers -> shifted CE -> backward -> (N > 1: gradient all-reduce, train.FlatGradSync or DDP) -> AdamW on the trainable
+parameters (optim.FusedAdamW, or torch's).  Dropout is ON (p=0.1, train mode) exactly as in the reference's loop.
+Workload = BASELINE.json configs[1] (cfg2).
 
 Output: ONE JSON line (rank 0).  ``value`` = sections/s with the batch already resident in HBM; ``e2e`` = the same
 through the public nn.Module call with pinned HOST batches (H2D inside the timed region, loss read back every step);
 ``roofline`` = achieved TFLOP/s of the dominant kernel (the tcgen05 GEMM) from per-launch CUDA events in an
-instrumented replica of the timed region; ``cpu_baseline`` = the oracle port of the same step on the host cores.
+instrumented replica of the timed region; ``cpu_baseline`` = the reference's own modules (oracle/_ref) on the host cores.
 
 ``--impl reference`` times the REAL reference modules (oracle/_ref: /root/reference/model/*.py byte-compiled by
 oracle/build_ref.py) on the host cores; ``--impl eager`` runs the same modules in PyTorch eager on the B200 (the honest
