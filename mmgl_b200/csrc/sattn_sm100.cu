@@ -11,15 +11,15 @@
 // O += P_j V_j in TMEM.  One extra QK^T per block buys the absence of any accumulator correction.
 //
 //   forward : CTA = TWO 128-query tiles of one (head, sample) in ping-pong: 16 softmax warps (8 per tile, two threads per
-//             score row, each thread = one TMEM lane and half of the columns), two MMA-issuing warps (one per tile) and one
-//             TMA warp.  The K / V blocks stream once through a 3-stage ring for both tiles.  Pass 1 double-buffers S in TMEM;
-//             pass 2 works on 64-key half blocks with three S buffers (two at head_dim 128) and two P slabs per tile, so the
-//             tensor core runs ahead of the exponentials.  Only blocks at or below the diagonal are visited when causal (tiles
-//             are paired heavy-with-next-heavy, heavy pairs first).  A packed variable-length batch (cu_seqlens) is supported.
-//   backward: dQ kernel   item = (query tile i): loops key blocks j, dQ_i += dS_ij K_j            (accumulates in TMEM)
-//             dK/dV kernel item = (key block j): loops query tiles i, dV_j += P_ij^T dO_i, dK_j += dS_ij^T Q_i (TMEM)
-//             both recompute S and dP = dO V^T from Q, K, V, dO and the saved row statistics (m, 1/l); 512 threads = four per
-//             score row; persistent CTAs walk the items, heavy first.
+//             score row, each thread = one TMEM lane and half of the columns), two MMA-issuing warps (one per tile; the whole
+//             warp walks the schedule, an elected lane issues from uniform registers) and one TMA warp.  The K / V blocks
+//             stream once through a 4-stage ring (2 at head_dim 128) for both tiles.  Pass 1 double-buffers S in TMEM; pass 2
+//             works on 64-key half blocks with three S buffers per tile (two at head_dim 128); P is written back (bf16 pairs,
+//             tcgen05.st) over the head of the score columns it came from and P V reads it from tensor memory (TS form), so
+//             the tensor core runs ahead of the exponentials and P never touches shared memory.  Only blocks at or below the
+//             diagonal are visited when causal (tiles are paired heavy-with-next-heavy, heavy pairs first).  A packed
+//             variable-length batch (cu_seqlens) is supported.
+//   backward: csrc/sattn_bwd_sm100.cu (single pass).
 // Masks are bit masks: one 32-bit word per 32 keys (attend = exists AND not padding), built once per CTA; the causal
 // limit of the diagonal block is a per-thread shift.  Interior blocks (all 128 keys attended, not diagonal, no bias)
 // take a 3-instruction-per-score path.
@@ -88,18 +88,6 @@ __device__ __forceinline__ float exp_chunk(uint32_t (&rc)[32], uint32_t m, bool 
   }
   return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
-// 32 fp32 values of one row -> bf16, into the 128B-swizzled [128][128] tile (2 slabs of 64 columns) at chunk c
-__device__ __forceinline__ void store_chunk_bf16(uint32_t tile_base, int tid, int c, const uint32_t (&rc)[32]) {
-  const uint32_t slab = tile_base + (c >> 1) * 16384;
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-    sts128(swz(slab, tid, (c & 1) * 4 + g),
-           pack_bf16(__uint_as_float(rc[8 * g]), __uint_as_float(rc[8 * g + 1])),
-           pack_bf16(__uint_as_float(rc[8 * g + 2]), __uint_as_float(rc[8 * g + 3])),
-           pack_bf16(__uint_as_float(rc[8 * g + 4]), __uint_as_float(rc[8 * g + 5])),
-           pack_bf16(__uint_as_float(rc[8 * g + 6]), __uint_as_float(rc[8 * g + 7])));
-}
-
 // ------------------------------------------------------------------------------------------------ forward
 // barrier indices of the forward kernel
 template <int NS> struct FwdBars {
@@ -110,8 +98,8 @@ template <int NS> struct FwdBars {
   static constexpr int vfree = 2 + 3 * NS;   // [NS]
   static constexpr int sfull = 2 + 4 * NS;   // [2 buffers][2 tiles]  S_t = Q_t K_j^T complete in TMEM buffer (index 2 * buf + t)
   static constexpr int sfree = 6 + 4 * NS;   // [2 buffers][2 tiles]  pass 1: tile t's 128 threads have read that S buffer
-  static constexpr int pfull = 10 + 4 * NS;  // [2 buffers][2 tiles]  pass 2: tile t's P half-block is in shared memory (128 arrivals)
-  static constexpr int pfree = 14 + 4 * NS;  // [2 buffers][2 tiles]  P V of that half-block complete: P buffer reusable, O_t updated
+  static constexpr int pfull = 10 + 4 * NS;  // [2 parities][2 tiles]  pass 2: tile t's P half-block is in tensor memory (256 arrivals)
+  static constexpr int pfree = 14 + 4 * NS;  // [2 parities][2 tiles]  P V of that half-block complete: O_t updated
   static constexpr int s2full = 18 + 4 * NS; // [3 buffers][2 tiles]  pass 2: S of a half block complete in TMEM buffer (index 2 * buf + t)
   static constexpr int count = 24 + 4 * NS;
 };
@@ -257,8 +245,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       for (int tt = 0; tt < 2; ++tt)
         for (int jj = max(nblk[tt] - 2, 0); jj < nblk[tt]; ++jj)
           mbar_wait(&bars[B::sfree + 2 * (jj & 1) + tt], (jj >> 1) & 1);
-      // Pass 2 works on HALF blocks (64 keys) with NSB S buffers (TMEM) and two P slabs (shared memory) per tile: half block x
-      // = half (x & 1) of key block x >> 1 lives in S buffer x % NSB and P slab x & 1.  S(jj + NSB) is issued right after
+      // Pass 2 works on HALF blocks (64 keys) with NSB S buffers per tile in TMEM: half block x = half (x & 1) of key block
+      // x >> 1 lives in S buffer x % NSB, and so does its P once the softmax warps have written it back.  S(jj + NSB) is issued right after
       // P V(jj), so the softmax warps always find the next scores ready and the hand-off latency is off the critical path.
       constexpr int NSB = (D == 64) ? 3 : 2;                 // S buffers per tile in pass 2 (TMEM: 2 * NSB * 64 + 2 * D <= 512)
       const uint32_t cS2 = tmem_base + t * (NSB * 64);       // + v * 64
@@ -359,7 +347,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const bool none = !(mx > -FLT_MAX);
       const float c1 = none ? 0.f : scale * kL2E, mxc = none ? 0.f : mx * kL2E, bsc = none ? 0.f : kL2E;
       // ---------------- pass 2: P = exp(x - max), O += P V, on half blocks (64 keys = chunks 2u, 2u+1 of key block jj >> 1) with
-      // NSB S buffers in TMEM (3 at head_dim 64) and two P slabs in shared memory: while this tile's warps exponentiate half
+      // NSB S buffers in TMEM (3 at head_dim 64), P written back into the buffer it came from: while this tile's warps exponentiate half
       // block jj, the tensor core already holds S(jj + 1) (and S(jj + 2)) and is free to run P V(jj - 1) and S(jj + NSB), so the
       // softmax -> MMA -> softmax hand-off latency stays off the critical path.  This thread owns chunk 2u + hf.
       float sum = 0.f;
