@@ -5,8 +5,8 @@ same constructor arguments, same update (amsgrad / maximize / foreach / capturab
 ``state_dict`` layout (``step``, ``exp_avg``, ``exp_avg_sq`` per parameter), so optimizer checkpoints are interchangeable.
 Each fp32 CUDA parameter is updated by ``mmgl_adamw_step`` (csrc/optim.cu): one read of (p, g, m, v), one write of
 (p, m, v, bf16 p).  The bf16 copy is registered with ``ops.w16``'s cache, so the next forward finds its operand ready and
-the per-parameter fp32 -> bf16 conversion kernels disappear from the step.  Parameters that are not fp32 CUDA tensors
-(none on the benchmarked path) are updated with the same formula in plain torch ops.
+the per-parameter fp32 -> bf16 conversion kernels disappear from the step.  Parameters that are not contiguous fp32 CUDA
+tensors raise (no eager fallback).
 """
 from __future__ import annotations
 
@@ -64,12 +64,10 @@ class FusedAdamW(torch.optim.Optimizer):
                     if shadow is not None:
                         ops.register_shadow(p, shadow)
                 else:
-                    gg = g.to(torch.float32) * grad_scale
-                    p.mul_(1.0 - lr * wd)
-                    st["exp_avg"].mul_(b1).add_(gg.to(st["exp_avg"].dtype), alpha=1.0 - b1)
-                    st["exp_avg_sq"].mul_(b2).addcmul_(gg.to(st["exp_avg_sq"].dtype), gg.to(st["exp_avg_sq"].dtype), value=1.0 - b2)
-                    denom = (st["exp_avg_sq"].sqrt() / (1.0 - b2 ** t) ** 0.5).add_(eps)
-                    p.addcdiv_(st["exp_avg"], denom, value=-lr / (1.0 - b1 ** t))
+                    raise NotImplementedError(
+                        "FusedAdamW updates contiguous fp32 CUDA parameters with fp32 gradients (the master weights "
+                        f"prepare_for_training() leaves trainable); got {p.dtype} on {p.device} with a {g.dtype} gradient -- "
+                        "there is no eager fallback, use torch.optim.AdamW for such parameters")
         return loss
 
     def state_dict(self):

@@ -269,3 +269,17 @@ def test_host_plan_equals_the_device_side_bookkeeping():
             assert torch.equal(tok, p.tok_idx) and torch.equal(cu, p.cu) and (total, max_len) == (p.total, p.max_len)
     moved = p.to("cpu").pin_memory() if torch.cuda.is_available() else p.to("cpu")
     assert moved.total == p.total and torch.equal(moved.text_idx, p.text_idx)
+
+
+def test_fused_adamw_has_no_cpu_fallback():
+    """optim.FusedAdamW is a CUDA-kernel optimizer: a CPU parameter must raise, not run an eager update."""
+    import pytest
+    import torch
+    from mmgl_b200.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.randn(4))
+    opt = FusedAdamW([p], lr=1e-3)
+    p.grad = torch.randn(4)
+    with pytest.raises(NotImplementedError):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        FusedAdamW([p], amsgrad=True)
