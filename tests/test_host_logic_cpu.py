@@ -283,3 +283,24 @@ def test_fused_adamw_has_no_cpu_fallback():
         opt.step()
     with pytest.raises(NotImplementedError):
         FusedAdamW([p], amsgrad=True)
+
+
+def test_optimizer_step_drops_trainable_weight_shadows():
+    """torch.optim.AdamW(fused=True) updates parameters without bumping ``_version``; the bf16 shadow cache (ops.w16) must
+    not survive an optimizer step of any optimizer (global post-step hook in ops.py), while frozen shadows stay cached."""
+    import torch
+    from mmgl_b200 import ops
+    w = torch.nn.Parameter(torch.randn(8, 4))
+    frozen = torch.nn.Parameter(torch.randn(8, 4), requires_grad=False)
+    s0, f0 = ops.w16(w), ops.w16(frozen)
+    assert ops.w16(w) is s0 and ops.w16(frozen) is f0              # cached
+    opt = torch.optim.AdamW([w], lr=0.1, fused=True)
+    v0 = w._version
+    w.grad = torch.ones_like(w)
+    opt.step()
+    s1 = ops.w16(w)
+    assert s1 is not s0, "stale shadow served after optimizer.step()"
+    assert torch.equal(s1, w.detach().to(torch.bfloat16))
+    assert ops.w16(frozen) is f0                                   # frozen operands (fused Wq|Wk|Wv rows etc.) survive
+    if w._version == v0:                                            # the reason the hook exists (torch 2.11: true)
+        assert not torch.equal(s0, s1)
